@@ -1,0 +1,125 @@
+"""Generate tests/golden/*.npz.  Run in the build container (needs /root/reference); the fixtures are committed.
+
+Two kinds of fixture:
+  ref_<name>.npz      outputs of the UNMODIFIED reference (oracle/run_reference.py) on seeded synthetic catalogues
+                      (measure_ia_b200.synthetic.uniform_box).  Stored: the config (json), a sha256 of the inputs, and
+                      every dataset the reference wrote to its HDF5 file.
+  hdf5_<file>.npz     the reference's own golden HDF5 outputs (tests/data/processed/TNG300/*.hdf5) decoded with
+                      measure_ia_b200.h5lite; they pin the analytic-RR / xi / w / multipole / jackknife formulas.
+
+Usage:  python oracle/make_golden.py [name ...]
+"""
+import hashlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REPO = os.path.dirname(_HERE)
+sys.path.insert(0, _REPO)
+sys.path.insert(0, _HERE)
+
+from measure_ia_b200.synthetic import uniform_box  # noqa: E402
+import run_reference  # noqa: E402
+
+GOLDEN = os.path.join(_REPO, "tests", "golden")
+
+# name -> (catalogue kwargs, measurement kwargs)
+CONFIGS = {
+	"w_auto_jk27": (dict(n=3000, boxsize=205.0, seed=1), dict(kind="w", num_jk=27, num_bins_r=10, num_bins_pi=8)),
+	"m_auto_jk27": (dict(n=3000, boxsize=205.0, seed=1), dict(kind="multipoles", num_jk=27, num_bins_r=10, num_bins_pi=8)),
+	"w_auto_nojk_default_bins": (dict(n=3000, boxsize=205.0, seed=2), dict(kind="w", num_jk=0)),
+	"m_auto_nojk_default_bins": (dict(n=3000, boxsize=205.0, seed=2), dict(kind="multipoles", num_jk=0)),
+	"w_cross_weights_los0_jk8": (dict(n=2000, n_shape=1500, boxsize=205.0, seed=3, weights=True, los=0),
+								 dict(kind="w", num_jk=8, num_bins_r=10, num_bins_pi=8)),
+	"m_cross_weights_los1_jk8": (dict(n=2000, n_shape=1500, boxsize=205.0, seed=4, weights=True, los=1),
+								 dict(kind="multipoles", num_jk=8, num_bins_r=10, num_bins_pi=8)),
+	"w_pimax30_jk8": (dict(n=3000, boxsize=205.0, seed=5), dict(kind="w", num_jk=8, num_bins_r=6, num_bins_pi=6, pi_max=30.0)),
+	"w_nonperiodic": (dict(n=2500, boxsize=100.0, seed=6), dict(kind="w", num_jk=8, num_bins_r=5, num_bins_pi=4,
+																 periodicity=False, separation_limits=(0.5, 15.0))),
+	"m_nonperiodic": (dict(n=2500, boxsize=100.0, seed=6), dict(kind="multipoles", num_jk=8, num_bins_r=5, num_bins_pi=4,
+																 periodicity=False, separation_limits=(0.5, 15.0))),
+	"w_ellipticity_def": (dict(n=2000, boxsize=75.0, seed=7), dict(kind="w", num_jk=27, num_bins_r=6, num_bins_pi=10,
+																	ellipticity="ellipticity", separation_limits=(0.2, 10.0))),
+	"w_masked": (dict(n=3000, boxsize=205.0, seed=8, weights=True), dict(kind="w", num_jk=8, num_bins_r=10, num_bins_pi=8,
+																		 mask_seed=11)),
+	"m_masked": (dict(n=3000, boxsize=205.0, seed=8, weights=True), dict(kind="multipoles", num_jk=8, num_bins_r=10,
+																		 num_bins_pi=8, mask_seed=11)),
+	"w_small_box": (dict(n=400, boxsize=30.0, seed=9), dict(kind="w", num_jk=8, num_bins_r=4, num_bins_pi=4,
+															 separation_limits=(0.5, 12.0), variant="brute")),
+	"m_small_box": (dict(n=400, boxsize=30.0, seed=9), dict(kind="multipoles", num_jk=8, num_bins_r=4, num_bins_pi=4,
+															 separation_limits=(0.5, 12.0), variant="brute")),
+	"w_auto_jk27_30k": (dict(n=30000, boxsize=205.0, seed=1), dict(kind="w", num_jk=27, num_bins_r=10, num_bins_pi=8)),
+	"m_auto_jk27_30k": (dict(n=30000, boxsize=205.0, seed=1), dict(kind="multipoles", num_jk=27, num_bins_r=10, num_bins_pi=8)),
+}
+
+
+def make_masks(data, mask_seed):
+	"""Boolean masks in the form of reference tests/test_masks.py:15-18 (same key set as the data dict)."""
+	rng = np.random.default_rng(mask_seed)
+	n_p, n_s = len(data["Position"]), len(data["Position_shape_sample"])
+	same = data["Position"] is data["Position_shape_sample"]
+	mp = rng.random(n_p) < 0.7
+	ms = mp if same else rng.random(n_s) < 0.6
+	return {"Position": mp, "Position_shape_sample": ms, "Axis_Direction": ms, "q": ms, "weight": mp,
+			"weight_shape_sample": ms}
+
+
+def build_inputs(cat_kw, meas_kw):
+	cat_kw = dict(cat_kw)
+	data = uniform_box(cat_kw.pop("n"), cat_kw.pop("boxsize"), **cat_kw)
+	meas_kw = dict(meas_kw)
+	masks = None
+	if "mask_seed" in meas_kw:
+		masks = make_masks(data, meas_kw.pop("mask_seed"))
+	return data, masks, meas_kw
+
+
+def input_digest(data, masks):
+	h = hashlib.sha256()
+	for k in sorted(data):
+		h.update(k.encode())
+		h.update(np.ascontiguousarray(data[k]).tobytes())
+	if masks:
+		for k in sorted(masks):
+			h.update(np.ascontiguousarray(masks[k]).tobytes())
+	return h.hexdigest()
+
+
+def generate(name):
+	cat_kw, meas_kw = CONFIGS[name]
+	data, masks, kw = build_inputs(cat_kw, meas_kw)
+	kind = kw.pop("kind")
+	t = time.time()
+	out = run_reference.run_reference(data, kind, boxsize=cat_kw["boxsize"], masks=masks, **kw)
+	meta = dict(name=name, catalogue=cat_kw, measurement=meas_kw, digest=input_digest(data, masks),
+				numpy=np.__version__, seconds=round(time.time() - t, 2))
+	path = os.path.join(GOLDEN, f"ref_{name}.npz")
+	np.savez_compressed(path, __meta__=np.array(json.dumps(meta)), **{k.replace("/", "|"): v for k, v in out.items()})
+	print(f"{name}: {len(out)} datasets, {meta['seconds']} s -> {os.path.relpath(path, _REPO)} "
+		  f"({os.path.getsize(path) // 1024} KiB)")
+
+
+def decode_reference_hdf5():
+	from measure_ia_b200 import h5lite
+	src = "/root/reference/tests/data/processed/TNG300"
+	for fn in ("mock_IA_TNG300.hdf5", "mock_IA_TNG300_large.hdf5"):
+		f = h5lite.File(os.path.join(src, fn), "r")
+		flat = run_reference._flatten(f)
+		f.close()
+		path = os.path.join(GOLDEN, "hdf5_" + fn.replace(".hdf5", ".npz"))
+		np.savez_compressed(path, **{k.replace("/", "|"): v for k, v in flat.items()})
+		print(f"{fn}: {len(flat)} datasets -> {os.path.relpath(path, _REPO)} ({os.path.getsize(path) // 1024} KiB)")
+
+
+if __name__ == "__main__":
+	os.makedirs(GOLDEN, exist_ok=True)
+	names = sys.argv[1:] or list(CONFIGS) + ["hdf5"]
+	for n in names:
+		if n == "hdf5":
+			decode_reference_hdf5()
+		else:
+			generate(n)
