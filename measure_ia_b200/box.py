@@ -1,0 +1,586 @@
+"""Host-side mirror of the reference's periodic-box API on top of the B200 pair-count operator.
+
+``MeasureIABox`` keeps the constructor, ``measure_xi_w`` / ``measure_xi_multipoles`` signatures, the data-dict input,
+the error behaviour and the HDF5 output layout of the reference (``src/measureia/measure_IA.py:10-262``; layout in
+DESIGN.md).  What changes underneath:
+
+* the twelve copy-pasted pair-loop variants ({brute, tree, multiprocessing} x {jackknife, none} x {(r_p, Pi),
+  (r, mu_r)}: ``measure_w_box.py``, ``measure_w_box_jk.py``, ``measure_m_box.py``, ``measure_m_box_jk.py``) collapse
+  into ONE call of ``torch.ops.measure_ia_b200.paircount`` (CUDA, sm_100a; no CPU fallback);
+* host preparation is vectorised (jackknife labels, responsivities) with the reference's boundary semantics;
+* ``num_nodes``, ``temp_file_path`` (beyond its None / False error contract) and ``chunk_size`` are accepted and
+  ignored: parallelism is one process per GPU via ``torch.distributed`` (shape-sample shards, one reduction).
+"""
+from __future__ import annotations
+
+import math
+import os
+import time
+
+import numpy as np
+
+from . import calib
+from .io import create_group_hdf5, open_file, write_dataset_hdf5
+from .sim_info import SimInfo
+
+
+def integer_cube_root(num_jk):
+	"""``sympy.integer_nthroot(num_jk, 3)`` without sympy (measure_IA.py:95-101)."""
+	root = round(num_jk ** (1.0 / 3.0))
+	for r in (root - 1, root, root + 1):
+		if r >= 0 and r ** 3 == num_jk:
+			return r, True
+	return int(num_jk ** (1.0 / 3.0)), False
+
+
+class MeasureIABase(SimInfo):
+	"""Binning set-up, helpers and host post-processing (reference ``measure_IA_base.py:63-668``)."""
+
+	verbose = False
+
+	def __init__(self, data, output_file_name, simulation=None, snapshot=None, separation_limits=[0.1, 20.0],
+				 num_bins_r=8, num_bins_pi=20, pi_max=None, boxsize=None, periodicity=True):
+		SimInfo.__init__(self, simulation, snapshot, boxsize)
+		self.data = data
+		self.output_file_name = output_file_name
+		self.periodicity = periodicity
+		try:
+			self.Num_position = len(data["Position"])
+			self.Num_shape = len(data["Position_shape_sample"])
+		except Exception:  # noqa: BLE001  (reference: bare except, measure_IA_base.py:135-145)
+			try:
+				self.Num_position = len(data["RA"])
+				self.Num_shape = len(data["RA_shape_sample"])
+			except Exception:  # noqa: BLE001
+				self.Num_position = 0
+				self.Num_shape = 0
+				if self.verbose:
+					print("Warning: no Postion or Position_shape_sample given.")
+		if self.Num_position > 0:  # default unit weights are injected into the caller's dict (:146-154)
+			if "weight" not in self.data:
+				self.data["weight"] = np.ones(self.Num_position)
+			if "weight_shape_sample" not in self.data:
+				self.data["weight_shape_sample"] = np.ones(self.Num_shape)
+		self.r_min = separation_limits[0]
+		self.r_max = separation_limits[1]
+		self.num_bins_r = num_bins_r
+		self.num_bins_pi = num_bins_pi
+		self.r_bins = np.logspace(np.log10(self.r_min), np.log10(self.r_max), self.num_bins_r + 1)
+		if pi_max is None:
+			if self.L_0p5 is None:
+				raise ValueError(
+					"Both pi_max and boxsize are None. Provide input on one of them to determine the integration limit pi_max.")
+			pi_max = self.L_0p5
+		self.pi_bins = np.linspace(-pi_max, pi_max, self.num_bins_pi + 1)
+		self.mu_r_bins = np.linspace(-1, 1, self.num_bins_pi + 1)
+		self._thresholds = {}
+
+	# ---- small helpers kept for API compatibility -------------------------------------------------------------------
+	@staticmethod
+	def calculate_dot_product_arrays(a1, a2):
+		dot = np.zeros(np.shape(a1)[0])
+		for i in range(np.shape(a1)[1]):
+			dot += a1[:, i] * a2[:, i]
+		return dot
+
+	@staticmethod
+	def get_ellipticity(e, phi):
+		return e * np.cos(2 * phi), e * np.sin(2 * phi)
+
+	@staticmethod
+	def get_random_pairs(rp_max, rp_min, pi_max, pi_min, L3, corrtype, Num_position, Num_shape):
+		"""Analytic RR in an (r_p, Pi) bin (measure_IA_base.py:229-272)."""
+		if corrtype == "auto":
+			return ((Num_position - 1.0) * Num_shape / 2.0 * np.pi * (rp_max ** 2 - rp_min ** 2)
+					* abs(pi_max - pi_min) / L3)
+		if corrtype == "cross":
+			return Num_position * Num_shape * np.pi * (rp_max ** 2 - rp_min ** 2) * abs(pi_max - pi_min) / L3
+		raise ValueError("Unknown input for corrtype, choose from auto or cross.")
+
+	@staticmethod
+	def get_volume_spherical_cap(mur, r):
+		return np.pi / 3.0 * r ** 3 * (2 + mur) * (1 - mur) ** 2
+
+	def get_random_pairs_r_mur(self, r_max, r_min, mur_max, mur_min, L3, corrtype, Num_position, Num_shape):
+		"""Analytic RR in an (r, mu_r) bin (measure_IA_base.py:293-351); note the (Np - 1) prefactor in both cases."""
+		cap = self.get_volume_spherical_cap
+		vol = cap(mur_min, r_max) - cap(mur_max, r_max) - (cap(mur_min, r_min) - cap(mur_max, r_min))
+		if corrtype == "auto":
+			return abs((Num_position - 1.0) / 2.0 * Num_shape * vol / L3)
+		if corrtype == "cross":
+			return abs((Num_position - 1.0) * Num_shape * vol / L3)
+		raise ValueError("Unknown input for corrtype, choose from auto or cross.")
+
+	# ---- vectorised grids of the analytic randoms -----------------------------------------------------------------------
+	def _rr_grid_rppi(self, volume, n_pos, n_shape):
+		rb, pb = self.r_bins, self.pi_bins
+		ring = (rb[1:] ** 2 - rb[:-1] ** 2)[:, None]
+		height = np.abs(pb[1:] - pb[:-1])[None, :]
+		return n_pos * n_shape * np.pi * ring * height / volume  # same operation order as get_random_pairs("cross")
+
+	def _rr_grid_rmu(self, volume, n_pos, n_shape):
+		if getattr(self, "_cap_grid", None) is None:
+			# shell-cap volumes per bin, evaluated with numpy SCALARS exactly as the reference does (its `r ** 3` on a
+			# scalar and numpy's vectorised power differ in the last bit); independent of the sample, so cached
+			rb, mb = self.r_bins, self.mu_r_bins
+			cap = self.get_volume_spherical_cap
+			vol = np.zeros((self.num_bins_r, self.num_bins_pi))
+			for i in range(self.num_bins_r):
+				for p in range(self.num_bins_pi):
+					vol[i, p] = (cap(mb[p], rb[i + 1]) - cap(mb[p + 1], rb[i + 1])
+								 - (cap(mb[p], rb[i]) - cap(mb[p + 1], rb[i])))
+			self._cap_grid = vol
+		return np.abs((n_pos - 1.0) * n_shape * self._cap_grid / volume)
+
+	# ---- jackknife regions ----------------------------------------------------------------------------------------------
+	def _jackknife_labels(self, positions, L_subboxes):
+		"""Label in [0, n^3) of the axis-aligned sub-box strictly containing each point; points on any sub-box face
+		(or outside the box) get label 0 -- the semantics of the reference's n^3 strict-inequality masks
+		(measure_IA_base.py:428-451), evaluated in O(N) instead of O(n^3 N)."""
+		n = int(L_subboxes)
+		L_sub = self.L_0p5 * 2.0 / n
+		bounds = np.arange(0, n + 1) * L_sub  # i * L_sub, the same products the reference forms
+		pos = np.asarray(positions, dtype=np.float64)
+		idx = np.empty(pos.shape, dtype=np.int64)
+		inside = np.ones(len(pos), dtype=bool)
+		for d in range(3):
+			i = np.searchsorted(bounds, pos[:, d], side="right") - 1
+			ok = (i >= 0) & (i < n)
+			ic = np.clip(i, 0, n - 1)
+			ok &= (pos[:, d] > bounds[ic]) & (pos[:, d] < bounds[ic + 1])
+			inside &= ok
+			idx[:, d] = ic
+		lab = idx[:, 0] * n * n + idx[:, 1] * n + idx[:, 2]
+		return np.where(inside, lab, 0).astype(int)
+
+	def _get_jackknife_region_indices(self, masks, L_subboxes):
+		if masks is None:
+			positions = self.data["Position"]
+			positions_shape_sample = self.data["Position_shape_sample"]
+		else:
+			positions = self.data["Position"][masks["Position"]]
+			positions_shape_sample = self.data["Position_shape_sample"][masks["Position_shape_sample"]]
+		return self._jackknife_labels(positions, L_subboxes), self._jackknife_labels(positions_shape_sample, L_subboxes)
+
+	# ---- post-processing on stored xi grids (file based, as in the reference) ----------------------------------------------
+	@staticmethod
+	def _w_from_xi(xi, pi_bins):
+		dpi = pi_bins[1:] - pi_bins[:-1]
+		return np.sum(xi * abs(np.array([dpi] * len(xi[:, 0]))), axis=1)  # measure_IA_base.py:553-562
+
+	@staticmethod
+	def _multipole_from_xi(xi, mu_r_bins, which):
+		"""(2l+1)/2 (l-s)!/(l+s)! P_l^s(mu) xi dmu summed over mu, (l, s) = (2, 2) for g+ and (0, 0) for gg
+		(measure_IA_base.py:628-655); P_2^2(x) = 3 (1 - x^2), P_0^0 = 1."""
+		l = sab = 2 if which == "g_plus" else 0
+		dmur = mu_r_bins[1:] - mu_r_bins[:-1]
+		mu_mid = mu_r_bins[:-1] + abs(dmur / 2.0)
+		leg = (3.0 * (1.0 - mu_mid * mu_mid)) if l == 2 else np.ones_like(mu_mid)
+		n_r = xi.shape[0]
+		Lg = np.array(list(leg) * n_r).reshape((n_r, len(leg)))
+		dmu = np.array(list(dmur) * n_r).reshape((n_r, len(dmur)))
+		mult = (2 * l + 1) / 2.0 * math.factorial(l - sab) / math.factorial(l + sab) * Lg * xi * dmu
+		return np.sum(mult, axis=1)
+
+	def _measure_w_g_i(self, dataset_name, corr_type="both", return_output=False, jk_group_name=""):
+		"""w = sum_Pi xi dPi from a stored xi grid (measure_IA_base.py:515-575)."""
+		try:
+			names = {"both": (["xi_g_plus", "xi_gg"], ["w_g_plus", "w_gg"]), "g+": (["xi_g_plus"], ["w_g_plus"]),
+					 "gg": (["xi_gg"], ["w_gg"])}[corr_type]
+		except KeyError:
+			raise KeyError("Unknown value for corr_type. Choose from [g+, gg, both]")
+		for xi_name, w_name in zip(*names):
+			f = open_file(self.output_file_name, "a")
+			try:
+				group = f[f"{self.snap_group}/w/{xi_name}/{jk_group_name}"]
+				xi = group[dataset_name][:]
+				pi = group[dataset_name + "_pi"][:]
+				rp = group[dataset_name + "_rp"][:]
+				dpi = self.pi_bins[1:] - self.pi_bins[:-1]
+				centres = self.pi_bins[:-1] + abs(dpi) / 2.0
+				if sum(np.isin(pi, centres)) != len(pi):
+					raise ValueError("Update pi bins in initialisation of object to match xi_g_plus dataset.")
+				w = self._w_from_xi(xi, self.pi_bins)
+				if return_output:
+					return np.array([rp, w]).transpose()
+				out = create_group_hdf5(f, f"{self.snap_group}/{w_name}/{jk_group_name}")
+				write_dataset_hdf5(out, dataset_name + "_rp", data=rp)
+				write_dataset_hdf5(out, dataset_name, data=w)
+			finally:
+				f.close()
+
+	def _measure_multipoles(self, dataset_name, corr_type="both", return_output=False, jk_group_name=""):
+		"""Multipoles from a stored (r, mu_r) xi grid (measure_IA_base.py:577-668)."""
+		try:
+			kinds = {"both": ["g_plus", "gg"], "g+": ["g_plus"], "gg": ["gg"]}[corr_type]
+		except KeyError:
+			raise KeyError("Unknown value for corr_type. Choose from [g+, gg, both]")
+		f = open_file(self.output_file_name, "a")
+		try:
+			dsep = (self.r_bins[1:] - self.r_bins[:-1]) / 2.0
+			separation = self.r_bins[:-1] + abs(dsep)
+			for which in kinds:
+				group = f[f"{self.snap_group}/multipoles/xi_{which}/{jk_group_name}"]
+				xi = group[dataset_name][:]
+				mult = self._multipole_from_xi(xi, self.mu_r_bins, which)
+				if return_output:
+					return np.array([separation, mult]).transpose()
+				out = create_group_hdf5(f, f"{self.snap_group}/multipoles_{which}/{jk_group_name}")
+				write_dataset_hdf5(out, dataset_name + "_r", data=separation)
+				write_dataset_hdf5(out, dataset_name, data=mult)
+		finally:
+			f.close()
+
+	@staticmethod
+	def _jackknife_stats(realisations):
+		"""mean, std, cov with cov = (n-1)/n sum_b (x_b - mean)(x_b - mean)^T (measure_IA_base.py:482-498)."""
+		x = np.asarray(realisations, dtype=np.float64)
+		num_box, n_r = x.shape
+		mean = np.zeros(n_r)
+		for b in range(num_box):
+			mean += x[b]
+		mean /= num_box
+		cov = np.zeros((n_r, n_r))
+		std = np.zeros(n_r)
+		for b in range(num_box):
+			d = x[b] - mean
+			std += d ** 2
+			cov += d[:, None] * d[None, :]
+		std *= (num_box - 1) / num_box
+		cov *= (num_box - 1) / num_box
+		return mean, np.sqrt(std), cov
+
+	def _combine_jackknife_information(self, dataset_name, jk_group_name, corr_group, num_box, return_output=False):
+		covs, stds = [], []
+		for corr in corr_group:
+			f = open_file(self.output_file_name, "a")
+			try:
+				grp = f[f"{self.snap_group}/{corr}/{jk_group_name}/"]
+				reals = np.array([grp[f"{dataset_name}_{b}"][:] for b in range(num_box)])
+				mean, std, cov = self._jackknife_stats(reals)
+				if return_output:
+					covs.append(cov)
+					stds.append(std)
+				else:
+					out = create_group_hdf5(f, f"{self.snap_group}/" + corr)
+					write_dataset_hdf5(out, dataset_name + "_mean_" + str(num_box), data=mean)
+					write_dataset_hdf5(out, dataset_name + "_jackknife_" + str(num_box), data=std)
+					write_dataset_hdf5(out, dataset_name + "_jackknife_cov_" + str(num_box), data=cov)
+			finally:
+				f.close()
+		if return_output:
+			return covs, stds
+
+
+class MeasureIABox(MeasureIABase):
+	"""Drop-in for ``measureia.MeasureIABox`` (measure_IA.py:10-262) running the pair loop on a B200."""
+
+	def __init__(self, data, output_file_name, simulation=None, snapshot=None, separation_limits=[0.1, 20.0],
+				 num_bins_r=8, num_bins_pi=20, pi_max=None, boxsize=None, periodicity=True, num_nodes=1):
+		super().__init__(data, output_file_name, simulation, snapshot, separation_limits, num_bins_r, num_bins_pi,
+						 pi_max, boxsize, periodicity)
+		self.num_nodes = num_nodes  # accepted for compatibility; GPUs are chosen by torch.distributed / MIA_DEVICE
+		self.randoms_data = None
+		self.data_dir = None
+		self.num_samples = None
+		self.kernel = os.environ.get("MIA_KERNEL", "auto")
+		self.device = None      # torch device; default: current CUDA device
+		self.last_stats = None  # dict filled by every measurement (pairs tested / binned, kernel, timings)
+
+	# ---- input preparation (measure_w_box_jk.py:322-364) ---------------------------------------------------------------
+	def _prepare(self, masks, ellipticity):
+		d = self.data
+		if masks is None:
+			pos, pos_s = d["Position"], d["Position_shape_sample"]
+			axis_v, q = d["Axis_Direction"], d["q"]
+			w, w_s = d["weight"], d["weight_shape_sample"]
+			same = pos is pos_s and w is w_s
+		else:
+			pos = d["Position"][masks["Position"]]
+			pos_s = d["Position_shape_sample"][masks["Position_shape_sample"]]
+			axis_v = d["Axis_Direction"][masks["Axis_Direction"]]
+			q = d["q"][masks["q"]]
+			# quirk kept from the reference (:338-347): without explicit weight masks the FIRST sum(mask) weights are
+			# used, and the fabricated masks are stored in the caller's dict
+			if "weight" not in masks:
+				m = np.ones(self.Num_position, dtype=bool)
+				m[sum(masks["Position"]):self.Num_position] = 0
+				masks["weight"] = m
+			if "weight_shape_sample" not in masks:
+				m = np.ones(self.Num_shape, dtype=bool)
+				m[sum(masks["Position_shape_sample"]):self.Num_shape] = 0
+				masks["weight_shape_sample"] = m
+			w = d["weight"][masks["weight"]]
+			w_s = d["weight_shape_sample"][masks["weight_shape_sample"]]
+			same = False
+		axis_len = np.sqrt(np.sum(axis_v ** 2, axis=1))
+		axis = (axis_v.transpose() / axis_len).transpose()
+		if ellipticity == "distortion":
+			e = (1 - q ** 2) / (1 + q ** 2)
+		elif ellipticity == "ellipticity":
+			e = (1 - q) / (1 + q)
+		else:
+			raise ValueError("Invalid value for ellipticity. Choose 'distortion' or 'ellipticity'.")
+		c = lambda a: np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
+		return c(pos), c(pos_s), c(axis), c(e), c(w), c(w_s), same
+
+	@staticmethod
+	def _responsivity(w_s, e, labels=None, num_box=0):
+		"""R = sum w (1 - e^2/2) / sum w (measure_w_box_jk.py:364) and, per jackknife region, the same over the shapes
+		NOT in the region (:463-466), from one pass of per-region partial sums."""
+		t = w_s * (1 - e ** 2 / 2.0)
+		R = float(np.cumsum(t)[-1] / np.cumsum(w_s)[-1]) if len(t) else float("nan")
+		if not num_box:
+			return R, None
+		tk = np.bincount(labels, weights=t, minlength=num_box)
+		wk = np.bincount(labels, weights=w_s, minlength=num_box)
+		R_jk = np.empty(num_box)
+		with np.errstate(invalid="ignore", divide="ignore"):
+			for k in range(num_box):
+				R_jk[k] = np.delete(tk, k).sum() / np.delete(wk, k).sum()
+		return R, R_jk
+
+	def _thresholds_for(self, geom, rp_cut):
+		key = (geom, rp_cut)
+		if key not in self._thresholds:
+			_, r2_thr, clean = calib.r_thresholds(self.r_min, self.r_max, self.num_bins_r, self.r_bins)
+			if geom == "rppi":
+				thr2 = calib.pi_thresholds(self.pi_bins, self.num_bins_pi)
+			else:
+				thr2 = calib.mu_thresholds(self.mu_r_bins, self.num_bins_pi)
+			self._thresholds[key] = (r2_thr, thr2, calib.rp_cut_threshold(rp_cut), clean)
+		return self._thresholds[key]
+
+	# ---- the pair loop: ONE operator call replaces the reference's twelve variants -----------------------------------------
+	def _pair_sums(self, geom, masks, L_subboxes, ellipticity, rp_cut=None):
+		import torch
+
+		from . import ops
+
+		t0 = time.perf_counter()
+		pos, pos_s, axis, e, w, w_s, same = self._prepare(masks, ellipticity)
+		num_box = L_subboxes ** 3 if L_subboxes else 0
+		jk_p = jk_s = None
+		if num_box:
+			jk_p = self._jackknife_labels(pos, L_subboxes)
+			jk_s = jk_p if same else self._jackknife_labels(pos_s, L_subboxes)
+		R, R_jk = self._responsivity(w_s, e, jk_s, num_box)
+		r2_thr, thr2, rp2_cut, clean = self._thresholds_for(geom, rp_cut)
+		if not torch.cuda.is_available():
+			raise RuntimeError("measure_ia_b200 needs a CUDA device: the pair-count operator has no CPU fallback")
+		dev = torch.device(self.device) if self.device is not None else torch.device("cuda", torch.cuda.current_device())
+		t1 = time.perf_counter()
+
+		def up(a, dtype=None):
+			if a is None:
+				return None
+			t = torch.from_numpy(np.ascontiguousarray(a))
+			if dtype is not None:
+				t = t.to(dtype)
+			return t.to(dev, non_blocking=False)
+
+		unit_p, unit_s = bool(np.all(w == 1.0)), bool(np.all(w_s == 1.0))
+		d_pos = up(pos)
+		d_w = None if unit_p else up(w)
+		d_jk = up(jk_p, torch.int32)
+		if same:
+			d_pos_s, d_w_s, d_jk_s = d_pos, d_w, d_jk
+		else:
+			d_pos_s, d_w_s, d_jk_s = up(pos_s), (None if unit_s else up(w_s)), up(jk_s, torch.int32)
+		d_axis, d_e = up(axis), up(e)
+
+		rank, world = 0, 1
+		if torch.distributed.is_available() and torch.distributed.is_initialized():
+			rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+		kernel = ops.KERNEL_NAMES[self.kernel]
+		out = torch.ops.measure_ia_b200.paircount(
+			d_pos, d_w, d_jk, d_pos_s, d_w_s, d_jk_s, d_axis, d_e, torch.from_numpy(r2_thr), torch.from_numpy(thr2),
+			ops.GEOM_RPPI if geom == "rppi" else ops.GEOM_RMU, int(self.data["LOS"]), bool(self.periodicity), num_box,
+			float(self.boxsize), float(self.r_bins[-1]), float(rp2_cut), kernel, rank, world)
+		dd_count, dd_w, spd, scd, jk_count, jk_w, spd_jk, stats = out
+		if world > 1:
+			dd_count, dd_w, spd, scd, jk_count, jk_w, spd_jk, stats = combine_across_ranks(
+				dd_count, dd_w, spd, scd, jk_count, jk_w, spd_jk, stats)
+		torch.cuda.synchronize(dev)
+		t2 = time.perf_counter()
+		res = dict(count=dd_count.cpu().numpy(), DD=dd_w.cpu().numpy(), SpD_raw=spd.cpu().numpy(),
+				   ScD_raw=scd.cpu().numpy(), count_jk=jk_count.cpu().numpy(), DD_jk=jk_w.cpu().numpy(),
+				   SpD_jk=spd_jk.cpu().numpy(), R=R, R_jk=R_jk, jk_p=jk_p, jk_s=jk_s, Np=len(pos), Ns=len(pos_s))
+		st = stats.cpu().numpy()
+		self.last_stats = dict(tested=int(st[0]), binned=int(st[1]), nan_rule=int(st[2]), kernel=int(st[4]),
+							   cells=int(st[5]), tasks=int(st[6]), thresholds_clean=bool(clean), rank=rank, world=world,
+							   t_prep=t1 - t0, t_device=t2 - t1)
+		return res
+
+	# ---- results -> the reference's HDF5 layout (measure_w_box_jk.py:498-539, measure_w_box.py:387-407) ------------------
+	def _write_xi(self, geom, res, dataset_name, num_box, jk_group_name, corr_type, return_output=False):
+		R = res["R"]
+		DD = res["DD"]
+		SpD = res["SpD_raw"] / (2 * R)
+		ScD = res["ScD_raw"] / (2 * R)
+		L3 = self.boxsize ** 3
+		rr_grid = self._rr_grid_rppi if geom == "rppi" else self._rr_grid_rmu
+		bins2 = self.pi_bins if geom == "rppi" else self.mu_r_bins
+		RR = rr_grid(L3, res["Np"], res["Ns"])
+		sep = self.r_bins[:-1] + abs((self.r_bins[1:] - self.r_bins[:-1]) / 2.0)
+		mid2 = bins2[:-1] + abs((bins2[1:] - bins2[:-1]) / 2.0)
+		top = "w" if geom == "rppi" else "multipoles"
+		n1, n2 = ("_rp", "_pi") if geom == "rppi" else ("_r", "_mu_r")
+		pre = "w_" if geom == "rppi" else "multipoles_"
+		try:
+			kinds = {"both": ["g_plus", "gg"], "g+": ["g_plus"], "gg": ["gg"]}[corr_type]
+		except KeyError:
+			raise KeyError("Unknown value for corr_type. Choose from [g+, gg, both]")
+		integrate = (lambda xi, which: self._w_from_xi(xi, self.pi_bins)) if geom == "rppi" else (
+			lambda xi, which: self._multipole_from_xi(xi, self.mu_r_bins, which))
+
+		with np.errstate(divide="ignore", invalid="ignore"):
+			xi_gp, xi_gx, xi_gg = SpD / RR, ScD / RR, (DD / RR) - 1
+			if return_output:
+				return xi_gp, xi_gg, sep, mid2, SpD, DD, RR
+			X = dataset_name
+			f = open_file(self.output_file_name, "a")
+			try:
+				snap = self.snap_group
+				g = create_group_hdf5(f, f"{snap}/{top}/xi_g_plus/")
+				write_dataset_hdf5(g, X, data=xi_gp)
+				write_dataset_hdf5(g, X + "_SplusD", data=SpD)
+				write_dataset_hdf5(g, X + "_RR_g_plus", data=RR)
+				if num_box:
+					write_dataset_hdf5(g, X + "_sigmasq", data=np.zeros_like(DD))
+				write_dataset_hdf5(g, X + n1, data=sep)
+				write_dataset_hdf5(g, X + n2, data=mid2)
+				g = create_group_hdf5(f, f"{snap}/{top}/xi_g_cross/{jk_group_name}")
+				write_dataset_hdf5(g, X + "_ScrossD", data=ScD)
+				write_dataset_hdf5(g, X, data=xi_gx)
+				write_dataset_hdf5(g, X + "_RR_g_cross", data=RR)
+				if num_box:
+					write_dataset_hdf5(g, X + "_sigmasq", data=np.zeros_like(DD))
+				write_dataset_hdf5(g, X + n1, data=sep)
+				write_dataset_hdf5(g, X + n2, data=mid2)
+				g = create_group_hdf5(f, f"{snap}/{top}/xi_gg/")
+				write_dataset_hdf5(g, X, data=xi_gg)
+				write_dataset_hdf5(g, X + "_DD", data=DD)
+				write_dataset_hdf5(g, X + "_RR_gg", data=RR)
+				if num_box:
+					write_dataset_hdf5(g, X + "_sigmasq", data=np.zeros_like(DD))
+				write_dataset_hdf5(g, X + n1, data=sep)
+				write_dataset_hdf5(g, X + n2, data=mid2)
+
+				xi_jk = {"g_plus": [], "gg": []}
+				if num_box:
+					R_jk = res["R_jk"]
+					vol_jk = L3 * (num_box - 1) / num_box
+					n_p_k = res["Np"] - np.bincount(res["jk_p"], minlength=num_box)
+					n_s_k = res["Ns"] - np.bincount(res["jk_s"], minlength=num_box)
+					gp = create_group_hdf5(f, f"{snap}/{top}/xi_g_plus/{jk_group_name}")
+					gg = create_group_hdf5(f, f"{snap}/{top}/xi_gg/{jk_group_name}")
+					for i in range(num_box):
+						RR_i = rr_grid(vol_jk, int(n_p_k[i]), int(n_s_k[i]))
+						corr = (SpD * (2 * R) - res["SpD_jk"][i]) / (RR_i * 2 * R_jk[i])
+						write_dataset_hdf5(gp, f"{X}_{i}", data=corr)
+						write_dataset_hdf5(gp, f"{X}_{i}_SplusD", data=(SpD * (2 * R) - res["SpD_jk"][i]) / (2 * R_jk[i]))
+						write_dataset_hdf5(gp, f"{X}_{i}_RR", data=RR_i)
+						write_dataset_hdf5(gp, f"{X}_{i}{n1}", data=sep)
+						write_dataset_hdf5(gp, f"{X}_{i}{n2}", data=mid2)
+						xgg = ((DD - res["DD_jk"][i]) / RR_i) - 1
+						write_dataset_hdf5(gg, f"{X}_{i}", data=xgg)
+						write_dataset_hdf5(gg, f"{X}_{i}_DD", data=DD - res["DD_jk"][i])
+						write_dataset_hdf5(gg, f"{X}_{i}_RR", data=RR_i)
+						write_dataset_hdf5(gg, f"{X}_{i}{n1}", data=sep)
+						write_dataset_hdf5(gg, f"{X}_{i}{n2}", data=mid2)
+						xi_jk["g_plus"].append(corr)
+						xi_jk["gg"].append(xgg)
+
+				# integrated statistics + jackknife covariance (measure_IA.py:136-149 / :234-247), same file handle
+				for which in kinds:
+					xi = xi_gp if which == "g_plus" else xi_gg
+					out = create_group_hdf5(f, f"{snap}/{pre}{which}/")
+					write_dataset_hdf5(out, X + n1, data=sep)
+					write_dataset_hdf5(out, X, data=integrate(xi, which))
+					if num_box:
+						outj = create_group_hdf5(f, f"{snap}/{pre}{which}/{jk_group_name}")
+						reals = []
+						for i in range(num_box):
+							val = integrate(xi_jk[which][i], which)
+							reals.append(val)
+							write_dataset_hdf5(outj, f"{X}_{i}{n1}", data=sep)
+							write_dataset_hdf5(outj, f"{X}_{i}", data=val)
+						mean, std, cov = self._jackknife_stats(np.array(reals))
+						write_dataset_hdf5(out, f"{X}_mean_{num_box}", data=mean)
+						write_dataset_hdf5(out, f"{X}_jackknife_{num_box}", data=std)
+						write_dataset_hdf5(out, f"{X}_jackknife_cov_{num_box}", data=cov)
+			finally:
+				f.close()
+
+	# ---- public API ---------------------------------------------------------------------------------------------------------
+	def _measure(self, geom, dataset_name, corr_type, num_jk, temp_file_path, masks, ellipticity, rp_cut=None):
+		L = 0
+		if num_jk > 0:
+			L, exact = integer_cube_root(num_jk)
+			if not exact:
+				raise ValueError(
+					f"Use x^3 as input for num_jk, with x as an int. {float(int(num_jk ** (1. / 3)))},{num_jk ** (1. / 3)}")
+		if temp_file_path is None:  # `temp_file_path == False` (no temporary storage) is fine; None is an error
+			raise ValueError(
+				"Input temp_file_path for faster computation. Do not want to save data temporarily? Input file_path_tree=False.")
+		if corr_type not in ("both", "g+", "gg"):
+			raise KeyError("Unknown value for corr_type. Choose from [g+, gg, both]")
+		t0 = time.perf_counter()
+		res = self._pair_sums(geom, masks, L, ellipticity, rp_cut)
+		t1 = time.perf_counter()
+		is_writer = self.last_stats["rank"] == 0
+		if is_writer and self.output_file_name is not None:
+			jk_group = f"{dataset_name}_jk{num_jk}" if num_jk > 0 else ""
+			self._write_xi(geom, res, dataset_name, num_jk if num_jk > 0 else 0, jk_group, corr_type)
+		self.last_stats["t_pairs"] = t1 - t0
+		self.last_stats["t_write"] = time.perf_counter() - t1
+		self.last_result = res
+
+	def measure_xi_w(self, dataset_name, corr_type, num_jk=0, temp_file_path=None, masks=None,
+					 ellipticity='distortion', chunk_size=1000):
+		r"""xi_gg, xi_g+ on the (r_p, Pi) grid, w_gg, w_g+ and (num_jk > 0) their jackknife covariance
+		(measure_IA.py:68-163)."""
+		self._measure("rppi", dataset_name, corr_type, num_jk, temp_file_path, masks, ellipticity)
+
+	def measure_xi_multipoles(self, dataset_name, corr_type, num_jk=0, temp_file_path=None, masks=None, rp_cut=None,
+							  ellipticity='distortion', chunk_size=1000):
+		r"""xi_gg, xi_g+ on the (r, mu_r) grid and the multipoles of Singh et al. (2024) (measure_IA.py:165-262).
+		``rp_cut`` is accepted and, exactly as in the reference, NOT forwarded to the pair loop (measure_IA.py:218-259
+		never passes it on), so it has no effect through this entry point."""
+		self._measure("rmu", dataset_name, corr_type, num_jk, temp_file_path, masks, ellipticity, rp_cut=None)
+
+
+def combine_across_ranks(dd_count, dd_w, spd, scd, jk_count, jk_w, spd_jk, stats):
+	"""The one exchange step of the sharded path (reference: parent-side `+=` over worker results,
+	measure_w_box_jk.py:775-780): integer counts by an all-reduce (exact in any order), fp64 sums by an all-gather
+	followed by a fixed rank-order sum so that the result does not depend on arrival order."""
+	import torch
+	import torch.distributed as dist
+
+	from . import ops
+
+	world = dist.get_world_size()
+	ints = torch.cat([dd_count.flatten(), jk_count.flatten(), stats.flatten()])
+	dist.all_reduce(ints, op=dist.ReduceOp.SUM)
+	n0, n1 = dd_count.numel(), jk_count.numel()
+	dd_count = ints[:n0].view_as(dd_count)
+	jk_count = ints[n0:n0 + n1].view_as(jk_count)
+	stats_sum = ints[n0 + n1:].view_as(stats)
+	floats = torch.cat([t.flatten() for t in (dd_w, spd, scd, jk_w, spd_jk)])
+	gathered = torch.empty((world, floats.numel()), dtype=floats.dtype, device=floats.device)
+	dist.all_gather_into_tensor(gathered, floats)
+	if floats.is_cuda:
+		total = ops.combine_partials(gathered)
+	else:  # gloo tests of the host logic
+		total = gathered[0].clone()
+		for r in range(1, world):
+			total += gathered[r]
+	outs, o = [], 0
+	for t in (dd_w, spd, scd, jk_w, spd_jk):
+		outs.append(total[o:o + t.numel()].view_as(t))
+		o += t.numel()
+	stats_out = stats_sum.clone()
+	stats_out[4] = stats[4]  # kernel id is not additive
+	stats_out[5] = stats[5]
+	return dd_count, outs[0], outs[1], outs[2], jk_count, outs[3], outs[4], stats_out

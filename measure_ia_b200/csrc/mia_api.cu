@@ -1,0 +1,450 @@
+// mia_api.cu -- C ABI of libmia_b200.so (see include/mia_b200.h) and the host-side orchestration:
+// workspace carving, cell-list build, kernel selection, fixed-order final reduction.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "mia_common.cuh"
+#include "mia_general.cuh"
+#include "mia_grid.cuh"
+#include "mia_tiled.cuh"
+
+using namespace mia;
+
+namespace {
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct Plan {
+	// grid
+	GridDims g;
+	int ku, kv, kl;
+	int kernel;       // resolved MIA_KERNEL_*
+	int key_bits;
+	int n_partials;   // accumulator copies (1 for the general kernel, one per CTA for the tiled kernel)
+	int rows;         // 2 * max(num_jk, 1)
+	int nb;
+	TiledConfig tiled;
+	// workspace offsets
+	size_t off_cand, off_cand_jk, off_prim, off_cell_start, off_prim_cell_start, off_keys_in, off_keys_out, off_idx_in,
+		off_idx_out, off_cub, cub_bytes, off_cnt, off_ddw, off_sp, off_sc, off_stats, off_flags, off_tiled, total;
+};
+
+int ilog2_ceil(uint64_t x) {
+	int b = 0;
+	while ((1ull << b) < x) b++;
+	return b;
+}
+
+int validate(const mia_params *p) {
+	if (!p || p->abi_version != MIA_ABI_VERSION) return MIA_ERR_ARG;
+	if (p->n_r < 1 || p->n_r > MIA_MAX_BINS || p->n_2 < 1 || p->n_2 > MIA_MAX_BINS) return MIA_ERR_ARG;
+	if (p->los < 0 || p->los > 2 || p->num_jk < 0 || !(p->boxsize > 0.0) || !(p->r_search > 0.0)) return MIA_ERR_ARG;
+	if (p->geometry != MIA_GEOM_RPPI && p->geometry != MIA_GEOM_RMU) return MIA_ERR_ARG;
+	if (!p->r2_thr_host || !p->thr2_host) return MIA_ERR_ARG;
+	return MIA_OK;
+}
+
+// Cell grid for the general kernel: cells at least one search radius wide, 3 x 3 (x 3) neighbourhood.
+void plan_general_grid(const mia_params *p, Plan &pl) {
+	const double reach = p->r_search * (1.0 + 1e-6);
+	int nc = (int)floor(p->boxsize / reach);
+	const int cap = (p->geometry == MIA_GEOM_RPPI) ? 1024 : 160;
+	if (nc > cap) nc = cap;
+	if (nc < 3) nc = 1;
+	pl.g.ncu = pl.g.ncv = nc;
+	pl.g.ncl = (p->geometry == MIA_GEOM_RMU) ? nc : 1;
+	pl.g.inv_cu = pl.g.inv_cv = nc / p->boxsize;
+	pl.g.inv_cl = pl.g.ncl / p->boxsize;
+	pl.ku = pl.kv = 1;
+	pl.kl = (p->geometry == MIA_GEOM_RMU) ? 1 : 0;
+}
+
+int make_plan(const mia_params *p, int64_t nD, int64_t nS, Plan &pl) {
+	memset(&pl, 0, sizeof(pl));
+	pl.nb = p->n_r * p->n_2;
+	const int J = p->num_jk > 0 ? p->num_jk : 1;
+	pl.rows = 2 * J;
+	pl.g.jk_rows = J;
+	pl.kernel = p->kernel;
+	if (pl.kernel == MIA_KERNEL_AUTO || pl.kernel == MIA_KERNEL_TILED) {
+		if (plan_tiled(p, nD, nS, pl.g, pl.ku, pl.kv, pl.kl, pl.tiled)) {
+			pl.kernel = MIA_KERNEL_TILED;
+		} else {
+			if (pl.kernel == MIA_KERNEL_TILED) return MIA_ERR_UNSUPPORTED;
+			pl.kernel = MIA_KERNEL_GENERAL;
+		}
+	}
+	if (pl.kernel == MIA_KERNEL_GENERAL) {
+		plan_general_grid(p, pl);
+		pl.n_partials = 1;
+	} else {
+		pl.n_partials = pl.tiled.n_partials;
+	}
+	const uint64_t nkeys = (uint64_t)pl.g.ncell() * (uint64_t)J;
+	if (nkeys > (1ull << 31)) return MIA_ERR_UNSUPPORTED;
+	pl.key_bits = ilog2_ceil(nkeys > 1 ? nkeys : 2);
+	const int64_t nmax = nD > nS ? nD : nS;
+	if (nmax >= (1ll << 31)) return MIA_ERR_UNSUPPORTED;
+
+	size_t o = 0;
+	auto take = [&](size_t bytes) {
+		size_t at = o;
+		o = align_up(o + bytes);
+		return at;
+	};
+	pl.off_cand = take(sizeof(Cand) * (size_t)nD);
+	pl.off_cand_jk = take(sizeof(int32_t) * (size_t)nD);
+	pl.off_prim = take(sizeof(Prim) * (size_t)nS);
+	pl.off_cell_start = take(sizeof(int64_t) * (size_t)(pl.g.ncell() + 1));
+	pl.off_prim_cell_start = take(sizeof(int64_t) * (size_t)(pl.g.ncell() + 1));
+	pl.off_keys_in = take(sizeof(uint32_t) * (size_t)nmax);
+	pl.off_keys_out = take(sizeof(uint32_t) * (size_t)nmax);
+	pl.off_idx_in = take(sizeof(int32_t) * (size_t)nmax);
+	pl.off_idx_out = take(sizeof(int32_t) * (size_t)nmax);
+	pl.cub_bytes = cub_sort_bytes(nmax > 0 ? nmax : 1);
+	pl.off_cub = take(pl.cub_bytes);
+	const size_t acc = (size_t)pl.n_partials * pl.rows * pl.nb;
+	pl.off_cnt = take(sizeof(unsigned long long) * acc);
+	pl.off_ddw = take(sizeof(double) * acc);
+	pl.off_sp = take(sizeof(double) * acc);
+	pl.off_sc = take(sizeof(double) * acc);
+	pl.off_stats = take(sizeof(unsigned long long) * 8);
+	pl.off_flags = take(sizeof(int) * 8);
+	pl.off_tiled = take(pl.kernel == MIA_KERNEL_TILED ? tiled_workspace_bytes(pl.tiled, pl.g, nD, nS) : 0);
+	pl.total = o;
+	return MIA_OK;
+}
+
+void fill_dev_params(const mia_params *p, const Plan &pl, DevParams &P) {
+	memset(&P, 0, sizeof(P));
+	P.geom = p->geometry;
+	P.n_r = p->n_r;
+	P.n_2 = p->n_2;
+	P.los = p->los;
+	P.periodic = p->periodic ? 1 : 0;
+	P.num_jk = p->num_jk;
+	P.L = p->boxsize;
+	P.halfL = p->boxsize / 2.0;  // L_0p5 = boxsize / 2. (Sim_info.py:79)
+	P.rp2_cut = p->rp2_cut;
+	for (int b = 0; b <= p->n_r; b++) P.r2_thr[b] = p->r2_thr_host[b];
+	for (int b = 0; b <= p->n_2; b++) P.thr2[b] = p->thr2_host[b];
+	P.ncu = pl.g.ncu;
+	P.ncv = pl.g.ncv;
+	P.ncl = pl.g.ncl;
+	P.inv_cu = pl.g.inv_cu;
+	P.inv_cv = pl.g.inv_cv;
+	P.inv_cl = pl.g.inv_cl;
+	P.ku = pl.ku;
+	P.kv = pl.kv;
+	P.kl = pl.kl;
+}
+
+// Fixed-order reduction of the accumulator copies into the caller's output grids.
+__global__ void k_finalize(const unsigned long long *__restrict__ cnt, const double *__restrict__ ddw,
+						   const double *__restrict__ sp, const double *__restrict__ sc, int n_partials, int J, int nb,
+						   int num_jk, mia_hist out) {
+	const int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= nb) return;
+	const size_t part = (size_t)2 * J * nb;
+	unsigned long long t_cnt = 0;
+	double t_ddw = 0.0, t_sp = 0.0, t_sc = 0.0;
+	for (int k = 0; k < J; k++) {
+		unsigned long long a_cnt = 0, b_cnt = 0;
+		double a_ddw = 0.0, a_sp = 0.0, a_sc = 0.0, b_ddw = 0.0, b_sp = 0.0;
+		for (int p = 0; p < n_partials; p++) {
+			const size_t ia = p * part + (size_t)k * nb + b, ib = p * part + (size_t)(J + k) * nb + b;
+			a_cnt += cnt[ia];
+			a_ddw += ddw[ia];
+			a_sp += sp[ia];
+			a_sc += sc[ia];
+			b_cnt += cnt[ib];
+			b_ddw += ddw[ib];
+			b_sp += sp[ib];
+		}
+		t_cnt += a_cnt;
+		t_ddw += a_ddw;
+		t_sp += a_sp;
+		t_sc += a_sc;
+		if (num_jk > 0) {
+			if (out.dd_jk_count) out.dd_jk_count[(size_t)k * nb + b] = (int64_t)(a_cnt + b_cnt);
+			if (out.dd_jk_w) out.dd_jk_w[(size_t)k * nb + b] = a_ddw + b_ddw;
+			if (out.spd_jk) out.spd_jk[(size_t)k * nb + b] = a_sp + b_sp;
+		}
+	}
+	out.dd_count[b] = (int64_t)t_cnt;
+	out.dd_w[b] = t_ddw;
+	out.spd[b] = t_sp;
+	out.scd[b] = t_sc;
+}
+
+__global__ void k_copy_stats(const unsigned long long *in, uint64_t *out, unsigned long long kernel,
+							 unsigned long long cells, unsigned long long tasks) {
+	if (threadIdx.x < 4) out[threadIdx.x] = in[threadIdx.x];
+	if (threadIdx.x == 4) out[4] = kernel;
+	if (threadIdx.x == 5) out[5] = cells;
+	if (threadIdx.x == 6) out[6] = tasks;
+	if (threadIdx.x == 7) out[7] = 0;
+}
+
+__global__ void k_combine(const double *__restrict__ parts, int n_parts, int64_t n, double *__restrict__ out) {
+	int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	double s = 0.0;
+	for (int p = 0; p < n_parts; p++) s += parts[(size_t)p * n + i];
+	out[i] = s;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *mia_strerror(int code) {
+	switch (code) {
+		case MIA_OK: return "ok";
+		case MIA_ERR_ARG: return "bad argument";
+		case MIA_ERR_WORKSPACE: return "workspace too small (see mia_workspace_bytes)";
+		case MIA_ERR_RANGE: return "a coordinate lies outside [0, boxsize)";
+		case MIA_ERR_WINDOW: return "tiled kernel: a pair fell outside its accumulation window (internal error)";
+		case MIA_ERR_UNSUPPORTED: return "configuration not supported by the requested kernel";
+		default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+	}
+}
+
+int mia_abi_version(void) { return MIA_ABI_VERSION; }
+
+size_t mia_workspace_bytes(const mia_params *params, int64_t n_position, int64_t n_shape) {
+	if (validate(params) != MIA_OK || n_position < 0 || n_shape < 0) return 0;
+	Plan pl;
+	if (make_plan(params, n_position, n_shape, pl) != MIA_OK) return 0;
+	return pl.total + 256;
+}
+
+int mia_paircount(const mia_params *params, const mia_sample *D, const mia_sample *S, mia_shard shard,
+				  const mia_hist *out, void *workspace, size_t workspace_bytes, void *stream) {
+	int rc = validate(params);
+	if (rc != MIA_OK) return rc;
+	if (!D || !S || !out || D->n < 0 || S->n < 0) return MIA_ERR_ARG;
+	if ((D->n > 0 && !D->pos) || (S->n > 0 && (!S->pos || !S->axis || !S->e))) return MIA_ERR_ARG;
+	if (!out->dd_count || !out->dd_w || !out->spd || !out->scd) return MIA_ERR_ARG;
+	if (params->num_jk > 0 && (!D->jk || !S->jk)) return MIA_ERR_ARG;
+	if (shard.count < 1 || shard.index < 0 || shard.index >= shard.count) return MIA_ERR_ARG;
+	cudaStream_t st = (cudaStream_t)stream;
+	const int64_t nD = D->n, nS = S->n;
+
+	Plan pl;
+	rc = make_plan(params, nD, nS, pl);
+	if (rc != MIA_OK) return rc;
+	if (!workspace || workspace_bytes < pl.total) return MIA_ERR_WORKSPACE;
+	unsigned char *ws = (unsigned char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+	if (ws + pl.total > (unsigned char *)workspace + workspace_bytes) return MIA_ERR_WORKSPACE;
+
+	DevParams P;
+	fill_dev_params(params, pl, P);
+	const int nl0 = (params->los == 0) ? 1 : 0, nl1 = (params->los == 2) ? 1 : 2, los = params->los;
+
+	Cand *cand = (Cand *)(ws + pl.off_cand);
+	int32_t *cand_jk = (int32_t *)(ws + pl.off_cand_jk);
+	Prim *prim = (Prim *)(ws + pl.off_prim);
+	int64_t *cell_start = (int64_t *)(ws + pl.off_cell_start);
+	int64_t *prim_cell_start = (int64_t *)(ws + pl.off_prim_cell_start);
+	SortScratch sc;
+	sc.keys_in = (uint32_t *)(ws + pl.off_keys_in);
+	sc.keys_out = (uint32_t *)(ws + pl.off_keys_out);
+	sc.idx_in = (int32_t *)(ws + pl.off_idx_in);
+	sc.idx_out = (int32_t *)(ws + pl.off_idx_out);
+	sc.cub_tmp = ws + pl.off_cub;
+	sc.cub_bytes = pl.cub_bytes;
+	Accum A;
+	A.cnt = (unsigned long long *)(ws + pl.off_cnt);
+	A.ddw = (double *)(ws + pl.off_ddw);
+	A.sp = (double *)(ws + pl.off_sp);
+	A.sc = (double *)(ws + pl.off_sc);
+	A.stats = (unsigned long long *)(ws + pl.off_stats);
+	A.rows = pl.rows;
+	int *flags = (int *)(ws + pl.off_flags);
+
+	// zero accumulators, stats and flags (contiguous region from off_cnt to off_tiled)
+	MIA_CUDA_CHECK(cudaMemsetAsync(ws + pl.off_cnt, 0, pl.off_tiled - pl.off_cnt, st));
+
+	const int T = 256;
+	const int64_t ncell = pl.g.ncell();
+	// ---- position sample -> sorted candidates + cell offsets ------------------------------------------------------
+	rc = sort_by_cell(D->pos, D->jk, nD, nl0, nl1, los, pl.g, params->boxsize, sc, pl.key_bits, flags, st);
+	if (rc) return rc;
+	if (nD > 0) {
+		k_gather_cand<<<(unsigned)((nD + T - 1) / T), T, 0, st>>>(D->pos, D->weight, D->jk, sc.idx_out, nD, nl0, nl1, los,
+																   cand, cand_jk);
+	}
+	k_cell_start<<<(unsigned)((nD + 1 + T - 1) / T), T, 0, st>>>(sc.keys_out, nD, pl.g.jk_rows, ncell, cell_start);
+	MIA_CUDA_CHECK(cudaGetLastError());
+	if (pl.kernel == MIA_KERNEL_TILED) {
+		rc = tiled_prepare_candidates(pl.tiled, pl.g, P, sc.keys_out, cand, nD, cell_start, ws + pl.off_tiled, st);
+		if (rc) return rc;
+	}
+	// ---- shape sample -> sorted primaries ---------------------------------------------------------------------------
+	rc = sort_by_cell(S->pos, S->jk, nS, nl0, nl1, los, pl.g, params->boxsize, sc, pl.key_bits, flags, st);
+	if (rc) return rc;
+	if (nS > 0) {
+		k_gather_prim<<<(unsigned)((nS + T - 1) / T), T, 0, st>>>(S->pos, S->weight, S->jk, S->axis, S->e, sc.idx_out, nS,
+																   nl0, nl1, los, prim);
+	}
+	k_cell_start<<<(unsigned)((nS + 1 + T - 1) / T), T, 0, st>>>(sc.keys_out, nS, pl.g.jk_rows, ncell, prim_cell_start);
+	MIA_CUDA_CHECK(cudaGetLastError());
+
+	Grid G;
+	G.cand = cand;
+	G.cand_jk = cand_jk;
+	G.cell_start = cell_start;
+	G.n_cand = nD;
+	G.n_cell = ncell;
+
+	// ---- shard of the (cell-sorted) shape sample ---------------------------------------------------------------------
+	const int64_t s_begin = nS * shard.index / shard.count, s_end = nS * (shard.index + 1) / shard.count;
+	unsigned long long n_tasks = 0;
+
+	if (pl.kernel == MIA_KERNEL_GENERAL) {
+		if (s_end > s_begin && nD > 0) {
+			const int TB = 128;
+			const unsigned blocks = (unsigned)((s_end - s_begin + TB - 1) / TB);
+			const size_t smem = (size_t)pl.nb * (3 * sizeof(double) + sizeof(unsigned int));
+			if (params->geometry == MIA_GEOM_RPPI) {
+				MIA_CUDA_CHECK(cudaFuncSetAttribute(k_general<MIA_GEOM_RPPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+													(int)smem));
+				k_general<MIA_GEOM_RPPI><<<blocks, TB, smem, st>>>(P, G, prim, s_begin, s_end, A);
+			} else {
+				MIA_CUDA_CHECK(cudaFuncSetAttribute(k_general<MIA_GEOM_RMU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+													(int)smem));
+				k_general<MIA_GEOM_RMU><<<blocks, TB, smem, st>>>(P, G, prim, s_begin, s_end, A);
+			}
+			MIA_CUDA_CHECK(cudaGetLastError());
+			n_tasks = blocks;
+		}
+	} else {
+		rc = tiled_launch(pl.tiled, pl.g, P, G, prim, prim_cell_start, nS, s_begin, s_end, A, ws + pl.off_tiled, flags,
+						  &n_tasks, st);
+		if (rc) return rc;
+	}
+
+	// ---- fixed-order final reduction ----------------------------------------------------------------------------------
+	const int J = params->num_jk > 0 ? params->num_jk : 1;
+	k_finalize<<<(pl.nb + 127) / 128, 128, 0, st>>>(A.cnt, A.ddw, A.sp, A.sc, pl.n_partials, J, pl.nb, params->num_jk,
+													*out);
+	MIA_CUDA_CHECK(cudaGetLastError());
+	if (out->stats) {
+		k_copy_stats<<<1, 32, 0, st>>>(A.stats, out->stats, (unsigned long long)pl.kernel, (unsigned long long)ncell,
+									   n_tasks);
+		MIA_CUDA_CHECK(cudaGetLastError());
+	}
+	// range / window flags are checked synchronously: a wrong answer must never be returned silently
+	int h_flags[8];
+	MIA_CUDA_CHECK(cudaMemcpyAsync(h_flags, flags, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+	MIA_CUDA_CHECK(cudaStreamSynchronize(st));
+	if (h_flags[0]) return MIA_ERR_RANGE;
+	if (h_flags[1]) return MIA_ERR_WINDOW;
+	return MIA_OK;
+}
+
+int mia_paircount_host(const mia_params *params, const mia_sample *Dh, const mia_sample *Sh, mia_shard shard,
+					   const mia_hist *out_h, int device) {
+	int rc = validate(params);
+	if (rc != MIA_OK) return rc;
+	if (!Dh || !Sh || !out_h) return MIA_ERR_ARG;
+	MIA_CUDA_CHECK(cudaSetDevice(device));
+	const int64_t nD = Dh->n, nS = Sh->n;
+	const bool same = (Dh->pos == Sh->pos && Dh->weight == Sh->weight && Dh->jk == Sh->jk && nD == nS);
+	const int nb = params->n_r * params->n_2;
+	const int J = params->num_jk;
+	const size_t ws_bytes = mia_workspace_bytes(params, nD, nS);
+	if (ws_bytes == 0) return MIA_ERR_ARG;
+
+	// one device allocation, carved
+	size_t o = 0;
+	auto take = [&](size_t bytes) {
+		size_t at = o;
+		o = align_up(o + bytes);
+		return at;
+	};
+	const size_t o_dpos = take(sizeof(double) * 3 * nD), o_dw = take(Dh->weight ? sizeof(double) * nD : 0),
+				 o_djk = take(Dh->jk ? sizeof(int32_t) * nD : 0);
+	const size_t o_spos = same ? o_dpos : take(sizeof(double) * 3 * nS);
+	const size_t o_sw = same ? o_dw : take(Sh->weight ? sizeof(double) * nS : 0);
+	const size_t o_sjk = same ? o_djk : take(Sh->jk ? sizeof(int32_t) * nS : 0);
+	const size_t o_axis = take(sizeof(double) * 2 * nS), o_e = take(sizeof(double) * nS);
+	const size_t o_cnt = take(sizeof(int64_t) * nb), o_ddw = take(sizeof(double) * nb), o_sp = take(sizeof(double) * nb),
+				 o_sc = take(sizeof(double) * nb);
+	const size_t o_jcnt = take(sizeof(int64_t) * (size_t)J * nb), o_jddw = take(sizeof(double) * (size_t)J * nb),
+				 o_jsp = take(sizeof(double) * (size_t)J * nb);
+	const size_t o_stats = take(sizeof(uint64_t) * 8);
+	const size_t o_ws = take(ws_bytes);
+	unsigned char *d = nullptr;
+	MIA_CUDA_CHECK(cudaMalloc(&d, o + 256));
+	cudaStream_t st;
+	cudaError_t ce = cudaStreamCreate(&st);
+	if (ce != cudaSuccess) {
+		cudaFree(d);
+		return (int)ce;
+	}
+#define H2D(off, src, bytes)                                                                         \
+	if ((src) && (bytes) > 0 && rc == MIA_OK) {                                                      \
+		cudaError_t _e = cudaMemcpyAsync(d + (off), (src), (bytes), cudaMemcpyHostToDevice, st);     \
+		if (_e != cudaSuccess) rc = (int)_e;                                                         \
+	}
+	H2D(o_dpos, Dh->pos, sizeof(double) * 3 * nD);
+	H2D(o_dw, Dh->weight, sizeof(double) * nD);
+	H2D(o_djk, Dh->jk, sizeof(int32_t) * nD);
+	if (!same) {
+		H2D(o_spos, Sh->pos, sizeof(double) * 3 * nS);
+		H2D(o_sw, Sh->weight, sizeof(double) * nS);
+		H2D(o_sjk, Sh->jk, sizeof(int32_t) * nS);
+	}
+	H2D(o_axis, Sh->axis, sizeof(double) * 2 * nS);
+	H2D(o_e, Sh->e, sizeof(double) * nS);
+#undef H2D
+	if (rc == MIA_OK) {
+		mia_sample Dd = {nD, (const double *)(d + o_dpos), Dh->weight ? (const double *)(d + o_dw) : nullptr,
+						 Dh->jk ? (const int32_t *)(d + o_djk) : nullptr, nullptr, nullptr};
+		mia_sample Sd = {nS, (const double *)(d + o_spos), Sh->weight ? (const double *)(d + o_sw) : nullptr,
+						 Sh->jk ? (const int32_t *)(d + o_sjk) : nullptr, (const double *)(d + o_axis),
+						 (const double *)(d + o_e)};
+		mia_hist od;
+		od.dd_count = (int64_t *)(d + o_cnt);
+		od.dd_w = (double *)(d + o_ddw);
+		od.spd = (double *)(d + o_sp);
+		od.scd = (double *)(d + o_sc);
+		od.dd_jk_count = J > 0 ? (int64_t *)(d + o_jcnt) : nullptr;
+		od.dd_jk_w = J > 0 ? (double *)(d + o_jddw) : nullptr;
+		od.spd_jk = J > 0 ? (double *)(d + o_jsp) : nullptr;
+		od.stats = (uint64_t *)(d + o_stats);
+		rc = mia_paircount(params, &Dd, &Sd, shard, &od, d + o_ws, ws_bytes, (void *)st);
+	}
+#define D2H(dst, off, bytes)                                                                         \
+	if ((dst) && (bytes) > 0 && rc == MIA_OK) {                                                      \
+		cudaError_t _e = cudaMemcpyAsync((dst), d + (off), (bytes), cudaMemcpyDeviceToHost, st);     \
+		if (_e != cudaSuccess) rc = (int)_e;                                                         \
+	}
+	D2H(out_h->dd_count, o_cnt, sizeof(int64_t) * nb);
+	D2H(out_h->dd_w, o_ddw, sizeof(double) * nb);
+	D2H(out_h->spd, o_sp, sizeof(double) * nb);
+	D2H(out_h->scd, o_sc, sizeof(double) * nb);
+	D2H(out_h->dd_jk_count, o_jcnt, sizeof(int64_t) * (size_t)J * nb);
+	D2H(out_h->dd_jk_w, o_jddw, sizeof(double) * (size_t)J * nb);
+	D2H(out_h->spd_jk, o_jsp, sizeof(double) * (size_t)J * nb);
+	D2H(out_h->stats, o_stats, sizeof(uint64_t) * 8);
+#undef D2H
+	cudaError_t se = cudaStreamSynchronize(st);
+	if (rc == MIA_OK && se != cudaSuccess) rc = (int)se;
+	cudaStreamDestroy(st);
+	cudaFree(d);
+	return rc;
+}
+
+int mia_combine_partials_f64(const double *parts, int32_t n_parts, int64_t n_values, double *out, void *stream) {
+	if (!parts || !out || n_parts < 1 || n_values < 0) return MIA_ERR_ARG;
+	if (n_values == 0) return MIA_OK;
+	k_combine<<<(unsigned)((n_values + 255) / 256), 256, 0, (cudaStream_t)stream>>>(parts, n_parts, n_values, out);
+	MIA_CUDA_CHECK(cudaGetLastError());
+	return MIA_OK;
+}
+
+}  // extern "C"

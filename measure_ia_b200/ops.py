@@ -1,0 +1,168 @@
+"""PyTorch custom ops over the C ABI of libmia_b200.so (include/mia_b200.h).
+
+``torch.ops.measure_ia_b200.paircount`` is the operator the host mirror (``box.py``) calls; it hands raw device
+pointers and the current CUDA stream to ``mia_paircount`` through ctypes.  There is NO CPU implementation and no
+fallback: a missing library or a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import List, Optional
+
+import torch
+
+from .build import LIB_PATH
+
+MIA_ABI_VERSION = 1
+GEOM_RPPI, GEOM_RMU = 0, 1
+KERNEL_AUTO, KERNEL_GENERAL, KERNEL_TILED = 0, 1, 2
+KERNEL_NAMES = {"auto": KERNEL_AUTO, "general": KERNEL_GENERAL, "tiled": KERNEL_TILED}
+
+
+class MiaParams(ctypes.Structure):
+	_fields_ = [
+		("abi_version", ctypes.c_int32), ("geometry", ctypes.c_int32), ("n_r", ctypes.c_int32), ("n_2", ctypes.c_int32),
+		("los", ctypes.c_int32), ("periodic", ctypes.c_int32), ("num_jk", ctypes.c_int32), ("kernel", ctypes.c_int32),
+		("boxsize", ctypes.c_double), ("r_search", ctypes.c_double), ("rp2_cut", ctypes.c_double),
+		("r2_thr_host", ctypes.c_void_p), ("thr2_host", ctypes.c_void_p),
+	]
+
+
+class MiaSample(ctypes.Structure):
+	_fields_ = [("n", ctypes.c_int64), ("pos", ctypes.c_void_p), ("weight", ctypes.c_void_p), ("jk", ctypes.c_void_p),
+				("axis", ctypes.c_void_p), ("e", ctypes.c_void_p)]
+
+
+class MiaHist(ctypes.Structure):
+	_fields_ = [("dd_count", ctypes.c_void_p), ("dd_w", ctypes.c_void_p), ("spd", ctypes.c_void_p),
+				("scd", ctypes.c_void_p), ("dd_jk_count", ctypes.c_void_p), ("dd_jk_w", ctypes.c_void_p),
+				("spd_jk", ctypes.c_void_p), ("stats", ctypes.c_void_p)]
+
+
+class MiaShard(ctypes.Structure):
+	_fields_ = [("index", ctypes.c_int32), ("count", ctypes.c_int32)]
+
+
+EXPORTS = ("mia_strerror", "mia_abi_version", "mia_workspace_bytes", "mia_paircount", "mia_paircount_host",
+		   "mia_combine_partials_f64")
+
+_lib = None
+
+
+def load_library():
+	"""dlopen libmia_b200.so; raises (never falls back) when it is missing or has the wrong ABI."""
+	global _lib
+	if _lib is None:
+		if not os.path.exists(LIB_PATH):
+			raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+							   "(there is no CPU fallback for the pair-count operator)")
+		lib = ctypes.CDLL(LIB_PATH)
+		lib.mia_strerror.restype = ctypes.c_char_p
+		lib.mia_strerror.argtypes = [ctypes.c_int]
+		lib.mia_abi_version.restype = ctypes.c_int
+		lib.mia_workspace_bytes.restype = ctypes.c_size_t
+		lib.mia_workspace_bytes.argtypes = [ctypes.POINTER(MiaParams), ctypes.c_int64, ctypes.c_int64]
+		lib.mia_paircount.restype = ctypes.c_int
+		lib.mia_paircount.argtypes = [ctypes.POINTER(MiaParams), ctypes.POINTER(MiaSample), ctypes.POINTER(MiaSample),
+									  MiaShard, ctypes.POINTER(MiaHist), ctypes.c_void_p, ctypes.c_size_t,
+									  ctypes.c_void_p]
+		lib.mia_paircount_host.restype = ctypes.c_int
+		lib.mia_paircount_host.argtypes = [ctypes.POINTER(MiaParams), ctypes.POINTER(MiaSample),
+										   ctypes.POINTER(MiaSample), MiaShard, ctypes.POINTER(MiaHist), ctypes.c_int]
+		lib.mia_combine_partials_f64.restype = ctypes.c_int
+		lib.mia_combine_partials_f64.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p,
+												 ctypes.c_void_p]
+		if lib.mia_abi_version() != MIA_ABI_VERSION:
+			raise RuntimeError("libmia_b200.so ABI version mismatch; rebuild")
+		_lib = lib
+	return _lib
+
+
+def check(rc):
+	if rc != 0:
+		raise RuntimeError(f"libmia_b200: {load_library().mia_strerror(rc).decode()} (code {rc})")
+
+
+def make_params(geometry, n_r, n_2, los, periodic, num_jk, kernel, boxsize, r_search, rp2_cut, r2_thr, thr2):
+	"""r2_thr / thr2: CPU float64 tensors (kept alive by the caller for the duration of the call)."""
+	assert r2_thr.dtype == torch.float64 and thr2.dtype == torch.float64 and not r2_thr.is_cuda and not thr2.is_cuda
+	assert r2_thr.numel() == n_r + 1 and thr2.numel() == n_2 + 1
+	return MiaParams(MIA_ABI_VERSION, geometry, n_r, n_2, los, 1 if periodic else 0, num_jk, kernel, boxsize, r_search,
+					 rp2_cut, r2_thr.data_ptr(), thr2.data_ptr())
+
+
+def _dev_ptr(t: Optional[torch.Tensor], dtype, shape_tail=None):
+	if t is None:
+		return None
+	if not t.is_cuda:
+		raise RuntimeError("measure_ia_b200::paircount needs CUDA tensors (no CPU fallback)")
+	if t.dtype != dtype or not t.is_contiguous():
+		raise RuntimeError(f"expected a contiguous {dtype} tensor, got {t.dtype} (contiguous={t.is_contiguous()})")
+	return t.data_ptr()
+
+
+@torch.library.custom_op("measure_ia_b200::paircount", mutates_args=())
+def paircount(pos_d: torch.Tensor, weight_d: Optional[torch.Tensor], jk_d: Optional[torch.Tensor],
+			  pos_s: torch.Tensor, weight_s: Optional[torch.Tensor], jk_s: Optional[torch.Tensor],
+			  axis: torch.Tensor, e: torch.Tensor, r2_thr: torch.Tensor, thr2: torch.Tensor, geometry: int, los: int,
+			  periodic: bool, num_jk: int, boxsize: float, r_search: float, rp2_cut: float, kernel: int,
+			  shard_index: int, shard_count: int) -> List[torch.Tensor]:
+	"""Binned pair sums of the position sample ``*_d`` around the shape sample ``*_s``.
+
+	Returns [dd_count i64 (n_r,n_2), dd_w, spd, scd, dd_jk_count i64 (num_jk,n_r,n_2), dd_jk_w, spd_jk, stats u64->i64 (8)].
+	Semantics: include/mia_b200.h; reference seam: measure_w_box_jk.py:646 / measure_m_box_jk.py:682.
+	"""
+	lib = load_library()
+	dev = pos_d.device
+	n_r, n_2 = r2_thr.numel() - 1, thr2.numel() - 1
+	params = make_params(geometry, n_r, n_2, los, periodic, num_jk, kernel, boxsize, r_search, rp2_cut, r2_thr, thr2)
+	f64, i32, i64 = torch.float64, torch.int32, torch.int64
+	D = MiaSample(pos_d.shape[0], _dev_ptr(pos_d, f64), _dev_ptr(weight_d, f64), _dev_ptr(jk_d, i32), None, None)
+	S = MiaSample(pos_s.shape[0], _dev_ptr(pos_s, f64), _dev_ptr(weight_s, f64), _dev_ptr(jk_s, i32),
+				  _dev_ptr(axis, f64), _dev_ptr(e, f64))
+	with torch.cuda.device(dev):
+		dd_count = torch.empty((n_r, n_2), dtype=i64, device=dev)
+		dd_w, spd, scd = (torch.empty((n_r, n_2), dtype=f64, device=dev) for _ in range(3))
+		jk_count = torch.empty((num_jk, n_r, n_2), dtype=i64, device=dev)
+		jk_w, spd_jk = (torch.empty((num_jk, n_r, n_2), dtype=f64, device=dev) for _ in range(2))
+		stats = torch.zeros(8, dtype=i64, device=dev)
+		ws_bytes = lib.mia_workspace_bytes(ctypes.byref(params), D.n, S.n)
+		if ws_bytes == 0:
+			raise RuntimeError("libmia_b200: mia_workspace_bytes rejected the parameters")
+		ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+		H = MiaHist(dd_count.data_ptr(), dd_w.data_ptr(), spd.data_ptr(), scd.data_ptr(),
+					jk_count.data_ptr() if num_jk else None, jk_w.data_ptr() if num_jk else None,
+					spd_jk.data_ptr() if num_jk else None, stats.data_ptr())
+		stream = torch.cuda.current_stream(dev).cuda_stream
+		rc = lib.mia_paircount(ctypes.byref(params), ctypes.byref(D), ctypes.byref(S), MiaShard(shard_index, shard_count),
+							   ctypes.byref(H), ws.data_ptr(), ws_bytes, stream)
+	check(rc)
+	return [dd_count, dd_w, spd, scd, jk_count, jk_w, spd_jk, stats]
+
+
+@paircount.register_fake
+def _(pos_d, weight_d, jk_d, pos_s, weight_s, jk_s, axis, e, r2_thr, thr2, geometry, los, periodic, num_jk, boxsize,
+	  r_search, rp2_cut, kernel, shard_index, shard_count):
+	n_r, n_2 = r2_thr.numel() - 1, thr2.numel() - 1
+	f = lambda *s, dt=torch.float64: torch.empty(s, dtype=dt, device=pos_d.device)  # noqa: E731
+	return [f(n_r, n_2, dt=torch.int64), f(n_r, n_2), f(n_r, n_2), f(n_r, n_2), f(num_jk, n_r, n_2, dt=torch.int64),
+			f(num_jk, n_r, n_2), f(num_jk, n_r, n_2), f(8, dt=torch.int64)]
+
+
+def paircount_host(params: MiaParams, D: MiaSample, S: MiaSample, H: MiaHist, shard=(0, 1), device=0):
+	"""``mia_paircount_host``: host pointers in, host pointers out (what a non-torch binding would call)."""
+	check(load_library().mia_paircount_host(ctypes.byref(params), ctypes.byref(D), ctypes.byref(S),
+											MiaShard(shard[0], shard[1]), ctypes.byref(H), device))
+
+
+def combine_partials(parts: torch.Tensor) -> torch.Tensor:
+	"""Fixed-order sum over dim 0 of a [n_parts, ...] float64 CUDA tensor (measure_w_box_jk.py:775-780)."""
+	if not parts.is_cuda or parts.dtype != torch.float64:
+		raise RuntimeError("combine_partials needs a float64 CUDA tensor")
+	parts = parts.contiguous()
+	out = torch.empty(parts.shape[1:], dtype=torch.float64, device=parts.device)
+	with torch.cuda.device(parts.device):
+		check(load_library().mia_combine_partials_f64(parts.data_ptr(), parts.shape[0], out.numel(), out.data_ptr(),
+													  torch.cuda.current_stream(parts.device).cuda_stream))
+	return out

@@ -1,0 +1,206 @@
+"""GPU parity tests proper: the CUDA path (through the torch op and through the raw C ABI) against
+(a) outputs of the unmodified reference (tests/golden/ref_*.npz), (b) the CPU oracle on the same seeded inputs, and
+(c) size-independent properties at larger sizes."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import parity_util as pu
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = ["general", "auto"]
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+	import torch
+	assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+	from measure_ia_b200 import ops
+	ops.load_library()
+	return torch
+
+
+def read_all(path):
+	from measure_ia_b200 import h5lite
+	f = h5lite.File(path, "r")
+	out = {}
+
+	def walk(g, pre):
+		for k, v in g.items():
+			if isinstance(v, h5lite.Group):
+				walk(v, pre + k + "/")
+			else:
+				out[pre + k] = v[...]
+	walk(f, "")
+	f.close()
+	return out
+
+
+def run_box(meta, data, masks, kw, out, kernel):
+	from measure_ia_b200 import MeasureIABox
+	kw = dict(kw)
+	kind = kw.pop("kind")
+	kw.pop("variant", None)
+	num_jk = kw.pop("num_jk", 0)
+	ellipticity = kw.pop("ellipticity", "distortion")
+	box = MeasureIABox(data, out, None, None, list(kw.pop("separation_limits", (0.1, 20.0))), kw.pop("num_bins_r", 8),
+					   kw.pop("num_bins_pi", 20), kw.pop("pi_max", None), meta["catalogue"]["boxsize"],
+					   kw.pop("periodicity", True))
+	assert not kw, kw
+	box.kernel = kernel
+	run = box.measure_xi_w if kind == "w" else box.measure_xi_multipoles
+	run("All", "both", num_jk=num_jk, temp_file_path=False, masks=masks, ellipticity=ellipticity)
+	return box
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("name", pu.fixture_names())
+def test_reference_fixture(torch_cuda, tmp_path, name, kernel):
+	"""Whole API path on the GPU vs the files the unmodified reference wrote for the same inputs."""
+	meta, want = pu.load_fixture(name)
+	data, masks, kw = pu.rebuild_inputs(meta)
+	if kw.get("variant") == "brute":
+		want = {k: v for k, v in want.items() if not k.endswith("_sigmasq")}
+	out = str(tmp_path / "out.hdf5")
+	box = run_box(meta, data, masks, kw, out, kernel)
+	got = read_all(out)
+	pu.assert_datasets_match(got, want, exact_counts=not meta["catalogue"].get("weights"), label=f"{name}[{kernel}]: ")
+	dd_key = [k for k in want if k.endswith("xi_gg/All_DD")][0]
+	if not meta["catalogue"].get("weights"):
+		assert box.last_stats["binned"] == int(want[dd_key].sum())
+		assert np.array_equal(box.last_result["count"], want[dd_key].astype(np.int64))
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("geom,kind", [("rppi", "w"), ("rmu", "multipoles")])
+def test_against_oracle_100k(torch_cuda, oracle, tmp_path, geom, kind, kernel):
+	"""N = 1e5 (3e8 / 4e7 pairs): far beyond what the Python reference can do; oracle = C restatement."""
+	from measure_ia_b200 import MeasureIABox
+	from measure_ia_b200.synthetic import uniform_box
+	data = uniform_box(100000, 205.0, seed=77, weights=(geom == "rmu"))
+	out = str(tmp_path / "o.hdf5")
+	box = MeasureIABox(data, out, boxsize=205.0, num_bins_r=10, num_bins_pi=8)
+	box.kernel = kernel
+	(box.measure_xi_w if kind == "w" else box.measure_xi_multipoles)("All", "both", num_jk=27, temp_file_path=False)
+	want = oracle.measure(data, kind, num_jk=27, boxsize=205.0, num_bins_r=10, num_bins_pi=8,
+						  n_threads=oracle.max_threads())
+	count = want.pop("__meta__/count")
+	want.pop("__meta__/n_tested")
+	assert np.array_equal(box.last_result["count"], count)
+	pu.assert_datasets_match(read_all(out), want, exact_counts=(geom == "rppi"), label=f"{geom}[{kernel}]: ")
+
+
+def _host_call(torch, oracle, data, geom, num_jk, boxsize, n_r, n_2, kernel=0, shard=(0, 1)):
+	"""mia_paircount_host through ctypes only (host numpy buffers in / out)."""
+	from measure_ia_b200 import MeasureIABox, ops
+	box = MeasureIABox(data, None, boxsize=boxsize, num_bins_r=n_r, num_bins_pi=n_2)
+	pos, pos_s, axis, e, w, w_s, same = box._prepare(None, "distortion")
+	L = round(num_jk ** (1 / 3)) if num_jk else 0
+	jk = box._jackknife_labels(pos, L).astype(np.int32) if num_jk else None
+	r2_thr, thr2, rp2_cut, _ = box._thresholds_for(geom, None)
+	P = ops.MiaParams(1, 0 if geom == "rppi" else 1, n_r, n_2, int(data["LOS"]), 1, num_jk, kernel, boxsize,
+					  float(box.r_bins[-1]), rp2_cut, r2_thr.ctypes.data, thr2.ctypes.data)
+	ptr = lambda a: a.ctypes.data if a is not None else None  # noqa: E731
+	D = ops.MiaSample(len(pos), ptr(pos), ptr(w), ptr(jk), None, None)
+	S = ops.MiaSample(len(pos_s), ptr(pos_s), ptr(w_s), ptr(jk), ptr(axis), ptr(e))
+	nb = (n_r, n_2)
+	o = dict(dd_count=np.zeros(nb, np.int64), dd_w=np.zeros(nb), spd=np.zeros(nb), scd=np.zeros(nb),
+			 dd_jk_count=np.zeros((num_jk,) + nb, np.int64), dd_jk_w=np.zeros((num_jk,) + nb),
+			 spd_jk=np.zeros((num_jk,) + nb), stats=np.zeros(8, np.uint64))
+	H = ops.MiaHist(*[ptr(o[k]) if o[k].size else None for k in ("dd_count", "dd_w", "spd", "scd", "dd_jk_count",
+																   "dd_jk_w", "spd_jk", "stats")])
+	ops.paircount_host(P, D, S, H, shard=shard, device=0)
+	R, _ = box._responsivity(w_s, e)
+	ref = oracle.paircount(geom, pos, w, jk, pos_s, axis, e, w_s, jk, box.r_bins, (0.1, 20.0),
+						   box.pi_bins if geom == "rppi" else box.mu_r_bins, boxsize, True, int(data["LOS"]), 1.0,
+						   num_box=num_jk, n_threads=oracle.max_threads())
+	return o, ref
+
+
+@pytest.mark.parametrize("geom", ["rppi", "rmu"])
+def test_c_abi_host_entry(torch_cuda, oracle, geom):
+	from measure_ia_b200.synthetic import uniform_box
+	data = uniform_box(20000, 150.0, seed=5, weights=True, los=1)
+	o, ref = _host_call(torch_cuda, oracle, data, geom, 8, 150.0, 6, 12)
+	assert np.array_equal(o["dd_count"], ref["count"])
+	assert int(o["stats"][1]) == int(ref["count"].sum())
+	for a, b in ((o["dd_w"], ref["DD"]), (o["spd"], ref["SpD"]), (o["scd"], ref["ScD"]), (o["dd_jk_w"], ref["DD_jk"]),
+				 (o["spd_jk"], ref["SpD_jk"])):
+		np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-11 * np.abs(b).max())
+
+
+def test_shards_sum_to_whole(torch_cuda, oracle):
+	"""Multi-GPU partitioning property on one GPU: the shards of the shape sample add up to the unsharded result."""
+	from measure_ia_b200.synthetic import uniform_box
+	data = uniform_box(30000, 205.0, seed=9)
+	whole, _ = _host_call(torch_cuda, oracle, data, "rppi", 27, 205.0, 10, 8)
+	parts = [_host_call(torch_cuda, oracle, data, "rppi", 27, 205.0, 10, 8, shard=(i, 3))[0] for i in range(3)]
+	assert np.array_equal(sum(p["dd_count"] for p in parts), whole["dd_count"])
+	assert np.array_equal(sum(p["dd_jk_count"] for p in parts), whole["dd_jk_count"])
+	np.testing.assert_allclose(sum(p["spd"] for p in parts), whole["spd"], rtol=1e-10, atol=1e-9)
+
+
+def test_exact_quarter_scaling_with_half_weights(torch_cuda, tmp_path):
+	"""Reference tests/test_weights.py:34-35: weights 0.5 scale DD and w_g+ by EXACTLY 1/4 (needs run-to-run
+	deterministic accumulation order), covariances by 1/16."""
+	from measure_ia_b200 import MeasureIABox
+	from measure_ia_b200.synthetic import uniform_box
+	data = uniform_box(20000, 205.0, seed=31)
+	out = str(tmp_path / "w.hdf5")
+	box = MeasureIABox(data, out, boxsize=205.0, num_bins_r=10, num_bins_pi=8)
+	box.measure_xi_w("A", "both", 8, temp_file_path=False)
+	box.data["weight"] = np.array([0.5] * 20000)
+	box.data["weight_shape_sample"] = np.array([0.5] * 20000)
+	box.measure_xi_w("B", "both", 8, temp_file_path=False)
+	g = read_all(out)
+	assert np.array_equal(g["w/xi_gg/A_DD"], 4 * g["w/xi_gg/B_DD"])
+	if box.last_stats["kernel"] == 2:  # the tiled kernel accumulates in a fixed order
+		assert np.array_equal(g["w_g_plus/A"], 4 * g["w_g_plus/B"])
+	np.testing.assert_allclose(g["w_g_plus/A"], 4 * g["w_g_plus/B"], rtol=1e-12)
+	np.testing.assert_allclose(g["w_g_plus/A_jackknife_cov_8"], 16 * g["w_g_plus/B_jackknife_cov_8"], rtol=1e-9)
+	np.testing.assert_allclose(g["w_gg/A_jackknife_cov_8"], 16 * g["w_gg/B_jackknife_cov_8"], rtol=1e-9)
+
+
+def test_corr_type_invariance_and_symmetry(torch_cuda, tmp_path):
+	"""Reference tests/test_w_sim_internal_consistency.py:35-54: 'g+', 'gg' and 'both' give identical numbers; plus the
+	auto-correlation symmetry DD(r_p, Pi) == DD(r_p, -Pi)."""
+	from measure_ia_b200 import MeasureIABox
+	from measure_ia_b200.synthetic import uniform_box
+	data = uniform_box(30000, 205.0, seed=41)
+	out = str(tmp_path / "c.hdf5")
+	box = MeasureIABox(data, out, boxsize=205.0, num_bins_r=10, num_bins_pi=8)
+	box.measure_xi_w("both", "both", 0, temp_file_path=False)
+	box.measure_xi_w("gp", "g+", 0, temp_file_path=False)
+	box.measure_xi_w("gg", "gg", 0, temp_file_path=False)
+	g = read_all(out)
+	assert np.array_equal(g["w_gg/both"], g["w_gg/gg"]) or np.allclose(g["w_gg/both"], g["w_gg/gg"], rtol=1e-13)
+	np.testing.assert_allclose(g["w_g_plus/both"], g["w_g_plus/gp"], rtol=1e-10, atol=1e-14)
+	assert "w_gg/gp" not in g and "w_g_plus/gg" not in g
+	dd = g["w/xi_gg/both_DD"]
+	assert np.array_equal(dd, dd[:, ::-1])
+
+
+def test_out_of_box_coordinates_fail_loudly(torch_cuda):
+	from measure_ia_b200 import MeasureIABox
+	from measure_ia_b200.synthetic import uniform_box
+	data = uniform_box(1000, 100.0, seed=3)
+	data["Position"] = data["Position"].copy()
+	data["Position"][7, 1] = 100.0  # == boxsize: scipy's periodic KDTree raises in the reference
+	box = MeasureIABox(data, None, boxsize=100.0)
+	with pytest.raises(RuntimeError, match="outside"):
+		box.measure_xi_w("x", "both", 0, temp_file_path=False)
+
+
+def test_empty_and_tiny_inputs(torch_cuda, oracle, tmp_path):
+	from measure_ia_b200 import MeasureIABox
+	from measure_ia_b200.synthetic import uniform_box
+	for n in (1, 2, 33):
+		data = uniform_box(n, 50.0, seed=n)
+		box = MeasureIABox(data, str(tmp_path / f"t{n}.hdf5"), boxsize=50.0, num_bins_r=4, num_bins_pi=4)
+		for kind, run in (("w", box.measure_xi_w), ("multipoles", box.measure_xi_multipoles)):
+			run("All", "both", 8, temp_file_path=False)
+			want = oracle.measure(data, kind, num_jk=8, boxsize=50.0, num_bins_r=4, num_bins_pi=4)
+			assert np.array_equal(box.last_result["count"], want["__meta__/count"])
