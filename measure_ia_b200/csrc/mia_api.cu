@@ -178,12 +178,32 @@ __global__ void k_finalize(const unsigned long long *__restrict__ cnt, const dou
 	out.scd[b] = t_sc;
 }
 
+// Sum the accumulator copies (one per warp of the tiled kernel) into copy 0, in copy order: fixed => reproducible.
+__global__ void k_reduce_partials(unsigned long long *__restrict__ cnt, double *__restrict__ ddw, double *__restrict__ sp,
+								  double *__restrict__ sc, int n_partials, size_t n_el) {
+	const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+	if (e >= n_el) return;
+	unsigned long long c = 0;
+	double a = 0.0, b = 0.0, d = 0.0;
+	for (int p = 0; p < n_partials; p++) {
+		const size_t i = (size_t)p * n_el + e;
+		c += cnt[i];
+		a += ddw[i];
+		b += sp[i];
+		d += sc[i];
+	}
+	cnt[e] = c;
+	ddw[e] = a;
+	sp[e] = b;
+	sc[e] = d;
+}
+
 __global__ void k_copy_stats(const unsigned long long *in, uint64_t *out, unsigned long long kernel,
 							 unsigned long long cells, unsigned long long tasks) {
 	if (threadIdx.x < 4) out[threadIdx.x] = in[threadIdx.x];
 	if (threadIdx.x == 4) out[4] = kernel;
 	if (threadIdx.x == 5) out[5] = cells;
-	if (threadIdx.x == 6) out[6] = tasks;
+	if (threadIdx.x == 6) out[6] = tasks ? tasks : in[6];
 	if (threadIdx.x == 7) out[7] = 0;
 }
 
@@ -279,7 +299,7 @@ int mia_paircount(const mia_params *params, const mia_sample *D, const mia_sampl
 	k_cell_start<<<(unsigned)((nD + 1 + T - 1) / T), T, 0, st>>>(sc.keys_out, nD, pl.g.jk_rows, ncell, cell_start);
 	MIA_CUDA_CHECK(cudaGetLastError());
 	if (pl.kernel == MIA_KERNEL_TILED) {
-		rc = tiled_prepare_candidates(pl.tiled, pl.g, P, sc.keys_out, cand, nD, cell_start, ws + pl.off_tiled, st);
+		rc = tiled_prepare_candidates(pl.tiled, pl.g, P, sc.keys_out, cand, cand_jk, nD, cell_start, ws + pl.off_tiled, st);
 		if (rc) return rc;
 	}
 	// ---- shape sample -> sorted primaries ---------------------------------------------------------------------------
@@ -321,15 +341,19 @@ int mia_paircount(const mia_params *params, const mia_sample *D, const mia_sampl
 			n_tasks = blocks;
 		}
 	} else {
-		rc = tiled_launch(pl.tiled, pl.g, P, G, prim, prim_cell_start, nS, s_begin, s_end, A, ws + pl.off_tiled, flags,
-						  &n_tasks, st);
+		const bool unit_w = (D->weight == nullptr && S->weight == nullptr);
+		rc = tiled_launch(pl.tiled, pl.g, P, G, prim, prim_cell_start, nS, unit_w, shard, A, ws + pl.off_tiled, flags, st);
 		if (rc) return rc;
+		if (pl.n_partials > 1) {
+			const size_t n_el = (size_t)pl.rows * pl.nb;
+			k_reduce_partials<<<(unsigned)((n_el + 127) / 128), 128, 0, st>>>(A.cnt, A.ddw, A.sp, A.sc, pl.n_partials, n_el);
+			MIA_CUDA_CHECK(cudaGetLastError());
+		}
 	}
 
 	// ---- fixed-order final reduction ----------------------------------------------------------------------------------
 	const int J = params->num_jk > 0 ? params->num_jk : 1;
-	k_finalize<<<(pl.nb + 127) / 128, 128, 0, st>>>(A.cnt, A.ddw, A.sp, A.sc, pl.n_partials, J, pl.nb, params->num_jk,
-													*out);
+	k_finalize<<<(pl.nb + 127) / 128, 128, 0, st>>>(A.cnt, A.ddw, A.sp, A.sc, 1, J, pl.nb, params->num_jk, *out);
 	MIA_CUDA_CHECK(cudaGetLastError());
 	if (out->stats) {
 		k_copy_stats<<<1, 32, 0, st>>>(A.stats, out->stats, (unsigned long long)pl.kernel, (unsigned long long)ncell,

@@ -1,16 +1,1000 @@
-// mia_tiled.cuh -- placeholder until the tiled kernel lands (plan_tiled returns false => general kernel).
+// mia_tiled.cuh -- the TILED (r_p, Pi) pair kernel for sm_100a: the fast, bit-reproducible path.
+//
+// Replaces the hot loop of the reference, src/measureia/measure_w_box_jk.py:387-461 (and measure_w_box.py:313-365).
+//
+// Idea ("windowed private histograms"):
+//   * one thread owns one shape galaxy (registers); a CTA owns TP consecutive cell-sorted shape galaxies of one grid
+//     COLUMN (a cell of the two projected axes spanning the whole line of sight);
+//   * position galaxies are staged cell by cell into shared memory with 1-D bulk (TMA) copies -- a cell is one
+//     contiguous 32-byte-per-galaxy range of the sorted catalogue -- double buffered behind an mbarrier, and every
+//     thread of the CTA reads the same candidate (shared-memory broadcast);
+//   * the grid is cut along the line of sight into slabs thinner than one Pi bin.  For a given shape galaxy, all
+//     candidates of one slab fall into at most TWO Pi bins, and all candidates of one staged cell carry ONE jackknife
+//     label.  So between two flushes a thread only ever touches 2 * n_r histogram slots: they are thread-private
+//     shared-memory words, updated with plain loads and stores -- no atomics anywhere in the pair loop;
+//   * at a flush (slab change or candidate-label change) the warp reduces its slots with shuffles in a fixed order and
+//     adds them to its own accumulator copy in HBM (rows A[jk_shape], B[jk_position]); a final kernel sums the copies
+//     in a fixed order.  Tasks are assigned to CTAs by a prefix sum of estimated work.  => results are identical from
+//     run to run, which the reference's exact-scaling test (tests/test_weights.py:34-35) needs.
+//
+// Exactness: separations are formed with the reference's operation sequence (__d*_rn, no contraction); range and bin
+// decisions are comparisons against the host-calibrated thresholds; the only approximate arithmetic is the VALUE of
+// e+ / ex (reciprocal by Newton iteration, FMA), accurate to ~1e-16, far inside the 1e-10 contract.  Pairs whose |cos|
+// is within 1e-12 of 1 re-evaluate cos with the reference's sequence to apply its NaN rule (measure_w_box_jk.py:416).
 #pragma once
+#include <cub/cub.cuh>
 #include "mia_common.cuh"
 #include "mia_grid.cuh"
 
 namespace mia {
-struct TiledConfig { int n_partials; };
-inline bool plan_tiled(const mia_params *, int64_t, int64_t, GridDims &, int &, int &, int &, TiledConfig &) { return false; }
-inline size_t tiled_workspace_bytes(const TiledConfig &, const GridDims &, int64_t, int64_t) { return 0; }
-inline int tiled_prepare_candidates(const TiledConfig &, const GridDims &, const DevParams &, const uint32_t *, const Cand *,
-									int64_t, const int64_t *, void *, cudaStream_t) { return MIA_ERR_UNSUPPORTED; }
-inline int tiled_launch(const TiledConfig &, const GridDims &, const DevParams &, const Grid &, const Prim *, const int64_t *,
-						int64_t, int64_t, int64_t, const Accum &, void *, int *, unsigned long long *, cudaStream_t) {
-	return MIA_ERR_UNSUPPORTED;
+
+constexpr int TP = 128;          // threads = shape galaxies per CTA
+constexpr int TW = TP / 32;      // warps per CTA
+constexpr int CH = 128;          // candidates per staged chunk
+constexpr int MAX_NEIGH = 128;   // neighbour columns per task
+constexpr int LUT_SIZE = 256;
+constexpr int MAX_SLOTS = 32;    // 2 * n_r <= 32
+constexpr int SLOTS_PER_SM = 6;    // work slots (= CTAs launched) per SM; fixed so that results do not depend on occupancy
+
+struct LutEntry {
+	double thr;  // threshold inside this entry's range of s (or +inf)
+	int base;    // r-bin of the smallest s of the entry
+	int pad;
+};
+
+struct CellInfo {
+	double umin, umax, vmin, vmax;
+	int label;  // jackknife label of the first candidate
+	int nlab;   // number of label runs in the cell (1 = uniform)
+};
+
+struct Desc {  // one neighbour cell of the current slab (shared memory)
+	long long start;
+	int n, label, nlab, pad;
+	double umin, umax, vmin, vmax;
+};
+
+struct TiledConfig {
+	int n_partials;  // accumulator copies = work slots * warps per CTA
+	int n_slots;
+	int num_sms;
+	int nz;
+	int n_side;
+	int lut_hi0, lut_shift, lut_n;
+	int max_tasks;
+	LutEntry lut[LUT_SIZE];
+};
+
+struct TiledArgs {
+	DevParams P;
+	const Cand *cand;
+	const int32_t *cand_jk;
+	const int64_t *cell_start;
+	const CellInfo *cinfo;
+	const double *slab_lo, *slab_hi;
+	const Prim *prim;
+	const int32_t *task_col;
+	const int64_t *task_first;
+	const int32_t *task_n;
+	const unsigned long long *task_cost, *task_cum;
+	const int32_t *n_tasks;
+	const LutEntry *lut;
+	int lut_hi0, lut_shift, lut_n;
+	Accum A;
+	int nz, n_side, G, shard_index, shard_count, max_tasks;
+	int *flags;
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// planning (host)
+// ------------------------------------------------------------------------------------------------------------------
+inline int hi_word(double x) {
+	long long b;
+	memcpy(&b, &x, 8);
+	return (int)(b >> 32);
 }
+
+inline double from_hi_lo(int hi, unsigned lo) {
+	long long b = ((long long)hi << 32) | lo;
+	double x;
+	memcpy(&x, &b, 8);
+	return x;
+}
+
+// Look-up table over the high word of s = r_p^2: entry e covers hi in [hi0 + e*2^shift, hi0 + (e+1)*2^shift).
+inline bool build_lut(const mia_params *p, TiledConfig &cfg) {
+	const double *thr = p->r2_thr_host;
+	const int n_r = p->n_r;
+	if (!(thr[0] > 0.0) || !(thr[n_r] > thr[0]) || !std::isfinite(thr[n_r])) return false;
+	const int hi0 = hi_word(thr[0]), hi1 = hi_word(thr[n_r]);
+	int shift = 0;
+	while ((((long long)hi1 - hi0) >> shift) + 1 > LUT_SIZE) shift++;
+	const int n = (int)((((long long)hi1 - hi0) >> shift) + 1);
+	for (int e = 0; e < n; e++) {
+		const double lowest = from_hi_lo(hi0 + (e << shift), 0u);
+		const double next_lowest = from_hi_lo(hi0 + ((e + 1) << shift), 0u);
+		int base = 0, inside = 0;
+		double t_in = INFINITY;
+		for (int b = 1; b < n_r; b++) {
+			if (thr[b] <= lowest) base++;
+			else if (thr[b] < next_lowest) {
+				inside++;
+				t_in = thr[b];
+			}
+		}
+		if (inside > 1) return false;  // bins finer than the table: leave it to the general kernel
+		cfg.lut[e].thr = t_in;
+		cfg.lut[e].base = base;
+		cfg.lut[e].pad = 0;
+	}
+	for (int e = n; e < LUT_SIZE; e++) cfg.lut[e] = LutEntry{INFINITY, n_r - 1, 0};
+	cfg.lut_hi0 = hi0;
+	cfg.lut_shift = shift;
+	cfg.lut_n = n;
+	return true;
+}
+
+inline size_t tiled_smem_bytes(int n_r, bool unit_w) {
+	const size_t fixed = sizeof(Cand) * 2 * CH + sizeof(LutEntry) * LUT_SIZE + sizeof(Desc) * MAX_NEIGH +
+						 sizeof(int) * MAX_NEIGH * 2 + 256;
+	const size_t per_slot = (size_t)TP * (8 + 8 + 4 + (unit_w ? 0 : 8));
+	return fixed + per_slot * 2 * n_r;
+}
+
+inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g, int &ku, int &kv, int &kl,
+					   TiledConfig &cfg) {
+	if (p->geometry != MIA_GEOM_RPPI) return false;
+	if (2 * p->n_r > MAX_SLOTS) return false;
+	const double L = p->boxsize, reach = p->r_search * (1.0 + 1e-6);
+	// slabs thinner than the narrowest Pi bin
+	double dmin = INFINITY;
+	for (int b = 0; b < p->n_2; b++) {
+		const double lo = p->thr2_host[b], hi = p->thr2_host[b + 1];
+		if (!std::isfinite(lo) || !std::isfinite(hi) || !(hi > lo)) return false;
+		dmin = fmin(dmin, hi - lo);
+	}
+	const double nz_d = floor(L / (dmin * (1.0 - 1e-9))) + 1.0;
+	if (!(nz_d >= 1.0) || nz_d > 512.0) return false;
+	const int nz = (int)nz_d;
+	// columns: about a quarter of the search radius wide
+	int nc = (int)floor(L / (reach / 4.0));
+	if (nc > 2048) nc = 2048;
+	if (nc < 1) nc = 1;
+	const double cs = L / nc;
+	int k = (int)ceil(reach / cs);
+	if (k < 1) k = 1;
+	const bool all_mode = (2 * k + 1 >= nc);
+	if (all_mode ? ((long long)nc * nc > MAX_NEIGH) : ((2 * k + 1) * (2 * k + 1) > MAX_NEIGH)) return false;
+	if (!build_lut(p, cfg)) return false;
+	g.ncu = g.ncv = nc;
+	g.ncl = nz;
+	g.inv_cu = g.inv_cv = nc / L;
+	g.inv_cl = nz / L;
+	ku = kv = k;
+	kl = nz;  // all slabs
+	cfg.nz = nz;
+	int n_side = 1;
+	while ((n_side + 1) * (n_side + 1) * (n_side + 1) <= (p->num_jk > 0 ? p->num_jk : 1)) n_side++;
+	cfg.n_side = n_side;
+	int dev = 0, sms = 148;
+	if (cudaGetDevice(&dev) == cudaSuccess) {
+		int v = 0;
+		if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+	} else {
+		cudaGetLastError();
+	}
+	cfg.num_sms = sms;
+	cfg.n_slots = sms * SLOTS_PER_SM;
+	cfg.n_partials = cfg.n_slots * TW;
+	cfg.max_tasks = (int)(nS / TP + (int64_t)nc * nc + 1);
+	return true;
+}
+
+struct TiledWorkspace {
+	CellInfo *cinfo;
+	double *slab_lo, *slab_hi;
+	int32_t *col_chunks, *task_off, *task_col, *task_n, *n_tasks;
+	int64_t *task_first;
+	unsigned long long *task_cost, *task_cum;
+	LutEntry *lut;
+	void *cub_tmp;
+	size_t cub_bytes;
+	size_t total;
+};
+
+inline size_t tiled_cub_bytes(int64_t ncol, int max_tasks) {
+	size_t a = 0, b = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, a, (const int32_t *)nullptr, (int32_t *)nullptr, (int)(ncol + 1));
+	cub::DeviceScan::InclusiveSum(nullptr, b, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+								  max_tasks);
+	return a > b ? a : b;
+}
+
+inline TiledWorkspace carve_tiled(const TiledConfig &cfg, const GridDims &g, void *base) {
+	TiledWorkspace w;
+	size_t o = 0;
+	unsigned char *b = (unsigned char *)base;
+	auto take = [&](size_t bytes) {
+		size_t at = o;
+		o = (o + bytes + 255) / 256 * 256;
+		return b ? (void *)(b + at) : (void *)nullptr;
+	};
+	const int64_t ncell = g.ncell(), ncol = (int64_t)g.ncu * g.ncv;
+	w.cinfo = (CellInfo *)take(sizeof(CellInfo) * ncell);
+	w.slab_lo = (double *)take(sizeof(double) * cfg.nz);
+	w.slab_hi = (double *)take(sizeof(double) * cfg.nz);
+	w.col_chunks = (int32_t *)take(sizeof(int32_t) * (ncol + 1));
+	w.task_off = (int32_t *)take(sizeof(int32_t) * (ncol + 1));
+	w.task_col = (int32_t *)take(sizeof(int32_t) * cfg.max_tasks);
+	w.task_n = (int32_t *)take(sizeof(int32_t) * cfg.max_tasks);
+	w.n_tasks = (int32_t *)take(sizeof(int32_t) * 4);
+	w.task_first = (int64_t *)take(sizeof(int64_t) * cfg.max_tasks);
+	w.task_cost = (unsigned long long *)take(sizeof(unsigned long long) * cfg.max_tasks);
+	w.task_cum = (unsigned long long *)take(sizeof(unsigned long long) * cfg.max_tasks);
+	w.lut = (LutEntry *)take(sizeof(LutEntry) * LUT_SIZE);
+	w.cub_bytes = tiled_cub_bytes(ncol, cfg.max_tasks);
+	w.cub_tmp = take(w.cub_bytes);
+	w.total = o;
+	return w;
+}
+
+inline size_t tiled_workspace_bytes(const TiledConfig &cfg, const GridDims &g, int64_t, int64_t) {
+	return carve_tiled(cfg, g, nullptr).total;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// preparation kernels
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void k_cell_info(const Cand *__restrict__ cand, const int32_t *__restrict__ cand_jk,
+							const int64_t *__restrict__ cell_start, int64_t ncell, int nz, CellInfo *__restrict__ info,
+							unsigned long long *__restrict__ slab_lo, unsigned long long *__restrict__ slab_hi) {
+	const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+	if (c >= ncell) return;
+	const int64_t j0 = cell_start[c], j1 = cell_start[c + 1];
+	CellInfo ci;
+	ci.umin = ci.vmin = INFINITY;
+	ci.umax = ci.vmax = -INFINITY;
+	ci.label = -1;
+	ci.nlab = 0;
+	if (j1 > j0) {
+		double lmin = INFINITY, lmax = -INFINITY;
+		int prev = -1;
+		for (int64_t j = j0; j < j1; j++) {
+			const Cand q = cand[j];
+			ci.umin = fmin(ci.umin, q.u);
+			ci.umax = fmax(ci.umax, q.u);
+			ci.vmin = fmin(ci.vmin, q.v);
+			ci.vmax = fmax(ci.vmax, q.v);
+			lmin = fmin(lmin, q.l);
+			lmax = fmax(lmax, q.l);
+			const int lab = cand_jk[j];
+			if (j == j0) ci.label = lab;
+			if (lab != prev) ci.nlab++;
+			prev = lab;
+		}
+		const int s = (int)(c % nz);
+		// l >= 0, so the bit pattern of (l + 0.0) is monotone in l
+		atomicMin(&slab_lo[s], (unsigned long long)__double_as_longlong(lmin + 0.0));
+		atomicMax(&slab_hi[s], (unsigned long long)__double_as_longlong(lmax + 0.0));
+	}
+	info[c] = ci;
+}
+
+__global__ void k_col_chunks(const int64_t *__restrict__ prim_cell_start, int64_t ncol, int nz,
+							 int32_t *__restrict__ col_chunks) {
+	const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+	if (c > ncol) return;
+	if (c == ncol) {
+		col_chunks[c] = 0;
+		return;
+	}
+	const int64_t n = prim_cell_start[(c + 1) * nz] - prim_cell_start[c * nz];
+	col_chunks[c] = (int32_t)((n + TP - 1) / TP);
+}
+
+__device__ __forceinline__ bool neighbour_offset_ok(int ou, int ov, double cs, double reach) {
+	const double mu = (abs(ou) > 1) ? (double)(abs(ou) - 1) : 0.0, mv = (abs(ov) > 1) ? (double)(abs(ov) - 1) : 0.0;
+	return (mu * mu + mv * mv) * cs * cs * (1.0 - 1e-6) < reach * reach;
+}
+
+__global__ void k_fill_tasks(const int64_t *__restrict__ prim_cell_start, const int64_t *__restrict__ cell_start,
+							 const int32_t *__restrict__ task_off, int ncu, int ncv, int nz, int k, int periodic,
+							 double cs, double reach, int32_t *__restrict__ task_col, int64_t *__restrict__ task_first,
+							 int32_t *__restrict__ task_n, unsigned long long *__restrict__ task_cost,
+							 int32_t *__restrict__ n_tasks) {
+	const int64_t ncol = (int64_t)ncu * ncv;
+	const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+	if (c == 0) n_tasks[0] = task_off[ncol];
+	if (c >= ncol) return;
+	const int64_t p0 = prim_cell_start[c * nz], p1 = prim_cell_start[(c + 1) * nz];
+	if (p1 <= p0) return;
+	const int cu = (int)(c / ncv), cv = (int)(c % ncv);
+	const bool all_u = 2 * k + 1 >= ncu, all_v = 2 * k + 1 >= ncv;
+	unsigned long long W = 0;
+	for (int iu = all_u ? 0 : -k; iu <= (all_u ? ncu - 1 : k); iu++) {
+		int nu = all_u ? iu : cu + iu;
+		if (nu < 0 || nu >= ncu) {
+			if (!periodic) continue;
+			nu = (nu + ncu) % ncu;
+		}
+		for (int iv = all_v ? 0 : -k; iv <= (all_v ? ncv - 1 : k); iv++) {
+			int nv = all_v ? iv : cv + iv;
+			if (nv < 0 || nv >= ncv) {
+				if (!periodic) continue;
+				nv = (nv + ncv) % ncv;
+			}
+			if (!all_u && !all_v && !neighbour_offset_ok(iu, iv, cs, reach)) continue;
+			const int64_t nc = (int64_t)nu * ncv + nv;
+			W += (unsigned long long)(cell_start[(nc + 1) * nz] - cell_start[nc * nz]);
+		}
+	}
+	int t = task_off[c];
+	for (int64_t p = p0; p < p1; p += TP, t++) {
+		const int n = (int)((p1 - p < TP) ? (p1 - p) : TP);
+		task_col[t] = (int32_t)c;
+		task_first[t] = p;
+		task_n[t] = n;
+		task_cost[t] = (unsigned long long)n * W + 1ull;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// device helpers: mbarrier + 1-D bulk (TMA) copy
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"MIA_WAIT:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra MIA_DONE;\n"
+		"bra MIA_WAIT;\n"
+		"MIA_DONE:\n"
+		"}\n" ::"r"(smem_u32(bar)),
+		"r"(parity)
+		: "memory");
+}
+// global -> shared bulk copy (UBLKCP), completion signalled on `bar` as transaction bytes
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+					 smem_u32(dst)),
+				 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+				 : "memory");
+}
+
+__device__ __forceinline__ double fast_rcp(double x) {
+	double y;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+	double e = fma(-x, y, 1.0);
+	y = fma(y, e, y);
+	e = fma(-x, y, 1.0);
+	return fma(y, e, y);
+}
+
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+	return x;
+}
+
+// extended bin of x on the second axis: -1 below range, n_2 at/above the upper range edge
+__device__ __forceinline__ int ebin2(double x, const DevParams &P) {
+	int c = 0;
+	for (int b = 0; b <= P.n_2; b++) c += (x >= P.thr2[b]) ? 1 : 0;
+	return c - 1;
+}
+
+struct ZWindow {
+	double t_split, t_lo, t_hi;
+	int b0, b1;
+	bool gen, dead, err;
+};
+
+// Which (at most two) Pi bins can pairs of this shape galaxy with candidates of a slab [zlo, zhi] fall in?
+__device__ __forceinline__ ZWindow z_window(double pl, double zlo, double zhi, const DevParams &P) {
+	ZWindow w;
+	w.t_split = INFINITY;
+	w.t_lo = -INFINITY;
+	w.t_hi = INFINITY;
+	w.b0 = w.b1 = -1;
+	w.gen = false;
+	w.dead = false;
+	w.err = false;
+	const int n2 = P.n_2;
+	double lo = __dsub_rn(pl, zhi), hi = __dsub_rn(pl, zlo);  // fl(s - c) is monotone in c
+	bool straddle = false;
+	if (P.periodic && !(lo >= -P.halfL && hi <= P.halfL)) {
+		w.gen = true;
+		if (lo > P.halfL) {
+			lo = __dsub_rn(lo, P.L);
+			hi = __dsub_rn(hi, P.L);
+		} else if (hi < -P.halfL) {
+			lo = __dadd_rn(lo, P.L);
+			hi = __dadd_rn(hi, P.L);
+		} else {
+			straddle = true;
+		}
+	}
+	if (!straddle) {
+		const int ea = ebin2(lo, P), eb = ebin2(hi, P);
+		if (eb - ea > 1) w.err = true;
+		if (ea >= 0 && ea < n2) w.b0 = ea;
+		if (eb != ea) {
+			if (eb >= 0 && eb < n2) w.b1 = eb;
+			w.t_split = P.thr2[eb <= n2 ? (eb < 0 ? 0 : eb) : n2];
+		}
+		if (ea < 0) {
+			w.t_lo = P.thr2[0];
+			w.gen = true;
+		}
+		if (eb >= n2) {
+			w.t_hi = P.thr2[n2];
+			w.gen = true;
+		}
+	} else {
+		// part A: values close to +L/2, part B: values close to -L/2 (one of them wrapped)
+		double a_lo, b_hi;
+		if (hi > P.halfL) {
+			a_lo = lo;
+			b_hi = __dsub_rn(hi, P.L);
+		} else {
+			a_lo = __dadd_rn(lo, P.L);
+			b_hi = hi;
+		}
+		const int ea_a = ebin2(a_lo, P), eb_a = ebin2(P.halfL, P);
+		const int ea_b = ebin2(-P.halfL, P), eb_b = ebin2(b_hi, P);
+		int na = 0, nbb = 0, va = -1, vb = -1;
+		for (int e = ea_a; e <= eb_a; e++)
+			if (e >= 0 && e < n2) {
+				na++;
+				va = e;
+			}
+		for (int e = ea_b; e <= eb_b; e++)
+			if (e >= 0 && e < n2) {
+				nbb++;
+				vb = e;
+			}
+		if (na > 1 || nbb > 1) w.err = true;
+		w.b0 = vb;
+		w.b1 = va;
+		w.t_split = 0.0;
+		w.t_lo = P.thr2[0];
+		w.t_hi = P.thr2[n2];
+		if (w.b0 == w.b1) {
+			w.b1 = -1;
+			w.t_split = INFINITY;
+		}
+	}
+	w.dead = (w.b0 < 0 && w.b1 < 0);
+	return w;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// the pair kernel
+// ------------------------------------------------------------------------------------------------------------------
+struct Chunk {
+	long long start;
+	int n, label, desc;
+};
+
+template <bool UNITW>
+struct PrivAcc {
+	double *sp, *sc, *dw;
+	unsigned int *cnt;
+};
+
+template <bool UNITW, bool XYW, bool ZG>
+__device__ __forceinline__ void pair_loop(const Cand *__restrict__ buf, int n, const DevParams &P, double pu, double pv,
+										  double pl, double a0, double a1, double t0, double tn, const ZWindow &zw,
+										  const LutEntry *__restrict__ lut, int lut_hi0, int lut_shift,
+										  const PrivAcc<UNITW> &acc, int tid, unsigned long long &nan_pairs) {
+	const double L = P.L, halfL = P.halfL;
+#pragma unroll 2
+	for (int j = 0; j < n; j++) {
+		const double2 q0 = reinterpret_cast<const double2 *>(buf + j)[0];
+		const double2 q1 = reinterpret_cast<const double2 *>(buf + j)[1];
+		double du = __dsub_rn(pu, q0.x), dv = __dsub_rn(pv, q0.y);  // shape minus position, :401
+		if (XYW) {
+			if (du > halfL) du = __dsub_rn(du, L);
+			if (du < -halfL) du = __dadd_rn(du, L);
+			if (dv > halfL) dv = __dsub_rn(dv, L);
+			if (dv < -halfL) dv = __dadd_rn(dv, L);
+		}
+		const double r2 = __dadd_rn(__dmul_rn(du, du), __dmul_rn(dv, dv));  // :407 (before the sqrt)
+		double dz = __dsub_rn(pl, q1.x);
+		bool ok = (r2 >= t0) && (r2 < tn);
+		if (ZG) {
+			if (P.periodic) {
+				if (dz > halfL) dz = __dsub_rn(dz, L);
+				if (dz < -halfL) dz = __dadd_rn(dz, L);
+			}
+			ok = ok && (dz >= zw.t_lo) && (dz < zw.t_hi);
+		}
+		if (ok) {
+			const int idx = (__double2hiint(r2) - lut_hi0) >> lut_shift;
+			const LutEntry le = lut[idx];
+			const int rbin = le.base + ((r2 >= le.thr) ? 1 : 0);
+			const int slot = 2 * rbin + ((dz >= zw.t_split) ? 1 : 0);
+			const double cr = fma(du, a0, __dmul_rn(dv, a1));   // r_p cos(phi)
+			const double sr = fma(du, a1, -__dmul_rn(dv, a0));  // r_p sin(phi) (sign irrelevant)
+			const double inv = fast_rcp(r2);
+			const double inv2 = inv + inv;
+			const double t = cr * cr;
+			double gp = fma(t, inv2, -1.0);          // cos 2phi = 2 cos^2 - 1
+			double gc = (cr * fabs(sr)) * inv2;      // sin 2phi = 2 cos phi |sin phi|   (phi in [0, pi])
+			if (t >= r2 * (1.0 - 1e-12)) {           // |cos| ~ 1: apply the reference's NaN rule exactly
+				const double rp = __dsqrt_rn(r2);
+				const double c = __dadd_rn(__dmul_rn(__ddiv_rn(du, rp), a0), __dmul_rn(__ddiv_rn(dv, rp), a1));
+				if (!(fabs(c) <= 1.0)) {
+					gp = 0.0;
+					gc = 0.0;
+					nan_pairs++;
+				}
+			}
+			const int o = slot * TP + tid;
+			if (!UNITW) {
+				gp *= q1.y;
+				gc *= q1.y;
+				acc.dw[o] += q1.y;
+			}
+			acc.sp[o] += gp;
+			acc.sc[o] += gc;
+			acc.cnt[o] += 1u;
+		}
+	}
+}
+
+template <bool UNITW>
+__global__ void __launch_bounds__(TP) k_tiled_rppi(const TiledArgs a) {
+	extern __shared__ __align__(128) unsigned char smem[];
+	const DevParams &P = a.P;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int NS = 2 * P.n_r, nb = P.n_r * P.n_2;
+	const int J = P.num_jk > 0 ? P.num_jk : 1;
+
+	// ---- shared memory carve-up ------------------------------------------------------------------------------------
+	Cand *buf = reinterpret_cast<Cand *>(smem);
+	LutEntry *lut = reinterpret_cast<LutEntry *>(smem + sizeof(Cand) * 2 * CH);
+	Desc *desc = reinterpret_cast<Desc *>(reinterpret_cast<unsigned char *>(lut) + sizeof(LutEntry) * LUT_SIZE);
+	int *nlist = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(desc) + sizeof(Desc) * MAX_NEIGH);
+	int *nkey = nlist + MAX_NEIGH;
+	uint64_t *full = reinterpret_cast<uint64_t *>(nkey + MAX_NEIGH);
+	int *misc = reinterpret_cast<int *>(full + 2);  // [0] first task, [1] end task, [2] neighbour count
+	unsigned char *accbase = reinterpret_cast<unsigned char *>(full) + 256;
+	PrivAcc<UNITW> acc;
+	acc.sp = reinterpret_cast<double *>(accbase);
+	acc.sc = acc.sp + (size_t)NS * TP;
+	acc.dw = UNITW ? nullptr : acc.sc + (size_t)NS * TP;
+	acc.cnt = reinterpret_cast<unsigned int *>((UNITW ? acc.sc : acc.dw) + (size_t)NS * TP);
+
+	if (tid == 0) {
+		mbar_init(&full[0], 1);
+		mbar_init(&full[1], 1);
+		mbar_fence_init();
+		// ---- my share of the tasks: slots of equal estimated work ---------------------------------------------------
+		const int nt = a.n_tasks[0];
+		int t0 = 0, t1 = 0;
+		if (nt > 0) {
+			const double total2 = 2.0 * (double)a.task_cum[nt - 1];
+			const int RG = a.shard_count * a.G, mine = a.shard_index * a.G + (int)blockIdx.x;
+			auto slot_of = [&](int t) {
+				const double mid2 = 2.0 * (double)a.task_cum[t] - (double)a.task_cost[t];
+				int s = (int)(mid2 / total2 * (double)RG);
+				return s < RG - 1 ? s : RG - 1;
+			};
+			auto lower = [&](int target) {  // first task with slot >= target
+				int lo = 0, hi = nt;
+				while (lo < hi) {
+					const int mid = (lo + hi) >> 1;
+					if (slot_of(mid) >= target) hi = mid;
+					else lo = mid + 1;
+				}
+				return lo;
+			};
+			t0 = lower(mine);
+			t1 = lower(mine + 1);
+		}
+		misc[0] = t0;
+		misc[1] = t1;
+		if (blockIdx.x == 0) a.A.stats[6] = (unsigned long long)nt;
+	}
+	for (int e = tid; e < LUT_SIZE; e += TP) lut[e] = a.lut[e];
+	for (int s = 0; s < NS; s++) {
+		acc.sp[s * TP + tid] = 0.0;
+		acc.sc[s * TP + tid] = 0.0;
+		if (!UNITW) acc.dw[s * TP + tid] = 0.0;
+		acc.cnt[s * TP + tid] = 0u;
+	}
+	__syncthreads();
+	const int task0 = misc[0], task1 = misc[1];
+
+	// this warp's accumulator copy in HBM
+	const size_t part = (size_t)(blockIdx.x * TW + warp) * (size_t)a.A.rows * nb;
+	unsigned long long *pcnt = a.A.cnt + part;
+	double *pddw = a.A.ddw + part, *psp = a.A.sp + part, *psc = a.A.sc + part;
+
+	uint32_t phase0 = 0, phase1 = 0;
+	unsigned long long tested = 0, binned = 0, nan_pairs = 0;
+	const double T0 = P.r2_thr[0], TN = P.r2_thr[P.n_r];
+	const double cs = P.L / P.ncu, reach = sqrt(TN) * (1.0 + 1e-6);
+
+	for (int task = task0; task < task1; task++) {
+		const int col = a.task_col[task];
+		const int np = a.task_n[task];
+		const bool active = tid < np;
+		Prim p;
+		if (active) {
+			p = a.prim[a.task_first[task] + tid];
+		} else {
+			p.u = p.v = p.l = 0.0;
+			p.w = 0.0;
+			p.a0 = 1.0;
+			p.a1 = 0.0;
+			p.e = 0.0;
+			p.jk = 0;
+			p.orig = -1;
+		}
+		const double pe = p.w * p.e;
+		const int cu0 = col / P.ncv, cv0 = col % P.ncv;
+
+		// ---- neighbour columns of this task, ordered by jackknife (u, v) region to minimise label changes -----------
+		{
+			const bool all_u = 2 * P.ku + 1 >= P.ncu, all_v = 2 * P.kv + 1 >= P.ncv;
+			const int wu = all_u ? P.ncu : 2 * P.ku + 1, wv = all_v ? P.ncv : 2 * P.kv + 1;
+			int my_col = -1, my_key = 0x7fffffff;
+			if (tid < wu * wv) {
+				const int iu = tid / wv, iv = tid % wv;
+				int nu = all_u ? iu : cu0 + iu - P.ku, nv = all_v ? iv : cv0 + iv - P.kv;
+				bool ok = true;
+				if (nu < 0 || nu >= P.ncu) {
+					if (!P.periodic) ok = false;
+					nu = ((nu % P.ncu) + P.ncu) % P.ncu;
+				}
+				if (nv < 0 || nv >= P.ncv) {
+					if (!P.periodic) ok = false;
+					nv = ((nv % P.ncv) + P.ncv) % P.ncv;
+				}
+				if (ok && !all_u && !all_v && !neighbour_offset_ok(iu - P.ku, iv - P.kv, cs, reach)) ok = false;
+				if (ok) {
+					my_col = nu * P.ncv + nv;
+					my_key = ((nu * a.n_side) / P.ncu) * a.n_side + (nv * a.n_side) / P.ncv;
+				}
+			}
+			if (tid < MAX_NEIGH) nkey[tid] = (my_col >= 0) ? my_key : 0x7fffffff;
+			if (tid == 0) misc[2] = 0;
+			__syncthreads();
+			if (my_col >= 0) {
+				int rank = 0;
+				for (int j = 0; j < wu * wv; j++) {
+					const int kj = nkey[j];
+					rank += (kj < my_key || (kj == my_key && j < tid)) ? 1 : 0;
+				}
+				nlist[rank] = my_col;
+				atomicAdd(&misc[2], 1);
+			}
+			__syncthreads();
+		}
+		const int nn = misc[2];
+
+		for (int s = 0; s < a.nz; s++) {
+			const double zlo = a.slab_lo[s], zhi = a.slab_hi[s];
+			if (!(zlo <= zhi)) continue;  // empty slab (uniform branch)
+			if (tid < nn) {
+				const int64_t c = (int64_t)nlist[tid] * a.nz + s;
+				const int64_t st = a.cell_start[c], en = a.cell_start[c + 1];
+				const CellInfo ci = a.cinfo[c];
+				Desc d;
+				d.start = st;
+				d.n = (int)(en - st);
+				d.label = ci.label;
+				d.nlab = ci.nlab;
+				d.pad = 0;
+				d.umin = ci.umin;
+				d.umax = ci.umax;
+				d.vmin = ci.vmin;
+				d.vmax = ci.vmax;
+				desc[tid] = d;
+			}
+			__syncthreads();
+
+			ZWindow zw = z_window(p.l, zlo, zhi, P);
+			if (!active) zw.dead = true;
+			if (active && zw.err) atomicExch(&a.flags[1], 1);
+			const double tn_lane = zw.dead ? -1.0 : TN;  // dead lanes never pass the range test
+			const bool warp_zg = __any_sync(0xffffffffu, !zw.dead && zw.gen);
+			const unsigned key = zw.dead ? 0xffffffffu
+										 : (((unsigned)p.jk << 16) | ((unsigned)(zw.b0 + 1) << 8) | (unsigned)(zw.b1 + 1));
+
+			// ---- flush: fixed-order warp reduction of the private slots into this warp's accumulator copy -------------
+			auto flush = [&](int jkD) {
+				unsigned todo = __ballot_sync(0xffffffffu, !zw.dead);
+				while (todo) {
+					const int leader = __ffs(todo) - 1;
+					const unsigned k = __shfl_sync(0xffffffffu, key, leader);
+					const unsigned grp = __ballot_sync(0xffffffffu, key == k) & todo;
+					const bool in = (grp >> lane) & 1u;
+					unsigned tot_cnt = 0;
+					double tot_sp = 0.0, tot_sc = 0.0, tot_dw = 0.0;
+					for (int sl = 0; sl < NS; sl++) {
+						const int o = sl * TP + tid;
+						const unsigned c = in ? acc.cnt[o] : 0u;
+						const unsigned csum = __reduce_add_sync(0xffffffffu, c);
+						if (csum == 0u) continue;
+						const double xs = warp_sum(in ? acc.sp[o] * pe : 0.0);
+						const double ys = warp_sum(in ? acc.sc[o] * pe : 0.0);
+						const double zs = UNITW ? (double)csum : warp_sum(in ? acc.dw[o] * p.w : 0.0);
+						if (lane == sl) {
+							tot_cnt = csum;
+							tot_sp = xs;
+							tot_sc = ys;
+							tot_dw = zs;
+						}
+					}
+					if (lane < NS && tot_cnt) {
+						const int kb0 = (int)((k >> 8) & 0xffu) - 1, kb1 = (int)(k & 0xffu) - 1, kjk = (int)(k >> 16);
+						const int b2 = (lane & 1) ? kb1 : kb0;
+						if (b2 < 0) {
+							atomicExch(&a.flags[1], 1);
+						} else {
+							const size_t bin = (size_t)(lane >> 1) * P.n_2 + b2;
+							const size_t ia = (size_t)kjk * nb + bin;
+							pcnt[ia] += tot_cnt;
+							pddw[ia] += tot_dw;
+							psp[ia] += tot_sp;
+							psc[ia] += tot_sc;
+							if (P.num_jk > 0 && jkD != kjk) {
+								const size_t ib = (size_t)(J + jkD) * nb + bin;
+								pcnt[ib] += tot_cnt;
+								pddw[ib] += tot_dw;
+								psp[ib] += tot_sp;
+							}
+							binned += tot_cnt;
+						}
+					}
+					todo &= ~grp;
+				}
+				__syncwarp();
+				for (int sl = 0; sl < NS; sl++) {
+					const int o = sl * TP + tid;
+					acc.sp[o] = 0.0;
+					acc.sc[o] = 0.0;
+					if (!UNITW) acc.dw[o] = 0.0;
+					acc.cnt[o] = 0u;
+				}
+			};
+
+			// ---- chunk iterator over the neighbour cells of this slab (uniform across the CTA) --------------------------
+			int it_e = -1;
+			long long it_pos = 0, it_sub_end = 0, it_cell_end = 0;
+			int it_label = -1;
+			auto next_chunk = [&](Chunk &c) -> bool {
+				for (;;) {
+					if (it_pos < it_sub_end) {
+						c.start = it_pos;
+						c.n = (int)((it_sub_end - it_pos < CH) ? (it_sub_end - it_pos) : CH);
+						c.label = it_label;
+						c.desc = it_e;
+						it_pos += c.n;
+						return true;
+					}
+					if (it_sub_end < it_cell_end) {  // next label run of a mixed cell (rare)
+						it_pos = it_sub_end;
+						it_label = a.cand_jk[it_pos];
+						long long q = it_pos + 1;
+						while (q < it_cell_end && a.cand_jk[q] == it_label) q++;
+						it_sub_end = q;
+						continue;
+					}
+					it_e++;
+					if (it_e >= nn) return false;
+					const Desc &d = desc[it_e];
+					if (d.n == 0) continue;
+					it_pos = d.start;
+					it_cell_end = d.start + d.n;
+					if (d.nlab <= 1) {
+						it_label = d.label;
+						it_sub_end = it_cell_end;
+					} else {
+						it_label = a.cand_jk[it_pos];
+						long long q = it_pos + 1;
+						while (q < it_cell_end && a.cand_jk[q] == it_label) q++;
+						it_sub_end = q;
+					}
+				}
+			};
+			auto issue = [&](const Chunk &c, int b) {
+				if (tid == 0) {
+					const uint32_t bytes = (uint32_t)c.n * (uint32_t)sizeof(Cand);
+					mbar_expect_tx(&full[b], bytes);
+					bulk_load(buf + (size_t)b * CH, a.cand + c.start, bytes, &full[b]);
+				}
+			};
+
+			Chunk cur, nxt;
+			bool have = next_chunk(cur);
+			int bi = 0;
+			int cur_label = -1;
+			if (have) issue(cur, bi);
+			while (have) {
+				const bool have_n = next_chunk(nxt);
+				if (have_n) issue(nxt, bi ^ 1);
+				if (cur.label != cur_label) {
+					if (cur_label >= 0) flush(cur_label);
+					cur_label = cur.label;
+				}
+				if (bi == 0) {
+					mbar_wait(&full[0], phase0);
+					phase0 ^= 1u;
+				} else {
+					mbar_wait(&full[1], phase1);
+					phase1 ^= 1u;
+				}
+				// ---- per-warp culling against the cell's bounding box, then the pair loop --------------------------------
+				{
+					const Desc &d = desc[cur.desc];
+					double ulo = __dsub_rn(p.u, d.umax), uhi = __dsub_rn(p.u, d.umin);
+					double vlo = __dsub_rn(p.v, d.vmax), vhi = __dsub_rn(p.v, d.vmin);
+					bool xyw = false, nocull = false;
+					if (P.periodic) {
+						if (!(ulo >= -P.halfL && uhi <= P.halfL)) {
+							xyw = true;
+							if (ulo > P.halfL) {
+								ulo = __dsub_rn(ulo, P.L);
+								uhi = __dsub_rn(uhi, P.L);
+							} else if (uhi < -P.halfL) {
+								ulo = __dadd_rn(ulo, P.L);
+								uhi = __dadd_rn(uhi, P.L);
+							} else {
+								nocull = true;
+							}
+						}
+						if (!(vlo >= -P.halfL && vhi <= P.halfL)) {
+							xyw = true;
+							if (vlo > P.halfL) {
+								vlo = __dsub_rn(vlo, P.L);
+								vhi = __dsub_rn(vhi, P.L);
+							} else if (vhi < -P.halfL) {
+								vlo = __dadd_rn(vlo, P.L);
+								vhi = __dadd_rn(vhi, P.L);
+							} else {
+								nocull = true;
+							}
+						}
+					}
+					const double mu = ulo > 0.0 ? ulo : (uhi < 0.0 ? -uhi : 0.0);
+					const double mv = vlo > 0.0 ? vlo : (vhi < 0.0 ? -vhi : 0.0);
+					const double dmin2 = __dadd_rn(__dmul_rn(mu, mu), __dmul_rn(mv, mv));
+					const bool need = !zw.dead && (nocull || dmin2 < TN);
+					if (__any_sync(0xffffffffu, need)) {
+						if (!zw.dead) tested += (unsigned long long)cur.n;
+						const bool warp_xyw = __any_sync(0xffffffffu, !zw.dead && xyw);
+						const Cand *cb = buf + (size_t)bi * CH;
+						if (!warp_xyw && !warp_zg)
+							pair_loop<UNITW, false, false>(cb, cur.n, P, p.u, p.v, p.l, p.a0, p.a1, T0, tn_lane, zw, lut,
+														   a.lut_hi0, a.lut_shift, acc, tid, nan_pairs);
+						else if (!warp_xyw)
+							pair_loop<UNITW, false, true>(cb, cur.n, P, p.u, p.v, p.l, p.a0, p.a1, T0, tn_lane, zw, lut,
+														  a.lut_hi0, a.lut_shift, acc, tid, nan_pairs);
+						else if (!warp_zg)
+							pair_loop<UNITW, true, false>(cb, cur.n, P, p.u, p.v, p.l, p.a0, p.a1, T0, tn_lane, zw, lut,
+														  a.lut_hi0, a.lut_shift, acc, tid, nan_pairs);
+						else
+							pair_loop<UNITW, true, true>(cb, cur.n, P, p.u, p.v, p.l, p.a0, p.a1, T0, tn_lane, zw, lut,
+														 a.lut_hi0, a.lut_shift, acc, tid, nan_pairs);
+					}
+				}
+				__syncthreads();  // every warp is done with buf[bi]: it may be refilled
+				bi ^= 1;
+				cur = nxt;
+				have = have_n;
+			}
+			if (cur_label >= 0) flush(cur_label);
+			__syncthreads();  // desc[] is rewritten for the next slab
+		}
+	}
+
+	// ---- statistics ------------------------------------------------------------------------------------------------------
+	for (int o = 16; o > 0; o >>= 1) {
+		tested += __shfl_down_sync(0xffffffffu, tested, o);
+		binned += __shfl_down_sync(0xffffffffu, binned, o);
+		nan_pairs += __shfl_down_sync(0xffffffffu, nan_pairs, o);
+	}
+	if (lane == 0) {
+		atomicAdd(&a.A.stats[0], tested);
+		atomicAdd(&a.A.stats[1], binned);
+		atomicAdd(&a.A.stats[2], nan_pairs);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------------------------------
+inline int tiled_prepare_candidates(const TiledConfig &cfg, const GridDims &g, const DevParams &P, const uint32_t *,
+									const Cand *cand, const int32_t *cand_jk, int64_t, const int64_t *cell_start,
+									void *ws, cudaStream_t st) {
+	TiledWorkspace w = carve_tiled(cfg, g, ws);
+	MIA_CUDA_CHECK(cudaMemsetAsync(w.slab_lo, 0xFF, sizeof(double) * cfg.nz, st));
+	MIA_CUDA_CHECK(cudaMemsetAsync(w.slab_hi, 0x00, sizeof(double) * cfg.nz, st));
+	const int64_t ncell = g.ncell();
+	k_cell_info<<<(unsigned)((ncell + 127) / 128), 128, 0, st>>>(cand, cand_jk, cell_start, ncell, cfg.nz, w.cinfo,
+																 (unsigned long long *)w.slab_lo,
+																 (unsigned long long *)w.slab_hi);
+	MIA_CUDA_CHECK(cudaGetLastError());
+	MIA_CUDA_CHECK(cudaMemcpyAsync(w.lut, cfg.lut, sizeof(LutEntry) * LUT_SIZE, cudaMemcpyHostToDevice, st));
+	(void)P;
+	return 0;
+}
+
+inline int tiled_launch(const TiledConfig &cfg, const GridDims &g, const DevParams &P, const Grid &G, const Prim *prim,
+						const int64_t *prim_cell_start, int64_t nS, bool unit_w, mia_shard shard, const Accum &A, void *ws,
+						int *flags, cudaStream_t st) {
+	TiledWorkspace w = carve_tiled(cfg, g, ws);
+	const int64_t ncol = (int64_t)g.ncu * g.ncv;
+	if (nS == 0 || G.n_cand == 0) return 0;
+	// ---- task table -------------------------------------------------------------------------------------------------------
+	MIA_CUDA_CHECK(cudaMemsetAsync(w.task_cost, 0, sizeof(unsigned long long) * cfg.max_tasks, st));
+	k_col_chunks<<<(unsigned)((ncol + 1 + 255) / 256), 256, 0, st>>>(prim_cell_start, ncol, cfg.nz, w.col_chunks);
+	MIA_CUDA_CHECK(cudaGetLastError());
+	size_t cb = w.cub_bytes;
+	MIA_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, cb, w.col_chunks, w.task_off, (int)(ncol + 1), st));
+	const double cs = P.L / g.ncu, reach = sqrt(P.r2_thr[P.n_r]) * (1.0 + 1e-6);
+	k_fill_tasks<<<(unsigned)((ncol + 255) / 256), 256, 0, st>>>(prim_cell_start, G.cell_start, w.task_off, g.ncu, g.ncv,
+																 cfg.nz, P.ku, P.periodic, cs, reach, w.task_col,
+																 w.task_first, w.task_n, w.task_cost, w.n_tasks);
+	MIA_CUDA_CHECK(cudaGetLastError());
+	cb = w.cub_bytes;
+	MIA_CUDA_CHECK(cub::DeviceScan::InclusiveSum(w.cub_tmp, cb, w.task_cost, w.task_cum, cfg.max_tasks, st));
+
+	// ---- launch: one CTA per work slot of equal estimated cost.  The slot count is fixed (SLOTS_PER_SM per SM), NOT
+	// derived from occupancy: the grouping of the fp64 sums, hence every output bit, is the same for the weighted and
+	// the unit-weight kernel variants, which is what lets w = 0.5 scale the results by exactly 1/4. ---------------------
+	const size_t smem = tiled_smem_bytes(P.n_r, unit_w);
+	if (unit_w) {
+		MIA_CUDA_CHECK(cudaFuncSetAttribute(k_tiled_rppi<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	} else {
+		MIA_CUDA_CHECK(cudaFuncSetAttribute(k_tiled_rppi<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	}
+	const int Gc = cfg.n_slots;
+	TiledArgs a;
+	a.P = P;
+	a.cand = G.cand;
+	a.cand_jk = G.cand_jk;
+	a.cell_start = G.cell_start;
+	a.cinfo = w.cinfo;
+	a.slab_lo = w.slab_lo;
+	a.slab_hi = w.slab_hi;
+	a.prim = prim;
+	a.task_col = w.task_col;
+	a.task_first = w.task_first;
+	a.task_n = w.task_n;
+	a.task_cost = w.task_cost;
+	a.task_cum = w.task_cum;
+	a.n_tasks = w.n_tasks;
+	a.lut = w.lut;
+	a.lut_hi0 = cfg.lut_hi0;
+	a.lut_shift = cfg.lut_shift;
+	a.lut_n = cfg.lut_n;
+	a.A = A;
+	a.nz = cfg.nz;
+	a.n_side = cfg.n_side;
+	a.G = Gc;
+	a.shard_index = shard.index;
+	a.shard_count = shard.count;
+	a.max_tasks = cfg.max_tasks;
+	a.flags = flags;
+	if (unit_w) k_tiled_rppi<true><<<Gc, TP, smem, st>>>(a);
+	else k_tiled_rppi<false><<<Gc, TP, smem, st>>>(a);
+	MIA_CUDA_CHECK(cudaGetLastError());
+	return 0;
+}
+
 }  // namespace mia

@@ -68,6 +68,8 @@ def test_reference_fixture(torch_cuda, tmp_path, name, kernel):
 	box = run_box(meta, data, masks, kw, out, kernel)
 	got = read_all(out)
 	pu.assert_datasets_match(got, want, exact_counts=not meta["catalogue"].get("weights"), label=f"{name}[{kernel}]: ")
+	if kernel == "auto" and meta["measurement"]["kind"] == "w":
+		assert box.last_stats["kernel"] == 2, "the tiled kernel should cover every (r_p, Pi) fixture"
 	dd_key = [k for k in want if k.endswith("xi_gg/All_DD")][0]
 	if not meta["catalogue"].get("weights"):
 		assert box.last_stats["binned"] == int(want[dd_key].sum())
