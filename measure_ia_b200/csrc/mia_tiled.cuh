@@ -30,7 +30,8 @@ namespace mia {
 
 constexpr int TP = 128;          // threads = shape galaxies per CTA
 constexpr int TW = TP / 32;      // warps per CTA
-constexpr int CH = 128;          // candidates per staged chunk
+constexpr int CH = 64;           // candidates per staged chunk
+constexpr int STAGES = 4;        // ring depth
 constexpr int MAX_NEIGH = 128;   // neighbour columns per task
 constexpr int LUT_SIZE = 256;
 constexpr int MAX_SLOTS = 32;    // 2 * n_r <= 32
@@ -135,7 +136,7 @@ inline bool build_lut(const mia_params *p, TiledConfig &cfg) {
 }
 
 inline size_t tiled_smem_bytes(int n_r, bool unit_w) {
-	const size_t fixed = sizeof(Cand) * 2 * CH + sizeof(LutEntry) * LUT_SIZE + sizeof(Desc) * MAX_NEIGH +
+	const size_t fixed = sizeof(Cand) * STAGES * CH + sizeof(LutEntry) * LUT_SIZE + sizeof(Desc) * MAX_NEIGH +
 						 sizeof(int) * MAX_NEIGH * 2 + 256;
 	const size_t per_slot = (size_t)TP * (8 + 8 + 4 + (unit_w ? 0 : 8));
 	return fixed + per_slot * 2 * n_r;
@@ -395,6 +396,7 @@ __device__ __forceinline__ int ebin2(double x, const DevParams &P) {
 
 struct ZWindow {
 	double t_split, t_lo, t_hi;
+	double shift;  // 0, -L or +L: the periodic image every pair of this lane with this slab takes (when not `gen`)
 	int b0, b1;
 	bool gen, dead, err;
 };
@@ -405,6 +407,7 @@ __device__ __forceinline__ ZWindow z_window(double pl, double zlo, double zhi, c
 	w.t_split = INFINITY;
 	w.t_lo = -INFINITY;
 	w.t_hi = INFINITY;
+	w.shift = 0.0;
 	w.b0 = w.b1 = -1;
 	w.gen = false;
 	w.dead = false;
@@ -413,15 +416,17 @@ __device__ __forceinline__ ZWindow z_window(double pl, double zlo, double zhi, c
 	double lo = __dsub_rn(pl, zhi), hi = __dsub_rn(pl, zlo);  // fl(s - c) is monotone in c
 	bool straddle = false;
 	if (P.periodic && !(lo >= -P.halfL && hi <= P.halfL)) {
-		w.gen = true;
-		if (lo > P.halfL) {
+		if (lo > P.halfL) {  // every pair wraps down: sep -= L (measure_w_box_jk.py:403)
 			lo = __dsub_rn(lo, P.L);
 			hi = __dsub_rn(hi, P.L);
-		} else if (hi < -P.halfL) {
+			w.shift = -P.L;
+		} else if (hi < -P.halfL) {  // every pair wraps up (:404)
 			lo = __dadd_rn(lo, P.L);
 			hi = __dadd_rn(hi, P.L);
+			w.shift = P.L;
 		} else {
 			straddle = true;
+			w.gen = true;
 		}
 	}
 	if (!straddle) {
@@ -479,6 +484,41 @@ __device__ __forceinline__ ZWindow z_window(double pl, double zlo, double zhi, c
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// explicit shared-memory access (32-bit shared addresses; keeps nvcc from re-deriving the shared window per access)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lds_v2(double &a, double &b, uint32_t addr) {
+	asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
+__device__ __forceinline__ void sts_v2(uint32_t addr, double a, double b) {
+	asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+	double a;
+	asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a) : "r"(addr));
+	return a;
+}
+__device__ __forceinline__ void sts_f64(uint32_t addr, double a) {
+	asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(a) : "memory");
+}
+__device__ __forceinline__ unsigned lds_u32(uint32_t addr) {
+	unsigned a;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a) : "r"(addr));
+	return a;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, unsigned a) {
+	asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
+}
+__device__ __forceinline__ void lds_lut(double &thr, int &base, uint32_t addr) {
+	long long a, b;
+	asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+	thr = __longlong_as_double(a);
+	base = (int)b;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // the pair kernel
 // ------------------------------------------------------------------------------------------------------------------
 struct Chunk {
@@ -486,23 +526,32 @@ struct Chunk {
 	int n, label, desc;
 };
 
-template <bool UNITW>
+// Shared-memory addresses (bytes, shared window) of the thread-private accumulators:
+//   a2 : [slot][thread] double2 {sum e+ , sum ex}     ac : [slot][thread] u32 pair count     aw : [slot][thread] sum w_D
 struct PrivAcc {
-	double *sp, *sc, *dw;
-	unsigned int *cnt;
+	uint32_t a2, ac, aw;
 };
 
+// One staged chunk against this thread's shape galaxy.
+//   XYW : compare-and-wrap the projected separations per pair (lanes whose column pair crosses the periodic boundary)
+//   ZG  : compare-and-wrap + range-check the line-of-sight separation per pair (slab straddles +-L/2 or the Pi range)
+//         otherwise the lane-constant image shift is added (exactly the reference's `sep -= L` / `sep += L`)
 template <bool UNITW, bool XYW, bool ZG>
-__device__ __forceinline__ void pair_loop(const Cand *__restrict__ buf, int n, const DevParams &P, double pu, double pv,
-										  double pl, double a0, double a1, double t0, double tn, const ZWindow &zw,
-										  const LutEntry *__restrict__ lut, int lut_hi0, int lut_shift,
-										  const PrivAcc<UNITW> &acc, int tid, unsigned long long &nan_pairs) {
+__device__ __forceinline__ void pair_loop(uint32_t cb, int n, const DevParams &P, double pu, double pv, double pl,
+										  double a0, double a1, double t0, double tn, const ZWindow &zw, uint32_t lut,
+										  int lut_hi0, int lut_shift, const PrivAcc &acc, unsigned long long &nan_pairs) {
 	const double L = P.L, halfL = P.halfL;
+	double cu, cv, cl, cw;
+	lds_v2(cu, cv, cb);
+	lds_v2(cl, cw, cb + 16);
 #pragma unroll 2
 	for (int j = 0; j < n; j++) {
-		const double2 q0 = reinterpret_cast<const double2 *>(buf + j)[0];
-		const double2 q1 = reinterpret_cast<const double2 *>(buf + j)[1];
-		double du = __dsub_rn(pu, q0.x), dv = __dsub_rn(pv, q0.y);  // shape minus position, :401
+		// software prefetch of the next candidate (clamped: the last iteration re-reads its own entry)
+		const uint32_t na = cb + (uint32_t)((j + 1 < n) ? (j + 1) : j) * (uint32_t)sizeof(Cand);
+		double nu, nv, nl, nw;
+		lds_v2(nu, nv, na);
+		lds_v2(nl, nw, na + 16);
+		double du = __dsub_rn(pu, cu), dv = __dsub_rn(pv, cv);  // shape minus position, :401
 		if (XYW) {
 			if (du > halfL) du = __dsub_rn(du, L);
 			if (du < -halfL) du = __dadd_rn(du, L);
@@ -510,75 +559,92 @@ __device__ __forceinline__ void pair_loop(const Cand *__restrict__ buf, int n, c
 			if (dv < -halfL) dv = __dadd_rn(dv, L);
 		}
 		const double r2 = __dadd_rn(__dmul_rn(du, du), __dmul_rn(dv, dv));  // :407 (before the sqrt)
-		double dz = __dsub_rn(pl, q1.x);
-		bool ok = (r2 >= t0) && (r2 < tn);
-		if (ZG) {
-			if (P.periodic) {
-				if (dz > halfL) dz = __dsub_rn(dz, L);
-				if (dz < -halfL) dz = __dadd_rn(dz, L);
-			}
-			ok = ok && (dz >= zw.t_lo) && (dz < zw.t_hi);
-		}
-		if (ok) {
-			const int idx = (__double2hiint(r2) - lut_hi0) >> lut_shift;
-			const LutEntry le = lut[idx];
-			const int rbin = le.base + ((r2 >= le.thr) ? 1 : 0);
-			const int slot = 2 * rbin + ((dz >= zw.t_split) ? 1 : 0);
-			const double cr = fma(du, a0, __dmul_rn(dv, a1));   // r_p cos(phi)
-			const double sr = fma(du, a1, -__dmul_rn(dv, a0));  // r_p sin(phi) (sign irrelevant)
-			const double inv = fast_rcp(r2);
-			const double inv2 = inv + inv;
-			const double t = cr * cr;
-			double gp = fma(t, inv2, -1.0);          // cos 2phi = 2 cos^2 - 1
-			double gc = (cr * fabs(sr)) * inv2;      // sin 2phi = 2 cos phi |sin phi|   (phi in [0, pi])
-			if (t >= r2 * (1.0 - 1e-12)) {           // |cos| ~ 1: apply the reference's NaN rule exactly
-				const double rp = __dsqrt_rn(r2);
-				const double c = __dadd_rn(__dmul_rn(__ddiv_rn(du, rp), a0), __dmul_rn(__ddiv_rn(dv, rp), a1));
-				if (!(fabs(c) <= 1.0)) {
-					gp = 0.0;
-					gc = 0.0;
-					nan_pairs++;
+		if ((r2 >= t0) && (r2 < tn)) {
+			double dz = __dsub_rn(pl, cl);
+			bool ok = true;
+			if (ZG) {
+				if (P.periodic) {
+					if (dz > halfL) dz = __dsub_rn(dz, L);
+					if (dz < -halfL) dz = __dadd_rn(dz, L);
 				}
+				ok = (dz >= zw.t_lo) && (dz < zw.t_hi);
+			} else {
+				dz = __dadd_rn(dz, zw.shift);
 			}
-			const int o = slot * TP + tid;
-			if (!UNITW) {
-				gp *= q1.y;
-				gc *= q1.y;
-				acc.dw[o] += q1.y;
+			if (ok) {
+				const int idx = (__double2hiint(r2) - lut_hi0) >> lut_shift;
+				double lthr;
+				int lbase;
+				lds_lut(lthr, lbase, lut + (uint32_t)idx * 16u);
+				const int rbin = lbase + ((r2 >= lthr) ? 1 : 0);
+				const uint32_t so = (uint32_t)(2 * rbin + ((dz >= zw.t_split) ? 1 : 0)) * (uint32_t)TP;
+				// private slots: issue the loads first, the arithmetic below hides their latency
+				double s0, s1, sw = 0.0;
+				lds_v2(s0, s1, acc.a2 + so * 16u);
+				const unsigned c0 = lds_u32(acc.ac + so * 4u);
+				if (!UNITW) sw = lds_f64(acc.aw + so * 8u);
+				const double cr = fma(du, a0, __dmul_rn(dv, a1));   // r_p cos(phi)
+				const double sr = fma(du, a1, -__dmul_rn(dv, a0));  // r_p sin(phi) (sign irrelevant)
+				const double inv = fast_rcp(r2);
+				const double inv2 = inv + inv;
+				const double t = cr * cr;
+				double gp = fma(t, inv2, -1.0);      // cos 2phi = 2 cos^2 - 1
+				double gc = (cr * fabs(sr)) * inv2;  // sin 2phi = 2 cos phi |sin phi|   (phi in [0, pi])
+				if (t >= r2 * (1.0 - 1e-12)) {       // |cos| ~ 1: apply the reference's NaN rule exactly
+					const double rp = __dsqrt_rn(r2);
+					const double c = __dadd_rn(__dmul_rn(__ddiv_rn(du, rp), a0), __dmul_rn(__ddiv_rn(dv, rp), a1));
+					if (!(fabs(c) <= 1.0)) {
+						gp = 0.0;
+						gc = 0.0;
+						nan_pairs++;
+					}
+				}
+				if (!UNITW) {
+					gp *= cw;
+					gc *= cw;
+					sts_f64(acc.aw + so * 8u, sw + cw);
+				}
+				sts_v2(acc.a2 + so * 16u, s0 + gp, s1 + gc);
+				sts_u32(acc.ac + so * 4u, c0 + 1u);
 			}
-			acc.sp[o] += gp;
-			acc.sc[o] += gc;
-			acc.cnt[o] += 1u;
 		}
+		cu = nu;
+		cv = nv;
+		cl = nl;
+		cw = nw;
 	}
 }
 
 template <bool UNITW>
-__global__ void __launch_bounds__(TP) k_tiled_rppi(const TiledArgs a) {
+__global__ void __launch_bounds__(TP + 32) k_tiled_rppi(const TiledArgs a) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	const DevParams &P = a.P;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const bool producer = (warp == TW);  // warp-specialised: TW consumer warps + one bulk-copy producer warp
 	const int NS = 2 * P.n_r, nb = P.n_r * P.n_2;
 	const int J = P.num_jk > 0 ? P.num_jk : 1;
 
 	// ---- shared memory carve-up ------------------------------------------------------------------------------------
-	Cand *buf = reinterpret_cast<Cand *>(smem);
-	LutEntry *lut = reinterpret_cast<LutEntry *>(smem + sizeof(Cand) * 2 * CH);
-	Desc *desc = reinterpret_cast<Desc *>(reinterpret_cast<unsigned char *>(lut) + sizeof(LutEntry) * LUT_SIZE);
+	Cand *ring = reinterpret_cast<Cand *>(smem);
+	LutEntry *lut_s = reinterpret_cast<LutEntry *>(smem + sizeof(Cand) * STAGES * CH);
+	Desc *desc = reinterpret_cast<Desc *>(reinterpret_cast<unsigned char *>(lut_s) + sizeof(LutEntry) * LUT_SIZE);
 	int *nlist = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(desc) + sizeof(Desc) * MAX_NEIGH);
 	int *nkey = nlist + MAX_NEIGH;
 	uint64_t *full = reinterpret_cast<uint64_t *>(nkey + MAX_NEIGH);
-	int *misc = reinterpret_cast<int *>(full + 2);  // [0] first task, [1] end task, [2] neighbour count
+	uint64_t *empty = full + STAGES;
+	int *misc = reinterpret_cast<int *>(empty + STAGES);  // [0] first task, [1] end task, [2] neighbour count
 	unsigned char *accbase = reinterpret_cast<unsigned char *>(full) + 256;
-	PrivAcc<UNITW> acc;
-	acc.sp = reinterpret_cast<double *>(accbase);
-	acc.sc = acc.sp + (size_t)NS * TP;
-	acc.dw = UNITW ? nullptr : acc.sc + (size_t)NS * TP;
-	acc.cnt = reinterpret_cast<unsigned int *>((UNITW ? acc.sc : acc.dw) + (size_t)NS * TP);
+	const uint32_t ring_u32 = smem_u32(ring), lut_u32 = smem_u32(lut_s), acc_u32 = smem_u32(accbase);
+	PrivAcc acc;  // addresses of slot 0 of this thread
+	acc.a2 = acc_u32 + (uint32_t)tid * 16u;
+	acc.aw = acc_u32 + (uint32_t)NS * TP * 16u + (uint32_t)tid * 8u;
+	acc.ac = acc_u32 + (uint32_t)NS * TP * (UNITW ? 16u : 24u) + (uint32_t)tid * 4u;
 
 	if (tid == 0) {
-		mbar_init(&full[0], 1);
-		mbar_init(&full[1], 1);
+		for (int s = 0; s < STAGES; s++) {
+			mbar_init(&full[s], 1);
+			mbar_init(&empty[s], TW);
+		}
 		mbar_fence_init();
 		// ---- my share of the tasks: slots of equal estimated work ---------------------------------------------------
 		const int nt = a.n_tasks[0];
@@ -607,22 +673,23 @@ __global__ void __launch_bounds__(TP) k_tiled_rppi(const TiledArgs a) {
 		misc[1] = t1;
 		if (blockIdx.x == 0) a.A.stats[6] = (unsigned long long)nt;
 	}
-	for (int e = tid; e < LUT_SIZE; e += TP) lut[e] = a.lut[e];
-	for (int s = 0; s < NS; s++) {
-		acc.sp[s * TP + tid] = 0.0;
-		acc.sc[s * TP + tid] = 0.0;
-		if (!UNITW) acc.dw[s * TP + tid] = 0.0;
-		acc.cnt[s * TP + tid] = 0u;
+	for (int e = tid; e < LUT_SIZE; e += blockDim.x) lut_s[e] = a.lut[e];
+	if (!producer) {
+		for (int s = 0; s < NS; s++) {
+			sts_v2(acc.a2 + (uint32_t)s * TP * 16u, 0.0, 0.0);
+			if (!UNITW) sts_f64(acc.aw + (uint32_t)s * TP * 8u, 0.0);
+			sts_u32(acc.ac + (uint32_t)s * TP * 4u, 0u);
+		}
 	}
 	__syncthreads();
 	const int task0 = misc[0], task1 = misc[1];
 
 	// this warp's accumulator copy in HBM
-	const size_t part = (size_t)(blockIdx.x * TW + warp) * (size_t)a.A.rows * nb;
+	const size_t part = (size_t)(blockIdx.x * TW + (producer ? 0 : warp)) * (size_t)a.A.rows * nb;
 	unsigned long long *pcnt = a.A.cnt + part;
 	double *pddw = a.A.ddw + part, *psp = a.A.sp + part, *psc = a.A.sc + part;
 
-	uint32_t phase0 = 0, phase1 = 0;
+	unsigned chunk_no = 0;  // running chunk counter: stage = chunk_no % STAGES, round parity = (chunk_no / STAGES) & 1
 	unsigned long long tested = 0, binned = 0, nan_pairs = 0;
 	const double T0 = P.r2_thr[0], TN = P.r2_thr[P.n_r];
 	const double cs = P.L / P.ncu, reach = sqrt(TN) * (1.0 + 1e-6);
@@ -630,7 +697,7 @@ __global__ void __launch_bounds__(TP) k_tiled_rppi(const TiledArgs a) {
 	for (int task = task0; task < task1; task++) {
 		const int col = a.task_col[task];
 		const int np = a.task_n[task];
-		const bool active = tid < np;
+		const bool active = !producer && tid < np;
 		Prim p;
 		if (active) {
 			p = a.prim[a.task_first[task] + tid];
@@ -706,73 +773,7 @@ __global__ void __launch_bounds__(TP) k_tiled_rppi(const TiledArgs a) {
 			}
 			__syncthreads();
 
-			ZWindow zw = z_window(p.l, zlo, zhi, P);
-			if (!active) zw.dead = true;
-			if (active && zw.err) atomicExch(&a.flags[1], 1);
-			const double tn_lane = zw.dead ? -1.0 : TN;  // dead lanes never pass the range test
-			const bool warp_zg = __any_sync(0xffffffffu, !zw.dead && zw.gen);
-			const unsigned key = zw.dead ? 0xffffffffu
-										 : (((unsigned)p.jk << 16) | ((unsigned)(zw.b0 + 1) << 8) | (unsigned)(zw.b1 + 1));
-
-			// ---- flush: fixed-order warp reduction of the private slots into this warp's accumulator copy -------------
-			auto flush = [&](int jkD) {
-				unsigned todo = __ballot_sync(0xffffffffu, !zw.dead);
-				while (todo) {
-					const int leader = __ffs(todo) - 1;
-					const unsigned k = __shfl_sync(0xffffffffu, key, leader);
-					const unsigned grp = __ballot_sync(0xffffffffu, key == k) & todo;
-					const bool in = (grp >> lane) & 1u;
-					unsigned tot_cnt = 0;
-					double tot_sp = 0.0, tot_sc = 0.0, tot_dw = 0.0;
-					for (int sl = 0; sl < NS; sl++) {
-						const int o = sl * TP + tid;
-						const unsigned c = in ? acc.cnt[o] : 0u;
-						const unsigned csum = __reduce_add_sync(0xffffffffu, c);
-						if (csum == 0u) continue;
-						const double xs = warp_sum(in ? acc.sp[o] * pe : 0.0);
-						const double ys = warp_sum(in ? acc.sc[o] * pe : 0.0);
-						const double zs = UNITW ? (double)csum : warp_sum(in ? acc.dw[o] * p.w : 0.0);
-						if (lane == sl) {
-							tot_cnt = csum;
-							tot_sp = xs;
-							tot_sc = ys;
-							tot_dw = zs;
-						}
-					}
-					if (lane < NS && tot_cnt) {
-						const int kb0 = (int)((k >> 8) & 0xffu) - 1, kb1 = (int)(k & 0xffu) - 1, kjk = (int)(k >> 16);
-						const int b2 = (lane & 1) ? kb1 : kb0;
-						if (b2 < 0) {
-							atomicExch(&a.flags[1], 1);
-						} else {
-							const size_t bin = (size_t)(lane >> 1) * P.n_2 + b2;
-							const size_t ia = (size_t)kjk * nb + bin;
-							pcnt[ia] += tot_cnt;
-							pddw[ia] += tot_dw;
-							psp[ia] += tot_sp;
-							psc[ia] += tot_sc;
-							if (P.num_jk > 0 && jkD != kjk) {
-								const size_t ib = (size_t)(J + jkD) * nb + bin;
-								pcnt[ib] += tot_cnt;
-								pddw[ib] += tot_dw;
-								psp[ib] += tot_sp;
-							}
-							binned += tot_cnt;
-						}
-					}
-					todo &= ~grp;
-				}
-				__syncwarp();
-				for (int sl = 0; sl < NS; sl++) {
-					const int o = sl * TP + tid;
-					acc.sp[o] = 0.0;
-					acc.sc[o] = 0.0;
-					if (!UNITW) acc.dw[o] = 0.0;
-					acc.cnt[o] = 0u;
-				}
-			};
-
-			// ---- chunk iterator over the neighbour cells of this slab (uniform across the CTA) --------------------------
+			// ---- chunk iterator over the neighbour cells of this slab: every warp walks the same sequence ---------------
 			int it_e = -1;
 			long long it_pos = 0, it_sub_end = 0, it_cell_end = 0;
 			int it_label = -1;
@@ -811,35 +812,98 @@ __global__ void __launch_bounds__(TP) k_tiled_rppi(const TiledArgs a) {
 					}
 				}
 			};
-			auto issue = [&](const Chunk &c, int b) {
-				if (tid == 0) {
-					const uint32_t bytes = (uint32_t)c.n * (uint32_t)sizeof(Cand);
-					mbar_expect_tx(&full[b], bytes);
-					bulk_load(buf + (size_t)b * CH, a.cand + c.start, bytes, &full[b]);
-				}
-			};
 
-			Chunk cur, nxt;
-			bool have = next_chunk(cur);
-			int bi = 0;
-			int cur_label = -1;
-			if (have) issue(cur, bi);
-			while (have) {
-				const bool have_n = next_chunk(nxt);
-				if (have_n) issue(nxt, bi ^ 1);
-				if (cur.label != cur_label) {
-					if (cur_label >= 0) flush(cur_label);
-					cur_label = cur.label;
+			if (producer) {
+				// ---- producer warp: keep the ring full with 1-D bulk copies -------------------------------------------
+				Chunk c;
+				while (next_chunk(c)) {
+					const unsigned st = chunk_no % STAGES, round = chunk_no / STAGES;
+					if (lane == 0) {
+						if (round > 0) mbar_wait(&empty[st], (round - 1) & 1u);
+						const uint32_t bytes = (uint32_t)c.n * (uint32_t)sizeof(Cand);
+						mbar_expect_tx(&full[st], bytes);
+						bulk_load(ring + (size_t)st * CH, a.cand + c.start, bytes, &full[st]);
+					}
+					chunk_no++;
 				}
-				if (bi == 0) {
-					mbar_wait(&full[0], phase0);
-					phase0 ^= 1u;
-				} else {
-					mbar_wait(&full[1], phase1);
-					phase1 ^= 1u;
-				}
-				// ---- per-warp culling against the cell's bounding box, then the pair loop --------------------------------
-				{
+			} else {
+				// ---- consumer warps ---------------------------------------------------------------------------------------
+				ZWindow zw = z_window(p.l, zlo, zhi, P);
+				if (!active) zw.dead = true;
+				if (active && zw.err) atomicExch(&a.flags[1], 1);
+				const double tn_lane = zw.dead ? -1.0 : TN;  // dead lanes never pass the range test
+				const bool warp_zg = __any_sync(0xffffffffu, !zw.dead && zw.gen);
+				const unsigned key = zw.dead ? 0xffffffffu
+											 : (((unsigned)p.jk << 16) | ((unsigned)(zw.b0 + 1) << 8) | (unsigned)(zw.b1 + 1));
+
+				// flush: fixed-order warp reduction of the private slots into this warp's accumulator copy
+				auto flush = [&](int jkD) {
+					unsigned todo = __ballot_sync(0xffffffffu, !zw.dead);
+					while (todo) {
+						const int leader = __ffs(todo) - 1;
+						const unsigned k = __shfl_sync(0xffffffffu, key, leader);
+						const unsigned grp = __ballot_sync(0xffffffffu, key == k) & todo;
+						const bool in = (grp >> lane) & 1u;
+						unsigned tot_cnt = 0;
+						double tot_sp = 0.0, tot_sc = 0.0, tot_dw = 0.0;
+						for (int sl = 0; sl < NS; sl++) {
+							const uint32_t so = (uint32_t)sl * TP;
+							const unsigned c = in ? lds_u32(acc.ac + so * 4u) : 0u;
+							const unsigned csum = __reduce_add_sync(0xffffffffu, c);
+							if (csum == 0u) continue;
+							double v0 = 0.0, v1 = 0.0;
+							if (in) lds_v2(v0, v1, acc.a2 + so * 16u);
+							const double xs = warp_sum(v0 * pe);
+							const double ys = warp_sum(v1 * pe);
+							const double zs = UNITW ? (double)csum : warp_sum(in ? lds_f64(acc.aw + so * 8u) * p.w : 0.0);
+							if (lane == sl) {
+								tot_cnt = csum;
+								tot_sp = xs;
+								tot_sc = ys;
+								tot_dw = zs;
+							}
+						}
+						if (lane < NS && tot_cnt) {
+							const int kb0 = (int)((k >> 8) & 0xffu) - 1, kb1 = (int)(k & 0xffu) - 1, kjk = (int)(k >> 16);
+							const int b2 = (lane & 1) ? kb1 : kb0;
+							if (b2 < 0) {
+								atomicExch(&a.flags[1], 1);
+							} else {
+								const size_t bin = (size_t)(lane >> 1) * P.n_2 + b2;
+								const size_t ia = (size_t)kjk * nb + bin;
+								pcnt[ia] += tot_cnt;
+								pddw[ia] += tot_dw;
+								psp[ia] += tot_sp;
+								psc[ia] += tot_sc;
+								if (P.num_jk > 0 && jkD != kjk) {
+									const size_t ib = (size_t)(J + jkD) * nb + bin;
+									pcnt[ib] += tot_cnt;
+									pddw[ib] += tot_dw;
+									psp[ib] += tot_sp;
+								}
+								binned += tot_cnt;
+							}
+						}
+						todo &= ~grp;
+					}
+					__syncwarp();
+					for (int sl = 0; sl < NS; sl++) {
+						sts_v2(acc.a2 + (uint32_t)sl * TP * 16u, 0.0, 0.0);
+						if (!UNITW) sts_f64(acc.aw + (uint32_t)sl * TP * 8u, 0.0);
+						sts_u32(acc.ac + (uint32_t)sl * TP * 4u, 0u);
+					}
+				};
+
+				Chunk cur;
+				int cur_label = -1;
+				while (next_chunk(cur)) {
+					const unsigned st = chunk_no % STAGES, round = chunk_no / STAGES;
+					chunk_no++;
+					if (cur.label != cur_label) {
+						if (cur_label >= 0) flush(cur_label);
+						cur_label = cur.label;
+					}
+					// per-warp culling against the cell's bounding box (needs no staged data)
 					const Desc &d = desc[cur.desc];
 					double ulo = __dsub_rn(p.u, d.umax), uhi = __dsub_rn(p.u, d.umin);
 					double vlo = __dsub_rn(p.v, d.vmax), vhi = __dsub_rn(p.v, d.vmin);
@@ -874,30 +938,30 @@ __global__ void __launch_bounds__(TP) k_tiled_rppi(const TiledArgs a) {
 					const double mv = vlo > 0.0 ? vlo : (vhi < 0.0 ? -vhi : 0.0);
 					const double dmin2 = __dadd_rn(__dmul_rn(mu, mu), __dmul_rn(mv, mv));
 					const bool need = !zw.dead && (nocull || dmin2 < TN);
-					if (__any_sync(0xffffffffu, need)) {
+					const bool go = __any_sync(0xffffffffu, need);
+					mbar_wait(&full[st], round & 1u);
+					if (go) {
 						if (!zw.dead) tested += (unsigned long long)cur.n;
 						const bool warp_xyw = __any_sync(0xffffffffu, !zw.dead && xyw);
-						const Cand *cb = buf + (size_t)bi * CH;
+						const uint32_t cb = ring_u32 + (uint32_t)st * (uint32_t)(CH * sizeof(Cand));
 						if (!warp_xyw && !warp_zg)
-							pair_loop<UNITW, false, false>(cb, cur.n, P, p.u, p.v, p.l, p.a0, p.a1, T0, tn_lane, zw, lut,
-														   a.lut_hi0, a.lut_shift, acc, tid, nan_pairs);
+							pair_loop<UNITW, false, false>(cb, cur.n, P, p.u, p.v, p.l, p.a0, p.a1, T0, tn_lane, zw, lut_u32,
+														   a.lut_hi0, a.lut_shift, acc, nan_pairs);
 						else if (!warp_xyw)
-							pair_loop<UNITW, false, true>(cb, cur.n, P, p.u, p.v, p.l, p.a0, p.a1, T0, tn_lane, zw, lut,
-														  a.lut_hi0, a.lut_shift, acc, tid, nan_pairs);
+							pair_loop<UNITW, false, true>(cb, cur.n, P, p.u, p.v, p.l, p.a0, p.a1, T0, tn_lane, zw, lut_u32,
+														  a.lut_hi0, a.lut_shift, acc, nan_pairs);
 						else if (!warp_zg)
-							pair_loop<UNITW, true, false>(cb, cur.n, P, p.u, p.v, p.l, p.a0, p.a1, T0, tn_lane, zw, lut,
-														  a.lut_hi0, a.lut_shift, acc, tid, nan_pairs);
+							pair_loop<UNITW, true, false>(cb, cur.n, P, p.u, p.v, p.l, p.a0, p.a1, T0, tn_lane, zw, lut_u32,
+														  a.lut_hi0, a.lut_shift, acc, nan_pairs);
 						else
-							pair_loop<UNITW, true, true>(cb, cur.n, P, p.u, p.v, p.l, p.a0, p.a1, T0, tn_lane, zw, lut,
-														 a.lut_hi0, a.lut_shift, acc, tid, nan_pairs);
+							pair_loop<UNITW, true, true>(cb, cur.n, P, p.u, p.v, p.l, p.a0, p.a1, T0, tn_lane, zw, lut_u32,
+														 a.lut_hi0, a.lut_shift, acc, nan_pairs);
 					}
+					__syncwarp();
+					if (lane == 0) mbar_arrive(&empty[st]);  // this warp is done with the stage
 				}
-				__syncthreads();  // every warp is done with buf[bi]: it may be refilled
-				bi ^= 1;
-				cur = nxt;
-				have = have_n;
+				if (cur_label >= 0) flush(cur_label);
 			}
-			if (cur_label >= 0) flush(cur_label);
 			__syncthreads();  // desc[] is rewritten for the next slab
 		}
 	}
@@ -908,7 +972,7 @@ __global__ void __launch_bounds__(TP) k_tiled_rppi(const TiledArgs a) {
 		binned += __shfl_down_sync(0xffffffffu, binned, o);
 		nan_pairs += __shfl_down_sync(0xffffffffu, nan_pairs, o);
 	}
-	if (lane == 0) {
+	if (lane == 0 && !producer) {
 		atomicAdd(&a.A.stats[0], tested);
 		atomicAdd(&a.A.stats[1], binned);
 		atomicAdd(&a.A.stats[2], nan_pairs);
@@ -991,8 +1055,8 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &g, const DevPara
 	a.shard_count = shard.count;
 	a.max_tasks = cfg.max_tasks;
 	a.flags = flags;
-	if (unit_w) k_tiled_rppi<true><<<Gc, TP, smem, st>>>(a);
-	else k_tiled_rppi<false><<<Gc, TP, smem, st>>>(a);
+	if (unit_w) k_tiled_rppi<true><<<Gc, TP + 32, smem, st>>>(a);
+	else k_tiled_rppi<false><<<Gc, TP + 32, smem, st>>>(a);
 	MIA_CUDA_CHECK(cudaGetLastError());
 	return 0;
 }
