@@ -30,8 +30,8 @@ namespace mia {
 
 constexpr int TP = 128;          // threads = shape galaxies per CTA
 constexpr int TW = TP / 32;      // warps per CTA
-constexpr int CH = 64;           // candidates per staged chunk
-constexpr int STAGES = 4;        // ring depth
+constexpr int CH = 32;           // candidates per staged chunk (<= 32: the suspect mask is one word)
+constexpr int STAGES = 2;        // per-warp double buffering
 constexpr int MAX_NEIGH = 128;   // neighbour columns per task
 constexpr int LUT_SIZE = 256;
 constexpr int MAX_SLOTS = 32;    // 2 * n_r <= 32
@@ -136,7 +136,7 @@ inline bool build_lut(const mia_params *p, TiledConfig &cfg) {
 }
 
 inline size_t tiled_smem_bytes(int n_r, bool unit_w) {
-	const size_t fixed = sizeof(Cand) * STAGES * CH + sizeof(LutEntry) * LUT_SIZE + sizeof(Desc) * MAX_NEIGH +
+	const size_t fixed = sizeof(Cand) * TW * STAGES * CH + sizeof(LutEntry) * LUT_SIZE + sizeof(Desc) * MAX_NEIGH +
 						 sizeof(int) * MAX_NEIGH * 2 + 256;
 	const size_t per_slot = (size_t)TP * (8 + 8 + 4 + (unit_w ? 0 : 8));
 	return fixed + per_slot * 2 * n_r;
@@ -532,15 +532,34 @@ struct PrivAcc {
 	uint32_t a2, ac, aw;
 };
 
-// One staged chunk against this thread's shape galaxy.
+// predicated shared stores: the pair loop is branch-free so that nvcc can interleave the arithmetic of consecutive
+// candidates (the FP64 pipe has ~8-cycle dependent-issue latency and only 3 warps per scheduler fit)
+__device__ __forceinline__ void sts_v2_if(bool p, uint32_t addr, double a, double b) {
+	asm volatile("{ .reg .pred q; setp.ne.u32 q, %3, 0; @q st.shared.v2.f64 [%0], {%1, %2}; }" ::"r"(addr), "d"(a), "d"(b),
+				 "r"((unsigned)p)
+				 : "memory");
+}
+__device__ __forceinline__ void sts_f64_if(bool p, uint32_t addr, double a) {
+	asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.shared.f64 [%0], %1; }" ::"r"(addr), "d"(a), "r"((unsigned)p)
+				 : "memory");
+}
+__device__ __forceinline__ void sts_u32_if(bool p, uint32_t addr, unsigned a) {
+	asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.shared.u32 [%0], %1; }" ::"r"(addr), "r"(a), "r"((unsigned)p)
+				 : "memory");
+}
+
+// One staged chunk (n <= 32 candidates at shared address cb) against this thread's shape galaxy.
 //   XYW : compare-and-wrap the projected separations per pair (lanes whose column pair crosses the periodic boundary)
 //   ZG  : compare-and-wrap + range-check the line-of-sight separation per pair (slab straddles +-L/2 or the Pi range)
 //         otherwise the lane-constant image shift is added (exactly the reference's `sep -= L` / `sep += L`)
+// Returns a bit mask of candidates whose |cos| is within 1e-12 of 1: they are NOT accumulated here but re-evaluated
+// with the reference's exact operation sequence by slow_pairs() (its NaN rule, measure_w_box_jk.py:416-417).
 template <bool UNITW, bool XYW, bool ZG>
-__device__ __forceinline__ void pair_loop(uint32_t cb, int n, const DevParams &P, double pu, double pv, double pl,
-										  double a0, double a1, double t0, double tn, const ZWindow &zw, uint32_t lut,
-										  int lut_hi0, int lut_shift, const PrivAcc &acc, unsigned long long &nan_pairs) {
+__device__ __forceinline__ unsigned pair_loop(uint32_t cb, int n, const DevParams &P, double pu, double pv, double pl,
+											  double a0, double a1, double t0, double tn, const ZWindow &zw, uint32_t lut,
+											  int lut_hi0, int lut_shift, const PrivAcc &acc) {
 	const double L = P.L, halfL = P.halfL;
+	unsigned suspects = 0u;
 	double cu, cv, cl, cw;
 	lds_v2(cu, cv, cb);
 	lds_v2(cl, cw, cb + 16);
@@ -553,98 +572,133 @@ __device__ __forceinline__ void pair_loop(uint32_t cb, int n, const DevParams &P
 		lds_v2(nl, nw, na + 16);
 		double du = __dsub_rn(pu, cu), dv = __dsub_rn(pv, cv);  // shape minus position, :401
 		if (XYW) {
-			if (du > halfL) du = __dsub_rn(du, L);
-			if (du < -halfL) du = __dadd_rn(du, L);
-			if (dv > halfL) dv = __dsub_rn(dv, L);
-			if (dv < -halfL) dv = __dadd_rn(dv, L);
+			du = (du > halfL) ? __dsub_rn(du, L) : du;
+			du = (du < -halfL) ? __dadd_rn(du, L) : du;
+			dv = (dv > halfL) ? __dsub_rn(dv, L) : dv;
+			dv = (dv < -halfL) ? __dadd_rn(dv, L) : dv;
 		}
 		const double r2 = __dadd_rn(__dmul_rn(du, du), __dmul_rn(dv, dv));  // :407 (before the sqrt)
-		if ((r2 >= t0) && (r2 < tn)) {
-			double dz = __dsub_rn(pl, cl);
-			bool ok = true;
-			if (ZG) {
-				if (P.periodic) {
-					if (dz > halfL) dz = __dsub_rn(dz, L);
-					if (dz < -halfL) dz = __dadd_rn(dz, L);
-				}
-				ok = (dz >= zw.t_lo) && (dz < zw.t_hi);
-			} else {
-				dz = __dadd_rn(dz, zw.shift);
+		bool ok = (r2 >= t0) && (r2 < tn);
+		double dz = __dsub_rn(pl, cl);
+		if (ZG) {
+			if (P.periodic) {
+				dz = (dz > halfL) ? __dsub_rn(dz, L) : dz;
+				dz = (dz < -halfL) ? __dadd_rn(dz, L) : dz;
 			}
-			if (ok) {
-				const int idx = (__double2hiint(r2) - lut_hi0) >> lut_shift;
-				double lthr;
-				int lbase;
-				lds_lut(lthr, lbase, lut + (uint32_t)idx * 16u);
-				const int rbin = lbase + ((r2 >= lthr) ? 1 : 0);
-				const uint32_t so = (uint32_t)(2 * rbin + ((dz >= zw.t_split) ? 1 : 0)) * (uint32_t)TP;
-				// private slots: issue the loads first, the arithmetic below hides their latency
-				double s0, s1, sw = 0.0;
-				lds_v2(s0, s1, acc.a2 + so * 16u);
-				const unsigned c0 = lds_u32(acc.ac + so * 4u);
-				if (!UNITW) sw = lds_f64(acc.aw + so * 8u);
-				const double cr = fma(du, a0, __dmul_rn(dv, a1));   // r_p cos(phi)
-				const double sr = fma(du, a1, -__dmul_rn(dv, a0));  // r_p sin(phi) (sign irrelevant)
-				const double inv = fast_rcp(r2);
-				const double inv2 = inv + inv;
-				const double t = cr * cr;
-				double gp = fma(t, inv2, -1.0);      // cos 2phi = 2 cos^2 - 1
-				double gc = (cr * fabs(sr)) * inv2;  // sin 2phi = 2 cos phi |sin phi|   (phi in [0, pi])
-				if (t >= r2 * (1.0 - 1e-12)) {       // |cos| ~ 1: apply the reference's NaN rule exactly
-					const double rp = __dsqrt_rn(r2);
-					const double c = __dadd_rn(__dmul_rn(__ddiv_rn(du, rp), a0), __dmul_rn(__ddiv_rn(dv, rp), a1));
-					if (!(fabs(c) <= 1.0)) {
-						gp = 0.0;
-						gc = 0.0;
-						nan_pairs++;
-					}
-				}
-				if (!UNITW) {
-					gp *= cw;
-					gc *= cw;
-					sts_f64(acc.aw + so * 8u, sw + cw);
-				}
-				sts_v2(acc.a2 + so * 16u, s0 + gp, s1 + gc);
-				sts_u32(acc.ac + so * 4u, c0 + 1u);
-			}
+			ok = ok && (dz >= zw.t_lo) && (dz < zw.t_hi);
+		} else {
+			dz = __dadd_rn(dz, zw.shift);
 		}
+		int idx = (__double2hiint(r2) - lut_hi0) >> lut_shift;
+		idx = min(max(idx, 0), LUT_SIZE - 1);  // rejected pairs may index anywhere: keep the load in bounds
+		double lthr;
+		int lbase;
+		lds_lut(lthr, lbase, lut + (uint32_t)idx * 16u);
+		const int rbin = lbase + ((r2 >= lthr) ? 1 : 0);
+		const uint32_t so = (uint32_t)(2 * rbin + ((dz >= zw.t_split) ? 1 : 0)) * (uint32_t)TP;
+		// private slots: loads first, the arithmetic below hides their latency
+		double s0, s1, sw = 0.0;
+		lds_v2(s0, s1, acc.a2 + so * 16u);
+		const unsigned c0 = lds_u32(acc.ac + so * 4u);
+		if (!UNITW) sw = lds_f64(acc.aw + so * 8u);
+		const double cr = fma(du, a0, __dmul_rn(dv, a1));   // r_p cos(phi)
+		const double sr = fma(du, a1, -__dmul_rn(dv, a0));  // r_p sin(phi) (sign irrelevant)
+		const double inv = fast_rcp(r2);
+		const double inv2 = inv + inv;
+		const double t = cr * cr;
+		double gp = fma(t, inv2, -1.0);      // cos 2phi = 2 cos^2 - 1
+		double gc = (cr * fabs(sr)) * inv2;  // sin 2phi = 2 cos phi |sin phi|   (phi in [0, pi])
+		const bool susp = ok && (t >= r2 * (1.0 - 1e-12));
+		suspects |= (susp ? 1u : 0u) << j;
+		ok = ok && !susp;
+		if (!UNITW) {
+			gp *= cw;
+			gc *= cw;
+			sts_f64_if(ok, acc.aw + so * 8u, sw + cw);
+		}
+		sts_v2_if(ok, acc.a2 + so * 16u, s0 + gp, s1 + gc);
+		sts_u32_if(ok, acc.ac + so * 4u, c0 + 1u);
 		cu = nu;
 		cv = nv;
 		cl = nl;
 		cw = nw;
 	}
+	return suspects;
+}
+
+// Rare path: the candidates flagged by pair_loop, with the reference's exact cos (and its NaN rule).
+template <bool UNITW>
+__device__ __noinline__ void slow_pairs(unsigned suspects, uint32_t cb, int periodic, double L, double halfL, double pu,
+										double pv, double pl, double a0, double a1, double t_split, uint32_t lut,
+										int lut_hi0, int lut_shift, PrivAcc acc, unsigned long long &nan_pairs) {
+	auto sep = [&](double s_, double c_) {  // measure_w_box_jk.py:401-404
+		double d = __dsub_rn(s_, c_);
+		if (periodic) {
+			if (d > halfL) d = __dsub_rn(d, L);
+			if (d < -halfL) d = __dadd_rn(d, L);
+		}
+		return d;
+	};
+	while (suspects) {
+		const int j = __ffs(suspects) - 1;
+		suspects &= suspects - 1u;
+		double cu, cv, cl, cw;
+		lds_v2(cu, cv, cb + (uint32_t)j * (uint32_t)sizeof(Cand));
+		lds_v2(cl, cw, cb + (uint32_t)j * (uint32_t)sizeof(Cand) + 16);
+		const double du = sep(pu, cu), dv = sep(pv, cv), dz = sep(pl, cl);
+		const double r2 = __dadd_rn(__dmul_rn(du, du), __dmul_rn(dv, dv));
+		const double rp = __dsqrt_rn(r2);
+		const double c = __dadd_rn(__dmul_rn(__ddiv_rn(du, rp), a0), __dmul_rn(__ddiv_rn(dv, rp), a1));
+		double gp = 0.0, gc = 0.0;
+		if (fabs(c) <= 1.0) shape_projection(c, gp, gc);
+		else nan_pairs++;
+		const int idx = (__double2hiint(r2) - lut_hi0) >> lut_shift;
+		double lthr;
+		int lbase;
+		lds_lut(lthr, lbase, lut + (uint32_t)idx * 16u);
+		const int rbin = lbase + ((r2 >= lthr) ? 1 : 0);
+		const uint32_t so = (uint32_t)(2 * rbin + ((dz >= t_split) ? 1 : 0)) * (uint32_t)TP;
+		double s0, s1;
+		lds_v2(s0, s1, acc.a2 + so * 16u);
+		const unsigned c0 = lds_u32(acc.ac + so * 4u);
+		if (!UNITW) {
+			gp *= cw;
+			gc *= cw;
+			sts_f64(acc.aw + so * 8u, lds_f64(acc.aw + so * 8u) + cw);
+		}
+		sts_v2(acc.a2 + so * 16u, s0 + gp, s1 + gc);
+		sts_u32(acc.ac + so * 4u, c0 + 1u);
+	}
 }
 
 template <bool UNITW>
-__global__ void __launch_bounds__(TP + 32) k_tiled_rppi(const TiledArgs a) {
+__global__ void __launch_bounds__(TP) k_tiled_rppi(const TiledArgs a) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	const DevParams &P = a.P;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const bool producer = (warp == TW);  // warp-specialised: TW consumer warps + one bulk-copy producer warp
 	const int NS = 2 * P.n_r, nb = P.n_r * P.n_2;
 	const int J = P.num_jk > 0 ? P.num_jk : 1;
 
 	// ---- shared memory carve-up ------------------------------------------------------------------------------------
-	Cand *ring = reinterpret_cast<Cand *>(smem);
-	LutEntry *lut_s = reinterpret_cast<LutEntry *>(smem + sizeof(Cand) * STAGES * CH);
+	Cand *ring = reinterpret_cast<Cand *>(smem);  // [warp][stage][CH]: every warp runs its own double-buffered stream
+	LutEntry *lut_s = reinterpret_cast<LutEntry *>(smem + sizeof(Cand) * TW * STAGES * CH);
 	Desc *desc = reinterpret_cast<Desc *>(reinterpret_cast<unsigned char *>(lut_s) + sizeof(LutEntry) * LUT_SIZE);
 	int *nlist = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(desc) + sizeof(Desc) * MAX_NEIGH);
 	int *nkey = nlist + MAX_NEIGH;
-	uint64_t *full = reinterpret_cast<uint64_t *>(nkey + MAX_NEIGH);
-	uint64_t *empty = full + STAGES;
-	int *misc = reinterpret_cast<int *>(empty + STAGES);  // [0] first task, [1] end task, [2] neighbour count
+	uint64_t *full = reinterpret_cast<uint64_t *>(nkey + MAX_NEIGH);  // [warp][stage]
+	int *misc = reinterpret_cast<int *>(full + TW * STAGES);          // [0] first task, [1] end task, [2] neighbour count
 	unsigned char *accbase = reinterpret_cast<unsigned char *>(full) + 256;
-	const uint32_t ring_u32 = smem_u32(ring), lut_u32 = smem_u32(lut_s), acc_u32 = smem_u32(accbase);
+	const uint32_t lut_u32 = smem_u32(lut_s), acc_u32 = smem_u32(accbase);
+	Cand *my_ring = ring + (size_t)warp * STAGES * CH;
+	uint64_t *my_full = full + warp * STAGES;
+	const uint32_t my_ring_u32 = smem_u32(my_ring);
 	PrivAcc acc;  // addresses of slot 0 of this thread
 	acc.a2 = acc_u32 + (uint32_t)tid * 16u;
 	acc.aw = acc_u32 + (uint32_t)NS * TP * 16u + (uint32_t)tid * 8u;
 	acc.ac = acc_u32 + (uint32_t)NS * TP * (UNITW ? 16u : 24u) + (uint32_t)tid * 4u;
 
 	if (tid == 0) {
-		for (int s = 0; s < STAGES; s++) {
-			mbar_init(&full[s], 1);
-			mbar_init(&empty[s], TW);
-		}
+		for (int s = 0; s < TW * STAGES; s++) mbar_init(&full[s], 1);
 		mbar_fence_init();
 		// ---- my share of the tasks: slots of equal estimated work ---------------------------------------------------
 		const int nt = a.n_tasks[0];
@@ -674,22 +728,22 @@ __global__ void __launch_bounds__(TP + 32) k_tiled_rppi(const TiledArgs a) {
 		if (blockIdx.x == 0) a.A.stats[6] = (unsigned long long)nt;
 	}
 	for (int e = tid; e < LUT_SIZE; e += blockDim.x) lut_s[e] = a.lut[e];
-	if (!producer) {
-		for (int s = 0; s < NS; s++) {
-			sts_v2(acc.a2 + (uint32_t)s * TP * 16u, 0.0, 0.0);
-			if (!UNITW) sts_f64(acc.aw + (uint32_t)s * TP * 8u, 0.0);
-			sts_u32(acc.ac + (uint32_t)s * TP * 4u, 0u);
-		}
+	for (int s = 0; s < NS; s++) {
+		sts_v2(acc.a2 + (uint32_t)s * TP * 16u, 0.0, 0.0);
+		if (!UNITW) sts_f64(acc.aw + (uint32_t)s * TP * 8u, 0.0);
+		sts_u32(acc.ac + (uint32_t)s * TP * 4u, 0u);
 	}
 	__syncthreads();
 	const int task0 = misc[0], task1 = misc[1];
 
 	// this warp's accumulator copy in HBM
-	const size_t part = (size_t)(blockIdx.x * TW + (producer ? 0 : warp)) * (size_t)a.A.rows * nb;
+	const size_t part = (size_t)(blockIdx.x * TW + warp) * (size_t)a.A.rows * nb;
 	unsigned long long *pcnt = a.A.cnt + part;
 	double *pddw = a.A.ddw + part, *psp = a.A.sp + part, *psc = a.A.sc + part;
 
-	unsigned chunk_no = 0;  // running chunk counter: stage = chunk_no % STAGES, round parity = (chunk_no / STAGES) & 1
+	uint32_t phase[STAGES];
+#pragma unroll
+	for (int s = 0; s < STAGES; s++) phase[s] = 0u;
 	unsigned long long tested = 0, binned = 0, nan_pairs = 0;
 	const double T0 = P.r2_thr[0], TN = P.r2_thr[P.n_r];
 	const double cs = P.L / P.ncu, reach = sqrt(TN) * (1.0 + 1e-6);
@@ -697,7 +751,7 @@ __global__ void __launch_bounds__(TP + 32) k_tiled_rppi(const TiledArgs a) {
 	for (int task = task0; task < task1; task++) {
 		const int col = a.task_col[task];
 		const int np = a.task_n[task];
-		const bool active = !producer && tid < np;
+		const bool active = tid < np;
 		Prim p;
 		if (active) {
 			p = a.prim[a.task_first[task] + tid];
@@ -773,17 +827,85 @@ __global__ void __launch_bounds__(TP + 32) k_tiled_rppi(const TiledArgs a) {
 			}
 			__syncthreads();
 
-			// ---- chunk iterator over the neighbour cells of this slab: every warp walks the same sequence ---------------
+			ZWindow zw = z_window(p.l, zlo, zhi, P);
+			if (!active) zw.dead = true;
+			if (active && zw.err) atomicExch(&a.flags[1], 1);
+			const double tn_lane = zw.dead ? -1.0 : TN;  // dead lanes never pass the range test
+			const bool warp_zg = __any_sync(0xffffffffu, !zw.dead && zw.gen);
+			const unsigned key = zw.dead ? 0xffffffffu
+										 : (((unsigned)p.jk << 16) | ((unsigned)(zw.b0 + 1) << 8) | (unsigned)(zw.b1 + 1));
+			const bool warp_live = __any_sync(0xffffffffu, !zw.dead);
+
+			// ---- flush: fixed-order warp reduction of the private slots into this warp's accumulator copy -------------
+			auto flush = [&](int jkD) {
+				unsigned todo = __ballot_sync(0xffffffffu, !zw.dead);
+				while (todo) {
+					const int leader = __ffs(todo) - 1;
+					const unsigned k = __shfl_sync(0xffffffffu, key, leader);
+					const unsigned grp = __ballot_sync(0xffffffffu, key == k) & todo;
+					const bool in = (grp >> lane) & 1u;
+					unsigned tot_cnt = 0;
+					double tot_sp = 0.0, tot_sc = 0.0, tot_dw = 0.0;
+					for (int sl = 0; sl < NS; sl++) {
+						const uint32_t so = (uint32_t)sl * TP;
+						const unsigned c = in ? lds_u32(acc.ac + so * 4u) : 0u;
+						const unsigned csum = __reduce_add_sync(0xffffffffu, c);
+						if (csum == 0u) continue;
+						double v0 = 0.0, v1 = 0.0;
+						if (in) lds_v2(v0, v1, acc.a2 + so * 16u);
+						const double xs = warp_sum(v0 * pe);
+						const double ys = warp_sum(v1 * pe);
+						const double zs = UNITW ? (double)csum : warp_sum(in ? lds_f64(acc.aw + so * 8u) * p.w : 0.0);
+						if (lane == sl) {
+							tot_cnt = csum;
+							tot_sp = xs;
+							tot_sc = ys;
+							tot_dw = zs;
+						}
+					}
+					if (lane < NS && tot_cnt) {
+						const int kb0 = (int)((k >> 8) & 0xffu) - 1, kb1 = (int)(k & 0xffu) - 1, kjk = (int)(k >> 16);
+						const int b2 = (lane & 1) ? kb1 : kb0;
+						if (b2 < 0) {
+							atomicExch(&a.flags[1], 1);
+						} else {
+							const size_t bin = (size_t)(lane >> 1) * P.n_2 + b2;
+							const size_t ia = (size_t)kjk * nb + bin;
+							pcnt[ia] += tot_cnt;
+							pddw[ia] += tot_dw;
+							psp[ia] += tot_sp;
+							psc[ia] += tot_sc;
+							if (P.num_jk > 0 && jkD != kjk) {
+								const size_t ib = (size_t)(J + jkD) * nb + bin;
+								pcnt[ib] += tot_cnt;
+								pddw[ib] += tot_dw;
+								psp[ib] += tot_sp;
+							}
+							binned += tot_cnt;
+						}
+					}
+					todo &= ~grp;
+				}
+				__syncwarp();
+				for (int sl = 0; sl < NS; sl++) {
+					sts_v2(acc.a2 + (uint32_t)sl * TP * 16u, 0.0, 0.0);
+					if (!UNITW) sts_f64(acc.aw + (uint32_t)sl * TP * 8u, 0.0);
+					sts_u32(acc.ac + (uint32_t)sl * TP * 4u, 0u);
+				}
+			};
+
+			// ---- chunk iterator over the neighbour cells of this slab ---------------------------------------------------
 			int it_e = -1;
 			long long it_pos = 0, it_sub_end = 0, it_cell_end = 0;
 			int it_label = -1;
+			bool it_go = false, it_xyw = false;  // verdict of the per-warp cull for the current cell
 			auto next_chunk = [&](Chunk &c) -> bool {
 				for (;;) {
 					if (it_pos < it_sub_end) {
 						c.start = it_pos;
 						c.n = (int)((it_sub_end - it_pos < CH) ? (it_sub_end - it_pos) : CH);
 						c.label = it_label;
-						c.desc = it_e;
+						c.desc = it_xyw ? 1 : 0;
 						it_pos += c.n;
 						return true;
 					}
@@ -799,6 +921,45 @@ __global__ void __launch_bounds__(TP + 32) k_tiled_rppi(const TiledArgs a) {
 					if (it_e >= nn) return false;
 					const Desc &d = desc[it_e];
 					if (d.n == 0) continue;
+					// per-warp culling against the cell's bounding box: can any lane have a pair within reach?
+					{
+						double ulo = __dsub_rn(p.u, d.umax), uhi = __dsub_rn(p.u, d.umin);
+						double vlo = __dsub_rn(p.v, d.vmax), vhi = __dsub_rn(p.v, d.vmin);
+						bool xyw = false, nocull = false;
+						if (P.periodic) {
+							if (!(ulo >= -P.halfL && uhi <= P.halfL)) {
+								xyw = true;
+								if (ulo > P.halfL) {
+									ulo = __dsub_rn(ulo, P.L);
+									uhi = __dsub_rn(uhi, P.L);
+								} else if (uhi < -P.halfL) {
+									ulo = __dadd_rn(ulo, P.L);
+									uhi = __dadd_rn(uhi, P.L);
+								} else {
+									nocull = true;
+								}
+							}
+							if (!(vlo >= -P.halfL && vhi <= P.halfL)) {
+								xyw = true;
+								if (vlo > P.halfL) {
+									vlo = __dsub_rn(vlo, P.L);
+									vhi = __dsub_rn(vhi, P.L);
+								} else if (vhi < -P.halfL) {
+									vlo = __dadd_rn(vlo, P.L);
+									vhi = __dadd_rn(vhi, P.L);
+								} else {
+									nocull = true;
+								}
+							}
+						}
+						const double mu = ulo > 0.0 ? ulo : (uhi < 0.0 ? -uhi : 0.0);
+						const double mv = vlo > 0.0 ? vlo : (vhi < 0.0 ? -vhi : 0.0);
+						const double dmin2 = __dadd_rn(__dmul_rn(mu, mu), __dmul_rn(mv, mv));
+						const bool need = !zw.dead && (nocull || dmin2 < TN);
+						it_go = __any_sync(0xffffffffu, need);
+						it_xyw = __any_sync(0xffffffffu, !zw.dead && xyw);
+					}
+					if (!it_go) continue;  // no lane of this warp can reach the cell: it is never even staged
 					it_pos = d.start;
 					it_cell_end = d.start + d.n;
 					if (d.nlab <= 1) {
@@ -812,153 +973,50 @@ __global__ void __launch_bounds__(TP + 32) k_tiled_rppi(const TiledArgs a) {
 					}
 				}
 			};
-
-			if (producer) {
-				// ---- producer warp: keep the ring full with 1-D bulk copies -------------------------------------------
-				Chunk c;
-				while (next_chunk(c)) {
-					const unsigned st = chunk_no % STAGES, round = chunk_no / STAGES;
-					if (lane == 0) {
-						if (round > 0) mbar_wait(&empty[st], (round - 1) & 1u);
-						const uint32_t bytes = (uint32_t)c.n * (uint32_t)sizeof(Cand);
-						mbar_expect_tx(&full[st], bytes);
-						bulk_load(ring + (size_t)st * CH, a.cand + c.start, bytes, &full[st]);
-					}
-					chunk_no++;
+			auto issue = [&](const Chunk &c, int st) {
+				if (lane == 0) {
+					const uint32_t bytes = (uint32_t)c.n * (uint32_t)sizeof(Cand);
+					mbar_expect_tx(&my_full[st], bytes);
+					bulk_load(my_ring + (size_t)st * CH, a.cand + c.start, bytes, &my_full[st]);
 				}
-			} else {
-				// ---- consumer warps ---------------------------------------------------------------------------------------
-				ZWindow zw = z_window(p.l, zlo, zhi, P);
-				if (!active) zw.dead = true;
-				if (active && zw.err) atomicExch(&a.flags[1], 1);
-				const double tn_lane = zw.dead ? -1.0 : TN;  // dead lanes never pass the range test
-				const bool warp_zg = __any_sync(0xffffffffu, !zw.dead && zw.gen);
-				const unsigned key = zw.dead ? 0xffffffffu
-											 : (((unsigned)p.jk << 16) | ((unsigned)(zw.b0 + 1) << 8) | (unsigned)(zw.b1 + 1));
+			};
 
-				// flush: fixed-order warp reduction of the private slots into this warp's accumulator copy
-				auto flush = [&](int jkD) {
-					unsigned todo = __ballot_sync(0xffffffffu, !zw.dead);
-					while (todo) {
-						const int leader = __ffs(todo) - 1;
-						const unsigned k = __shfl_sync(0xffffffffu, key, leader);
-						const unsigned grp = __ballot_sync(0xffffffffu, key == k) & todo;
-						const bool in = (grp >> lane) & 1u;
-						unsigned tot_cnt = 0;
-						double tot_sp = 0.0, tot_sc = 0.0, tot_dw = 0.0;
-						for (int sl = 0; sl < NS; sl++) {
-							const uint32_t so = (uint32_t)sl * TP;
-							const unsigned c = in ? lds_u32(acc.ac + so * 4u) : 0u;
-							const unsigned csum = __reduce_add_sync(0xffffffffu, c);
-							if (csum == 0u) continue;
-							double v0 = 0.0, v1 = 0.0;
-							if (in) lds_v2(v0, v1, acc.a2 + so * 16u);
-							const double xs = warp_sum(v0 * pe);
-							const double ys = warp_sum(v1 * pe);
-							const double zs = UNITW ? (double)csum : warp_sum(in ? lds_f64(acc.aw + so * 8u) * p.w : 0.0);
-							if (lane == sl) {
-								tot_cnt = csum;
-								tot_sp = xs;
-								tot_sc = ys;
-								tot_dw = zs;
-							}
-						}
-						if (lane < NS && tot_cnt) {
-							const int kb0 = (int)((k >> 8) & 0xffu) - 1, kb1 = (int)(k & 0xffu) - 1, kjk = (int)(k >> 16);
-							const int b2 = (lane & 1) ? kb1 : kb0;
-							if (b2 < 0) {
-								atomicExch(&a.flags[1], 1);
-							} else {
-								const size_t bin = (size_t)(lane >> 1) * P.n_2 + b2;
-								const size_t ia = (size_t)kjk * nb + bin;
-								pcnt[ia] += tot_cnt;
-								pddw[ia] += tot_dw;
-								psp[ia] += tot_sp;
-								psc[ia] += tot_sc;
-								if (P.num_jk > 0 && jkD != kjk) {
-									const size_t ib = (size_t)(J + jkD) * nb + bin;
-									pcnt[ib] += tot_cnt;
-									pddw[ib] += tot_dw;
-									psp[ib] += tot_sp;
-								}
-								binned += tot_cnt;
-							}
-						}
-						todo &= ~grp;
-					}
-					__syncwarp();
-					for (int sl = 0; sl < NS; sl++) {
-						sts_v2(acc.a2 + (uint32_t)sl * TP * 16u, 0.0, 0.0);
-						if (!UNITW) sts_f64(acc.aw + (uint32_t)sl * TP * 8u, 0.0);
-						sts_u32(acc.ac + (uint32_t)sl * TP * 4u, 0u);
-					}
-				};
-
-				Chunk cur;
-				int cur_label = -1;
-				while (next_chunk(cur)) {
-					const unsigned st = chunk_no % STAGES, round = chunk_no / STAGES;
-					chunk_no++;
+			if (warp_live) {
+				Chunk cur, nxt;
+				bool have = next_chunk(cur);
+				int st = 0, cur_label = -1;
+				if (have) issue(cur, st);
+				while (have) {
+					const bool have_n = next_chunk(nxt);
+					if (have_n) issue(nxt, st ^ 1);
 					if (cur.label != cur_label) {
 						if (cur_label >= 0) flush(cur_label);
 						cur_label = cur.label;
 					}
-					// per-warp culling against the cell's bounding box (needs no staged data)
-					const Desc &d = desc[cur.desc];
-					double ulo = __dsub_rn(p.u, d.umax), uhi = __dsub_rn(p.u, d.umin);
-					double vlo = __dsub_rn(p.v, d.vmax), vhi = __dsub_rn(p.v, d.vmin);
-					bool xyw = false, nocull = false;
-					if (P.periodic) {
-						if (!(ulo >= -P.halfL && uhi <= P.halfL)) {
-							xyw = true;
-							if (ulo > P.halfL) {
-								ulo = __dsub_rn(ulo, P.L);
-								uhi = __dsub_rn(uhi, P.L);
-							} else if (uhi < -P.halfL) {
-								ulo = __dadd_rn(ulo, P.L);
-								uhi = __dadd_rn(uhi, P.L);
-							} else {
-								nocull = true;
-							}
-						}
-						if (!(vlo >= -P.halfL && vhi <= P.halfL)) {
-							xyw = true;
-							if (vlo > P.halfL) {
-								vlo = __dsub_rn(vlo, P.L);
-								vhi = __dsub_rn(vhi, P.L);
-							} else if (vhi < -P.halfL) {
-								vlo = __dadd_rn(vlo, P.L);
-								vhi = __dadd_rn(vhi, P.L);
-							} else {
-								nocull = true;
-							}
-						}
-					}
-					const double mu = ulo > 0.0 ? ulo : (uhi < 0.0 ? -uhi : 0.0);
-					const double mv = vlo > 0.0 ? vlo : (vhi < 0.0 ? -vhi : 0.0);
-					const double dmin2 = __dadd_rn(__dmul_rn(mu, mu), __dmul_rn(mv, mv));
-					const bool need = !zw.dead && (nocull || dmin2 < TN);
-					const bool go = __any_sync(0xffffffffu, need);
-					mbar_wait(&full[st], round & 1u);
-					if (go) {
-						if (!zw.dead) tested += (unsigned long long)cur.n;
-						const bool warp_xyw = __any_sync(0xffffffffu, !zw.dead && xyw);
-						const uint32_t cb = ring_u32 + (uint32_t)st * (uint32_t)(CH * sizeof(Cand));
-						if (!warp_xyw && !warp_zg)
-							pair_loop<UNITW, false, false>(cb, cur.n, P, p.u, p.v, p.l, p.a0, p.a1, T0, tn_lane, zw, lut_u32,
-														   a.lut_hi0, a.lut_shift, acc, nan_pairs);
-						else if (!warp_xyw)
-							pair_loop<UNITW, false, true>(cb, cur.n, P, p.u, p.v, p.l, p.a0, p.a1, T0, tn_lane, zw, lut_u32,
-														  a.lut_hi0, a.lut_shift, acc, nan_pairs);
-						else if (!warp_zg)
-							pair_loop<UNITW, true, false>(cb, cur.n, P, p.u, p.v, p.l, p.a0, p.a1, T0, tn_lane, zw, lut_u32,
-														  a.lut_hi0, a.lut_shift, acc, nan_pairs);
-						else
-							pair_loop<UNITW, true, true>(cb, cur.n, P, p.u, p.v, p.l, p.a0, p.a1, T0, tn_lane, zw, lut_u32,
-														 a.lut_hi0, a.lut_shift, acc, nan_pairs);
-					}
-					__syncwarp();
-					if (lane == 0) mbar_arrive(&empty[st]);  // this warp is done with the stage
+					mbar_wait(&my_full[st], phase[st]);
+					phase[st] ^= 1u;
+					if (!zw.dead) tested += (unsigned long long)cur.n;
+					const uint32_t cb = my_ring_u32 + (uint32_t)st * (uint32_t)(CH * sizeof(Cand));
+					unsigned susp;
+					if (!cur.desc && !warp_zg)
+						susp = pair_loop<UNITW, false, false>(cb, cur.n, P, p.u, p.v, p.l, p.a0, p.a1, T0, tn_lane, zw, lut_u32,
+															  a.lut_hi0, a.lut_shift, acc);
+					else if (!cur.desc)
+						susp = pair_loop<UNITW, false, true>(cb, cur.n, P, p.u, p.v, p.l, p.a0, p.a1, T0, tn_lane, zw, lut_u32,
+															 a.lut_hi0, a.lut_shift, acc);
+					else if (!warp_zg)
+						susp = pair_loop<UNITW, true, false>(cb, cur.n, P, p.u, p.v, p.l, p.a0, p.a1, T0, tn_lane, zw, lut_u32,
+															 a.lut_hi0, a.lut_shift, acc);
+					else
+						susp = pair_loop<UNITW, true, true>(cb, cur.n, P, p.u, p.v, p.l, p.a0, p.a1, T0, tn_lane, zw, lut_u32,
+															a.lut_hi0, a.lut_shift, acc);
+					if (__any_sync(0xffffffffu, susp != 0u))
+						slow_pairs<UNITW>(susp, cb, P.periodic, P.L, P.halfL, p.u, p.v, p.l, p.a0, p.a1, zw.t_split, lut_u32,
+										  a.lut_hi0, a.lut_shift, acc, nan_pairs);
+					__syncwarp();  // every lane is done with the stage before it is refilled
+					st ^= 1;
+					cur = nxt;
+					have = have_n;
 				}
 				if (cur_label >= 0) flush(cur_label);
 			}
@@ -972,7 +1030,7 @@ __global__ void __launch_bounds__(TP + 32) k_tiled_rppi(const TiledArgs a) {
 		binned += __shfl_down_sync(0xffffffffu, binned, o);
 		nan_pairs += __shfl_down_sync(0xffffffffu, nan_pairs, o);
 	}
-	if (lane == 0 && !producer) {
+	if (lane == 0) {
 		atomicAdd(&a.A.stats[0], tested);
 		atomicAdd(&a.A.stats[1], binned);
 		atomicAdd(&a.A.stats[2], nan_pairs);
@@ -1055,8 +1113,8 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &g, const DevPara
 	a.shard_count = shard.count;
 	a.max_tasks = cfg.max_tasks;
 	a.flags = flags;
-	if (unit_w) k_tiled_rppi<true><<<Gc, TP + 32, smem, st>>>(a);
-	else k_tiled_rppi<false><<<Gc, TP + 32, smem, st>>>(a);
+	if (unit_w) k_tiled_rppi<true><<<Gc, TP, smem, st>>>(a);
+	else k_tiled_rppi<false><<<Gc, TP, smem, st>>>(a);
 	MIA_CUDA_CHECK(cudaGetLastError());
 	return 0;
 }
