@@ -559,14 +559,21 @@ __device__ __forceinline__ unsigned pair_loop(uint32_t cb, int n, const DevParam
 											  double a0, double a1, double t0, double tn, const ZWindow &zw, uint32_t lut,
 											  int lut_hi0, int lut_shift, const PrivAcc &acc) {
 	const double L = P.L, halfL = P.halfL;
+	// squared separations are non-negative doubles: their bit patterns order like the values, so every comparison of
+	// r_p^2 against a threshold is done on the INTEGER pipe and the FP64 pipe (the bound of this kernel) is spared
+	const long long t0b = __double_as_longlong(t0), tnb = __double_as_longlong(tn);
 	unsigned suspects = 0u;
-	double cu, cv, cl, cw;
+	double cu, cv, cl, cw, mu_, mv_, ml_, mw_;  // current candidate and the one after it (prefetch distance 2)
 	lds_v2(cu, cv, cb);
 	lds_v2(cl, cw, cb + 16);
-#pragma unroll 2
+	{
+		const uint32_t a1_ = cb + (uint32_t)((1 < n) ? 1 : 0) * (uint32_t)sizeof(Cand);
+		lds_v2(mu_, mv_, a1_);
+		lds_v2(ml_, mw_, a1_ + 16);
+	}
+#pragma unroll 4
 	for (int j = 0; j < n; j++) {
-		// software prefetch of the next candidate (clamped: the last iteration re-reads its own entry)
-		const uint32_t na = cb + (uint32_t)((j + 1 < n) ? (j + 1) : j) * (uint32_t)sizeof(Cand);
+		const uint32_t na = cb + (uint32_t)((j + 2 < n) ? (j + 2) : (n - 1)) * (uint32_t)sizeof(Cand);
 		double nu, nv, nl, nw;
 		lds_v2(nu, nv, na);
 		lds_v2(nl, nw, na + 16);
@@ -578,7 +585,8 @@ __device__ __forceinline__ unsigned pair_loop(uint32_t cb, int n, const DevParam
 			dv = (dv < -halfL) ? __dadd_rn(dv, L) : dv;
 		}
 		const double r2 = __dadd_rn(__dmul_rn(du, du), __dmul_rn(dv, dv));  // :407 (before the sqrt)
-		bool ok = (r2 >= t0) && (r2 < tn);
+		const long long r2b = __double_as_longlong(r2);
+		bool ok = (r2b >= t0b) && (r2b < tnb);
 		double dz = __dsub_rn(pl, cl);
 		if (ZG) {
 			if (P.periodic) {
@@ -589,12 +597,11 @@ __device__ __forceinline__ unsigned pair_loop(uint32_t cb, int n, const DevParam
 		} else {
 			dz = __dadd_rn(dz, zw.shift);
 		}
-		int idx = (__double2hiint(r2) - lut_hi0) >> lut_shift;
-		idx = min(max(idx, 0), LUT_SIZE - 1);  // rejected pairs may index anywhere: keep the load in bounds
-		double lthr;
-		int lbase;
-		lds_lut(lthr, lbase, lut + (uint32_t)idx * 16u);
-		const int rbin = lbase + ((r2 >= lthr) ? 1 : 0);
+		// rejected pairs may index anywhere: the unsigned clamp keeps the load in bounds
+		const unsigned idx = min((unsigned)(__double2hiint(r2) - lut_hi0) >> lut_shift, (unsigned)(LUT_SIZE - 1));
+		long long lthr, lbase;
+		asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lthr), "=l"(lbase) : "r"(lut + idx * 16u));
+		const int rbin = (int)lbase + ((r2b >= lthr) ? 1 : 0);
 		const uint32_t so = (uint32_t)(2 * rbin + ((dz >= zw.t_split) ? 1 : 0)) * (uint32_t)TP;
 		// private slots: loads first, the arithmetic below hides their latency
 		double s0, s1, sw = 0.0;
@@ -603,12 +610,19 @@ __device__ __forceinline__ unsigned pair_loop(uint32_t cb, int n, const DevParam
 		if (!UNITW) sw = lds_f64(acc.aw + so * 8u);
 		const double cr = fma(du, a0, __dmul_rn(dv, a1));   // r_p cos(phi)
 		const double sr = fma(du, a1, -__dmul_rn(dv, a0));  // r_p sin(phi) (sign irrelevant)
-		const double inv = fast_rcp(r2);
-		const double inv2 = inv + inv;
-		const double t = cr * cr;
-		double gp = fma(t, inv2, -1.0);      // cos 2phi = 2 cos^2 - 1
-		double gc = (cr * fabs(sr)) * inv2;  // sin 2phi = 2 cos phi |sin phi|   (phi in [0, pi])
-		const bool susp = ok && (t >= r2 * (1.0 - 1e-12));
+		// 2 / r2: 20-bit hardware seed, one cubically convergent step y(1 + e + e^2) (relative error ~1e-17; a plain
+		// Newton step leaves a one-signed 1e-12 bias that survives the cancellation in the S+D sums), then doubling by
+		// an exponent increment
+		double y;
+		asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r2));
+		{
+			const double e = fma(-r2, y, 1.0);
+			y = fma(y, fma(e, e, e), y);
+		}
+		const double inv2 = __hiloint2double(__double2hiint(y) + 0x00100000, __double2loint(y));
+		double gp = fma(cr * cr, inv2, -1.0);  // cos 2phi = 2 cos^2 - 1
+		double gc = (cr * fabs(sr)) * inv2;    // sin 2phi = 2 cos phi |sin phi|   (phi in [0, pi])
+		const bool susp = ok && (gp >= 1.0 - 1e-11);  // |cos| ~ 1: the reference's NaN rule may apply -> exact path
 		suspects |= (susp ? 1u : 0u) << j;
 		ok = ok && !susp;
 		if (!UNITW) {
@@ -618,10 +632,14 @@ __device__ __forceinline__ unsigned pair_loop(uint32_t cb, int n, const DevParam
 		}
 		sts_v2_if(ok, acc.a2 + so * 16u, s0 + gp, s1 + gc);
 		sts_u32_if(ok, acc.ac + so * 4u, c0 + 1u);
-		cu = nu;
-		cv = nv;
-		cl = nl;
-		cw = nw;
+		cu = mu_;
+		cv = mv_;
+		cl = ml_;
+		cw = mw_;
+		mu_ = nu;
+		mv_ = nv;
+		ml_ = nl;
+		mw_ = nw;
 	}
 	return suspects;
 }
@@ -741,9 +759,7 @@ __global__ void __launch_bounds__(TP) k_tiled_rppi(const TiledArgs a) {
 	unsigned long long *pcnt = a.A.cnt + part;
 	double *pddw = a.A.ddw + part, *psp = a.A.sp + part, *psc = a.A.sc + part;
 
-	uint32_t phase[STAGES];
-#pragma unroll
-	for (int s = 0; s < STAGES; s++) phase[s] = 0u;
+	uint32_t phase0 = 0u, phase1 = 0u;  // parity of the two stages of this warp's stream
 	unsigned long long tested = 0, binned = 0, nan_pairs = 0;
 	const double T0 = P.r2_thr[0], TN = P.r2_thr[P.n_r];
 	const double cs = P.L / P.ncu, reach = sqrt(TN) * (1.0 + 1e-6);
@@ -993,8 +1009,13 @@ __global__ void __launch_bounds__(TP) k_tiled_rppi(const TiledArgs a) {
 						if (cur_label >= 0) flush(cur_label);
 						cur_label = cur.label;
 					}
-					mbar_wait(&my_full[st], phase[st]);
-					phase[st] ^= 1u;
+					if (st == 0) {
+						mbar_wait(&my_full[0], phase0);
+						phase0 ^= 1u;
+					} else {
+						mbar_wait(&my_full[1], phase1);
+						phase1 ^= 1u;
+					}
 					if (!zw.dead) tested += (unsigned long long)cur.n;
 					const uint32_t cb = my_ring_u32 + (uint32_t)st * (uint32_t)(CH * sizeof(Cand));
 					unsigned susp;
