@@ -2,25 +2,29 @@
 //
 // Replaces the hot loop of the reference, src/measureia/measure_w_box_jk.py:387-461 (and measure_w_box.py:313-365).
 //
-// Idea ("windowed private histograms"):
-//   * one thread owns one shape galaxy (registers); a CTA owns TP consecutive cell-sorted shape galaxies of one grid
-//     COLUMN (a cell of the two projected axes spanning the whole line of sight);
-//   * position galaxies are staged cell by cell into shared memory with 1-D bulk (TMA) copies -- a cell is one
-//     contiguous 32-byte-per-galaxy range of the sorted catalogue -- double buffered behind an mbarrier, and every
-//     thread of the CTA reads the same candidate (shared-memory broadcast);
-//   * the grid is cut along the line of sight into slabs thinner than one Pi bin.  For a given shape galaxy, all
-//     candidates of one slab fall into at most TWO Pi bins, and all candidates of one staged cell carry ONE jackknife
-//     label.  So between two flushes a thread only ever touches 2 * n_r histogram slots: they are thread-private
-//     shared-memory words, updated with plain loads and stores -- no atomics anywhere in the pair loop;
-//   * at a flush (slab change or candidate-label change) the warp reduces its slots with shuffles in a fixed order and
-//     adds them to its own accumulator copy in HBM (rows A[jk_shape], B[jk_position]); a final kernel sums the copies
-//     in a fixed order.  Tasks are assigned to CTAs by a prefix sum of estimated work.  => results are identical from
-//     run to run, which the reference's exact-scaling test (tests/test_weights.py:34-35) needs.
+// Design ("windowed private histograms"):
+//   * one thread owns one shape galaxy (registers); one WARP owns 32 consecutive cell-sorted shape galaxies of one
+//     grid COLUMN (a cell of the two projected axes spanning the whole line of sight) and is the unit of scheduling:
+//     warps never synchronise with each other after start-up;
+//   * position galaxies are streamed cell by cell into shared memory by 1-D bulk (TMA) copies -- a cell is one
+//     contiguous 32-byte-per-galaxy range of the sorted catalogue -- double buffered behind mbarriers, one stream per
+//     warp; all 32 lanes read the same candidate (shared-memory broadcast);
+//   * the grid is cut along the line of sight into slabs thinner than one Pi bin.  For one shape galaxy, all candidates
+//     of a slab fall into at most TWO Pi bins; every staged cell carries ONE jackknife label; and r_p bins are visited
+//     in WINDOWS of W_R bins (the top window holds ~96% of all pairs for log-spaced bins, lower windows only re-visit
+//     the few nearest cells).  So between two flushes a thread touches 2 * W_R histogram slots: they are thread-private
+//     shared-memory words updated with plain loads and stores -- no atomics anywhere in the pair loop, and small enough
+//     (120 B per thread) that occupancy is limited by registers, not by shared memory;
+//   * at a flush (window / slab / candidate-label change) the warp reduces its slots with shuffles in a fixed order
+//     and adds them to its own accumulator copy in HBM (rows A[jk_shape], B[jk_position]); a final kernel sums the
+//     copies in a fixed order.  Warp tasks are assigned to warps by a prefix sum of estimated work.  => results are
+//     identical from run to run, which the reference's exact-scaling test (tests/test_weights.py:34-35) needs.
 //
 // Exactness: separations are formed with the reference's operation sequence (__d*_rn, no contraction); range and bin
 // decisions are comparisons against the host-calibrated thresholds; the only approximate arithmetic is the VALUE of
-// e+ / ex (reciprocal by Newton iteration, FMA), accurate to ~1e-16, far inside the 1e-10 contract.  Pairs whose |cos|
-// is within 1e-12 of 1 re-evaluate cos with the reference's sequence to apply its NaN rule (measure_w_box_jk.py:416).
+// e+ / ex (reciprocal by one cubic iteration, FMA), accurate to ~1e-16, far inside the 1e-10 contract.  Pairs whose
+// |cos| is within 1e-11 of 1 are re-evaluated with the reference's sequence to apply its NaN rule
+// (measure_w_box_jk.py:416-417).
 #pragma once
 #include <cub/cub.cuh>
 #include "mia_common.cuh"
@@ -28,14 +32,15 @@
 
 namespace mia {
 
-constexpr int TP = 128;          // threads = shape galaxies per CTA
-constexpr int TW = TP / 32;      // warps per CTA
+constexpr int TP = 128;          // threads per CTA
+constexpr int TW = TP / 32;      // warps per CTA (independent workers)
 constexpr int CH = 32;           // candidates per staged chunk (<= 32: the suspect mask is one word)
 constexpr int STAGES = 2;        // per-warp double buffering
 constexpr int MAX_NEIGH = 128;   // neighbour columns per task
 constexpr int LUT_SIZE = 256;
-constexpr int MAX_SLOTS = 32;    // 2 * n_r <= 32
-constexpr int SLOTS_PER_SM = 6;    // work slots (= CTAs launched) per SM; fixed so that results do not depend on occupancy
+constexpr int W_R = 3;           // r bins per accumulation window
+constexpr int NSLOT = 2 * W_R;   // private histogram slots per thread
+constexpr int SLOTS_PER_SM = 6;  // CTAs launched per SM; fixed, so that results do not depend on occupancy
 
 struct LutEntry {
 	double thr;  // threshold inside this entry's range of s (or +inf)
@@ -49,15 +54,9 @@ struct CellInfo {
 	int nlab;   // number of label runs in the cell (1 = uniform)
 };
 
-struct Desc {  // one neighbour cell of the current slab (shared memory)
-	long long start;
-	int n, label, nlab, pad;
-	double umin, umax, vmin, vmax;
-};
-
 struct TiledConfig {
-	int n_partials;  // accumulator copies = work slots * warps per CTA
-	int n_slots;
+	int n_partials;  // accumulator copies = worker warps
+	int n_ctas;
 	int num_sms;
 	int nz;
 	int n_side;
@@ -82,7 +81,7 @@ struct TiledArgs {
 	const LutEntry *lut;
 	int lut_hi0, lut_shift, lut_n;
 	Accum A;
-	int nz, n_side, G, shard_index, shard_count, max_tasks;
+	int nz, n_side, n_workers, shard_index, shard_count, max_tasks;
 	int *flags;
 };
 
@@ -135,17 +134,15 @@ inline bool build_lut(const mia_params *p, TiledConfig &cfg) {
 	return true;
 }
 
-inline size_t tiled_smem_bytes(int n_r, bool unit_w) {
-	const size_t fixed = sizeof(Cand) * TW * STAGES * CH + sizeof(LutEntry) * LUT_SIZE + sizeof(Desc) * MAX_NEIGH +
-						 sizeof(int) * MAX_NEIGH * 2 + 256;
+inline size_t tiled_smem_bytes(bool unit_w) {
+	const size_t fixed = sizeof(Cand) * TW * STAGES * CH + sizeof(LutEntry) * LUT_SIZE + sizeof(int) * TW * MAX_NEIGH + 256 + 768;
 	const size_t per_slot = (size_t)TP * (8 + 8 + 4 + (unit_w ? 0 : 8));
-	return fixed + per_slot * 2 * n_r;
+	return fixed + per_slot * NSLOT;
 }
 
 inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g, int &ku, int &kv, int &kl,
 					   TiledConfig &cfg) {
 	if (p->geometry != MIA_GEOM_RPPI) return false;
-	if (2 * p->n_r > MAX_SLOTS) return false;
 	const double L = p->boxsize, reach = p->r_search * (1.0 + 1e-6);
 	// slabs thinner than the narrowest Pi bin
 	double dmin = INFINITY;
@@ -185,9 +182,10 @@ inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g,
 		cudaGetLastError();
 	}
 	cfg.num_sms = sms;
-	cfg.n_slots = sms * SLOTS_PER_SM;
-	cfg.n_partials = cfg.n_slots * TW;
-	cfg.max_tasks = (int)(nS / TP + (int64_t)nc * nc + 1);
+	cfg.n_ctas = sms * SLOTS_PER_SM;
+	cfg.n_partials = cfg.n_ctas * TW;
+	cfg.max_tasks = (int)(nS / 32 + (int64_t)nc * nc + 1);
+	(void)nD;
 	return true;
 }
 
@@ -290,7 +288,7 @@ __global__ void k_col_chunks(const int64_t *__restrict__ prim_cell_start, int64_
 		return;
 	}
 	const int64_t n = prim_cell_start[(c + 1) * nz] - prim_cell_start[c * nz];
-	col_chunks[c] = (int32_t)((n + TP - 1) / TP);
+	col_chunks[c] = (int32_t)((n + 31) / 32);
 }
 
 __device__ __forceinline__ bool neighbour_offset_ok(int ou, int ov, double cs, double reach) {
@@ -298,6 +296,7 @@ __device__ __forceinline__ bool neighbour_offset_ok(int ou, int ov, double cs, d
 	return (mu * mu + mv * mv) * cs * cs * (1.0 - 1e-6) < reach * reach;
 }
 
+// One warp task = up to 32 consecutive shape galaxies of one column; cost = shapes x candidates in reach.
 __global__ void k_fill_tasks(const int64_t *__restrict__ prim_cell_start, const int64_t *__restrict__ cell_start,
 							 const int32_t *__restrict__ task_off, int ncu, int ncv, int nz, int k, int periodic,
 							 double cs, double reach, int32_t *__restrict__ task_col, int64_t *__restrict__ task_first,
@@ -330,8 +329,8 @@ __global__ void k_fill_tasks(const int64_t *__restrict__ prim_cell_start, const 
 		}
 	}
 	int t = task_off[c];
-	for (int64_t p = p0; p < p1; p += TP, t++) {
-		const int n = (int)((p1 - p < TP) ? (p1 - p) : TP);
+	for (int64_t p = p0; p < p1; p += 32, t++) {
+		const int n = (int)((p1 - p < 32) ? (p1 - p) : 32);
 		task_col[t] = (int32_t)c;
 		task_first[t] = p;
 		task_n[t] = n;
@@ -388,11 +387,19 @@ __device__ __forceinline__ double warp_sum(double x) {
 }
 
 // extended bin of x on the second axis: -1 below range, n_2 at/above the upper range edge
-__device__ __forceinline__ int ebin2(double x, const DevParams &P) {
+__device__ __forceinline__ int ebin2(double x, const double *thr2, int n_2) {
 	int c = 0;
-	for (int b = 0; b <= P.n_2; b++) c += (x >= P.thr2[b]) ? 1 : 0;
+	for (int b = 0; b <= n_2; b++) c += (x >= thr2[b]) ? 1 : 0;
 	return c - 1;
 }
+
+// the few scalars z_window needs (passed by value: a noinline function taking the kernel's parameter block by reference
+// would force a 1 KB copy of it into every thread's local memory)
+struct ZParams {
+	const double *thr2;  // shared-memory copy of the second-axis thresholds
+	double L, halfL;
+	int n_2, periodic;
+};
 
 struct ZWindow {
 	double t_split, t_lo, t_hi;
@@ -402,7 +409,7 @@ struct ZWindow {
 };
 
 // Which (at most two) Pi bins can pairs of this shape galaxy with candidates of a slab [zlo, zhi] fall in?
-__device__ __forceinline__ ZWindow z_window(double pl, double zlo, double zhi, const DevParams &P) {
+__device__ __noinline__ ZWindow z_window(double pl, double zlo, double zhi, const ZParams P) {
 	ZWindow w;
 	w.t_split = INFINITY;
 	w.t_lo = -INFINITY;
@@ -430,7 +437,7 @@ __device__ __forceinline__ ZWindow z_window(double pl, double zlo, double zhi, c
 		}
 	}
 	if (!straddle) {
-		const int ea = ebin2(lo, P), eb = ebin2(hi, P);
+		const int ea = ebin2(lo, P.thr2, P.n_2), eb = ebin2(hi, P.thr2, P.n_2);
 		if (eb - ea > 1) w.err = true;
 		if (ea >= 0 && ea < n2) w.b0 = ea;
 		if (eb != ea) {
@@ -455,8 +462,8 @@ __device__ __forceinline__ ZWindow z_window(double pl, double zlo, double zhi, c
 			a_lo = __dadd_rn(lo, P.L);
 			b_hi = hi;
 		}
-		const int ea_a = ebin2(a_lo, P), eb_a = ebin2(P.halfL, P);
-		const int ea_b = ebin2(-P.halfL, P), eb_b = ebin2(b_hi, P);
+		const int ea_a = ebin2(a_lo, P.thr2, P.n_2), eb_a = ebin2(P.halfL, P.thr2, P.n_2);
+		const int ea_b = ebin2(-P.halfL, P.thr2, P.n_2), eb_b = ebin2(b_hi, P.thr2, P.n_2);
 		int na = 0, nbb = 0, va = -1, vb = -1;
 		for (int e = ea_a; e <= eb_a; e++)
 			if (e >= 0 && e < n2) {
@@ -518,20 +525,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// the pair kernel
-// ------------------------------------------------------------------------------------------------------------------
-struct Chunk {
-	long long start;
-	int n, label, desc;
-};
-
-// Shared-memory addresses (bytes, shared window) of the thread-private accumulators:
-//   a2 : [slot][thread] double2 {sum e+ , sum ex}     ac : [slot][thread] u32 pair count     aw : [slot][thread] sum w_D
-struct PrivAcc {
-	uint32_t a2, ac, aw;
-};
-
 // predicated shared stores: the pair loop is branch-free so that nvcc can interleave the arithmetic of consecutive
 // candidates (the FP64 pipe has ~8-cycle dependent-issue latency and only 3 warps per scheduler fit)
 __device__ __forceinline__ void sts_v2_if(bool p, uint32_t addr, double a, double b) {
@@ -548,20 +541,34 @@ __device__ __forceinline__ void sts_u32_if(bool p, uint32_t addr, unsigned a) {
 				 : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// the pair kernel
+// ------------------------------------------------------------------------------------------------------------------
+// Shared-memory addresses (bytes, shared window) of the thread-private accumulators:
+//   a2 : [slot][thread] double2 {sum e+ , sum ex}     ac : [slot][thread] u32 pair count     aw : [slot][thread] sum w_D
+struct PrivAcc {
+	uint32_t a2, ac, aw;
+};
+
+// One accumulation window of r bins [ra, ra + W_R): squared-separation limits as bit patterns.
+struct RWindow {
+	long long lo_b, hi_b;  // pairs with lo <= r_p^2 < hi belong to the window
+	int ra;
+};
+
 // One staged chunk (n <= 32 candidates at shared address cb) against this thread's shape galaxy.
 //   XYW : compare-and-wrap the projected separations per pair (lanes whose column pair crosses the periodic boundary)
 //   ZG  : compare-and-wrap + range-check the line-of-sight separation per pair (slab straddles +-L/2 or the Pi range)
 //         otherwise the lane-constant image shift is added (exactly the reference's `sep -= L` / `sep += L`)
-// Returns a bit mask of candidates whose |cos| is within 1e-12 of 1: they are NOT accumulated here but re-evaluated
+// Returns a bit mask of candidates whose |cos| is within 1e-11 of 1: they are NOT accumulated here but re-evaluated
 // with the reference's exact operation sequence by slow_pairs() (its NaN rule, measure_w_box_jk.py:416-417).
 template <bool UNITW, bool XYW, bool ZG>
-__device__ __forceinline__ unsigned pair_loop(uint32_t cb, int n, const DevParams &P, double pu, double pv, double pl,
-											  double a0, double a1, double t0, double tn, const ZWindow &zw, uint32_t lut,
-											  int lut_hi0, int lut_shift, const PrivAcc &acc) {
-	const double L = P.L, halfL = P.halfL;
+__device__ __forceinline__ unsigned pair_loop(uint32_t cb, int n, int periodic, double L, double halfL, double pu,
+											  double pv, double pl, double a0, double a1, const RWindow &rw,
+											  long long hi_b_lane, const ZWindow &zw, uint32_t lut, int lut_hi0,
+											  int lut_shift, const PrivAcc &acc) {
 	// squared separations are non-negative doubles: their bit patterns order like the values, so every comparison of
 	// r_p^2 against a threshold is done on the INTEGER pipe and the FP64 pipe (the bound of this kernel) is spared
-	const long long t0b = __double_as_longlong(t0), tnb = __double_as_longlong(tn);
 	unsigned suspects = 0u;
 	double cu, cv, cl, cw, mu_, mv_, ml_, mw_;  // current candidate and the one after it (prefetch distance 2)
 	lds_v2(cu, cv, cb);
@@ -571,7 +578,7 @@ __device__ __forceinline__ unsigned pair_loop(uint32_t cb, int n, const DevParam
 		lds_v2(mu_, mv_, a1_);
 		lds_v2(ml_, mw_, a1_ + 16);
 	}
-#pragma unroll 4
+#pragma unroll 2
 	for (int j = 0; j < n; j++) {
 		const uint32_t na = cb + (uint32_t)((j + 2 < n) ? (j + 2) : (n - 1)) * (uint32_t)sizeof(Cand);
 		double nu, nv, nl, nw;
@@ -586,10 +593,10 @@ __device__ __forceinline__ unsigned pair_loop(uint32_t cb, int n, const DevParam
 		}
 		const double r2 = __dadd_rn(__dmul_rn(du, du), __dmul_rn(dv, dv));  // :407 (before the sqrt)
 		const long long r2b = __double_as_longlong(r2);
-		bool ok = (r2b >= t0b) && (r2b < tnb);
+		bool ok = (r2b >= rw.lo_b) && (r2b < hi_b_lane);
 		double dz = __dsub_rn(pl, cl);
 		if (ZG) {
-			if (P.periodic) {
+			if (periodic) {
 				dz = (dz > halfL) ? __dsub_rn(dz, L) : dz;
 				dz = (dz < -halfL) ? __dadd_rn(dz, L) : dz;
 			}
@@ -601,8 +608,9 @@ __device__ __forceinline__ unsigned pair_loop(uint32_t cb, int n, const DevParam
 		const unsigned idx = min((unsigned)(__double2hiint(r2) - lut_hi0) >> lut_shift, (unsigned)(LUT_SIZE - 1));
 		long long lthr, lbase;
 		asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lthr), "=l"(lbase) : "r"(lut + idx * 16u));
-		const int rbin = (int)lbase + ((r2b >= lthr) ? 1 : 0);
-		const uint32_t so = (uint32_t)(2 * rbin + ((dz >= zw.t_split) ? 1 : 0)) * (uint32_t)TP;
+		int rrel = (int)lbase + ((r2b >= lthr) ? 1 : 0) - rw.ra;  // r bin relative to the window
+		rrel = min(max(rrel, 0), W_R - 1);                         // (only rejected pairs are ever clamped)
+		const uint32_t so = (uint32_t)(2 * rrel + ((dz >= zw.t_split) ? 1 : 0)) * (uint32_t)TP;
 		// private slots: loads first, the arithmetic below hides their latency
 		double s0, s1, sw = 0.0;
 		lds_v2(s0, s1, acc.a2 + so * 16u);
@@ -647,7 +655,7 @@ __device__ __forceinline__ unsigned pair_loop(uint32_t cb, int n, const DevParam
 // Rare path: the candidates flagged by pair_loop, with the reference's exact cos (and its NaN rule).
 template <bool UNITW>
 __device__ __noinline__ void slow_pairs(unsigned suspects, uint32_t cb, int periodic, double L, double halfL, double pu,
-										double pv, double pl, double a0, double a1, double t_split, uint32_t lut,
+										double pv, double pl, double a0, double a1, double t_split, int ra, uint32_t lut,
 										int lut_hi0, int lut_shift, PrivAcc acc, unsigned long long &nan_pairs) {
 	auto sep = [&](double s_, double c_) {  // measure_w_box_jk.py:401-404
 		double d = __dsub_rn(s_, c_);
@@ -674,8 +682,8 @@ __device__ __noinline__ void slow_pairs(unsigned suspects, uint32_t cb, int peri
 		double lthr;
 		int lbase;
 		lds_lut(lthr, lbase, lut + (uint32_t)idx * 16u);
-		const int rbin = lbase + ((r2 >= lthr) ? 1 : 0);
-		const uint32_t so = (uint32_t)(2 * rbin + ((dz >= t_split) ? 1 : 0)) * (uint32_t)TP;
+		const int rrel = lbase + ((r2 >= lthr) ? 1 : 0) - ra;
+		const uint32_t so = (uint32_t)(2 * rrel + ((dz >= t_split) ? 1 : 0)) * (uint32_t)TP;
 		double s0, s1;
 		lds_v2(s0, s1, acc.a2 + so * 16u);
 		const unsigned c0 = lds_u32(acc.ac + so * 4u);
@@ -689,41 +697,194 @@ __device__ __noinline__ void slow_pairs(unsigned suspects, uint32_t cb, int peri
 	}
 }
 
+// Flush: fixed-order warp reduction of the private slots into this warp's accumulator copy in HBM.
+// Lanes are grouped by key = (jackknife label of the shape galaxy, its two Pi bins); groups are processed one after the
+// other, every slot of a group is summed over the lanes with a butterfly, and lane s adds slot s to the A / B rows.
+struct FlushCtx {
+	unsigned long long *pcnt;
+	double *pddw, *psp, *psc;
+	int *flags;
+	int n_2, nb, J, num_jk;
+};
+
 template <bool UNITW>
-__global__ void __launch_bounds__(TP) k_tiled_rppi(const TiledArgs a) {
+__device__ __noinline__ unsigned flush_slots(const FlushCtx &fc, PrivAcc acc, unsigned key, bool dead, double pe, double pw,
+											 int ra, int rb, int jkD) {
+	const int lane = threadIdx.x & 31;
+	unsigned binned = 0;
+	unsigned todo = __ballot_sync(0xffffffffu, !dead);
+	while (todo) {
+		const int leader = __ffs(todo) - 1;
+		const unsigned k = __shfl_sync(0xffffffffu, key, leader);
+		const unsigned grp = __ballot_sync(0xffffffffu, key == k) & todo;
+		const bool in = (grp >> lane) & 1u;
+		unsigned tot_cnt = 0;
+		double tot_sp = 0.0, tot_sc = 0.0, tot_dw = 0.0;
+#pragma unroll 1
+		for (int sl = 0; sl < NSLOT; sl++) {
+			const uint32_t so = (uint32_t)sl * TP;
+			const unsigned c = in ? lds_u32(acc.ac + so * 4u) : 0u;
+			const unsigned csum = __reduce_add_sync(0xffffffffu, c);
+			if (csum == 0u) continue;
+			double v0 = 0.0, v1 = 0.0;
+			if (in) lds_v2(v0, v1, acc.a2 + so * 16u);
+			const double xs = warp_sum(v0 * pe);
+			const double ys = warp_sum(v1 * pe);
+			const double zs = UNITW ? (double)csum : warp_sum(in ? lds_f64(acc.aw + so * 8u) * pw : 0.0);
+			if (lane == sl) {
+				tot_cnt = csum;
+				tot_sp = xs;
+				tot_sc = ys;
+				tot_dw = zs;
+			}
+		}
+		if (lane < NSLOT && tot_cnt) {
+			const int kb0 = (int)((k >> 8) & 0xffu) - 1, kb1 = (int)(k & 0xffu) - 1, kjk = (int)(k >> 16);
+			const int b2 = (lane & 1) ? kb1 : kb0;
+			const int rbin = ra + (lane >> 1);
+			if (b2 < 0 || rbin > rb) {
+				atomicExch(&fc.flags[1], 1);
+			} else {
+				const size_t bin = (size_t)rbin * fc.n_2 + b2;
+				const size_t ia = (size_t)kjk * fc.nb + bin;
+				fc.pcnt[ia] += tot_cnt;
+				fc.pddw[ia] += tot_dw;
+				fc.psp[ia] += tot_sp;
+				fc.psc[ia] += tot_sc;
+				if (fc.num_jk > 0 && jkD != kjk) {
+					const size_t ib = (size_t)(fc.J + jkD) * fc.nb + bin;
+					fc.pcnt[ib] += tot_cnt;
+					fc.pddw[ib] += tot_dw;
+					fc.psp[ib] += tot_sp;
+				}
+				binned += tot_cnt;
+			}
+		}
+		todo &= ~grp;
+	}
+	__syncwarp();
+#pragma unroll
+	for (int sl = 0; sl < NSLOT; sl++) {
+		sts_v2(acc.a2 + (uint32_t)sl * TP * 16u, 0.0, 0.0);
+		if (!UNITW) sts_f64(acc.aw + (uint32_t)sl * TP * 8u, 0.0);
+		sts_u32(acc.ac + (uint32_t)sl * TP * 4u, 0u);
+	}
+	return binned;
+}
+
+// Neighbour columns of a task's column, ordered by jackknife (u, v) region so that candidate labels change rarely.
+// Writes the list to nlist (per-warp shared scratch) and returns its length.
+__device__ __noinline__ int build_neighbour_list(int *nlist, int col, int ncu, int ncv, int ku, int kv, int periodic,
+												 int n_side, double cs, double reach) {
+	const int lane = threadIdx.x & 31;
+	const int cu0 = col / ncv, cv0 = col % ncv;
+	const bool all_u = 2 * ku + 1 >= ncu, all_v = 2 * kv + 1 >= ncv;
+	const int wu = all_u ? ncu : 2 * ku + 1, wv = all_v ? ncv : 2 * kv + 1;
+	const int n_off = wu * wv, n_keys = n_side * n_side;
+	int my_col[MAX_NEIGH / 32], my_key[MAX_NEIGH / 32];
+#pragma unroll 1
+	for (int r = 0; r < MAX_NEIGH / 32; r++) {
+		const int o = r * 32 + lane;
+		int c_ = -1, k_ = -1;
+		if (o < n_off) {
+			const int iu = o / wv, iv = o - iu * wv;
+			int nu = all_u ? iu : cu0 + iu - ku, nv = all_v ? iv : cv0 + iv - kv;
+			bool ok = true;
+			if (nu < 0) {
+				if (!periodic) ok = false;
+				nu += ncu;
+			} else if (nu >= ncu) {
+				if (!periodic) ok = false;
+				nu -= ncu;
+			}
+			if (nv < 0) {
+				if (!periodic) ok = false;
+				nv += ncv;
+			} else if (nv >= ncv) {
+				if (!periodic) ok = false;
+				nv -= ncv;
+			}
+			if (ok && !all_u && !all_v && !neighbour_offset_ok(iu - ku, iv - kv, cs, reach)) ok = false;
+			if (ok) {
+				c_ = nu * ncv + nv;
+				k_ = ((nu * n_side) / ncu) * n_side + (nv * n_side) / ncv;
+			}
+		}
+		if (r == 0) { my_col[0] = c_; my_key[0] = k_; }
+		if (r == 1) { my_col[1] = c_; my_key[1] = k_; }
+		if (r == 2) { my_col[2] = c_; my_key[2] = k_; }
+		if (r == 3) { my_col[3] = c_; my_key[3] = k_; }
+	}
+	__syncwarp();
+	int nn = 0;
+	for (int k = 0; k < n_keys; k++) {  // counting sort by region key, stable in offset order
+#pragma unroll
+		for (int r = 0; r < MAX_NEIGH / 32; r++) {
+			const unsigned m = __ballot_sync(0xffffffffu, my_key[r] == k);
+			if (my_key[r] == k) nlist[nn + __popc(m & ((1u << lane) - 1u))] = my_col[r];
+			nn += __popc(m);
+		}
+	}
+	__syncwarp();
+	return nn;
+}
+
+struct Chunk {
+	long long start;
+	int n, label;
+	bool xyw;
+};
+
+template <bool UNITW>
+__global__ void __launch_bounds__(TP, 4) k_tiled_rppi(const TiledArgs a) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	const DevParams &P = a.P;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int NS = 2 * P.n_r, nb = P.n_r * P.n_2;
+	const int nb = P.n_r * P.n_2;
 	const int J = P.num_jk > 0 ? P.num_jk : 1;
+	const int periodic = P.periodic;
+	const double L = P.L, halfL = P.halfL;
 
 	// ---- shared memory carve-up ------------------------------------------------------------------------------------
 	Cand *ring = reinterpret_cast<Cand *>(smem);  // [warp][stage][CH]: every warp runs its own double-buffered stream
 	LutEntry *lut_s = reinterpret_cast<LutEntry *>(smem + sizeof(Cand) * TW * STAGES * CH);
-	Desc *desc = reinterpret_cast<Desc *>(reinterpret_cast<unsigned char *>(lut_s) + sizeof(LutEntry) * LUT_SIZE);
-	int *nlist = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(desc) + sizeof(Desc) * MAX_NEIGH);
-	int *nkey = nlist + MAX_NEIGH;
-	uint64_t *full = reinterpret_cast<uint64_t *>(nkey + MAX_NEIGH);  // [warp][stage]
-	int *misc = reinterpret_cast<int *>(full + TW * STAGES);          // [0] first task, [1] end task, [2] neighbour count
-	unsigned char *accbase = reinterpret_cast<unsigned char *>(full) + 256;
+	int *nlist_all = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(lut_s) + sizeof(LutEntry) * LUT_SIZE);
+	uint64_t *full = reinterpret_cast<uint64_t *>(nlist_all + TW * MAX_NEIGH);  // [warp][stage]
+	double *thr2_s = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(full) + 256);
+	unsigned char *accbase = reinterpret_cast<unsigned char *>(thr2_s) + 768;
 	const uint32_t lut_u32 = smem_u32(lut_s), acc_u32 = smem_u32(accbase);
 	Cand *my_ring = ring + (size_t)warp * STAGES * CH;
 	uint64_t *my_full = full + warp * STAGES;
+	int *nlist = nlist_all + warp * MAX_NEIGH;
 	const uint32_t my_ring_u32 = smem_u32(my_ring);
 	PrivAcc acc;  // addresses of slot 0 of this thread
 	acc.a2 = acc_u32 + (uint32_t)tid * 16u;
-	acc.aw = acc_u32 + (uint32_t)NS * TP * 16u + (uint32_t)tid * 8u;
-	acc.ac = acc_u32 + (uint32_t)NS * TP * (UNITW ? 16u : 24u) + (uint32_t)tid * 4u;
+	acc.aw = acc_u32 + (uint32_t)NSLOT * TP * 16u + (uint32_t)tid * 8u;
+	acc.ac = acc_u32 + (uint32_t)NSLOT * TP * (UNITW ? 16u : 24u) + (uint32_t)tid * 4u;
 
 	if (tid == 0) {
 		for (int s = 0; s < TW * STAGES; s++) mbar_init(&full[s], 1);
 		mbar_fence_init();
-		// ---- my share of the tasks: slots of equal estimated work ---------------------------------------------------
+		if (blockIdx.x == 0) a.A.stats[6] = (unsigned long long)a.n_tasks[0];
+	}
+	for (int e = tid; e < LUT_SIZE; e += blockDim.x) lut_s[e] = a.lut[e];
+	for (int e = tid; e <= P.n_2; e += blockDim.x) thr2_s[e] = P.thr2[e];
+#pragma unroll
+	for (int s = 0; s < NSLOT; s++) {
+		sts_v2(acc.a2 + (uint32_t)s * TP * 16u, 0.0, 0.0);
+		if (!UNITW) sts_f64(acc.aw + (uint32_t)s * TP * 8u, 0.0);
+		sts_u32(acc.ac + (uint32_t)s * TP * 4u, 0u);
+	}
+	__syncthreads();  // the only CTA-wide synchronisation: from here on every warp works alone
+
+	// ---- this warp's share of the tasks: worker slots of equal estimated work -------------------------------------------
+	int task0 = 0, task1 = 0;
+	{
 		const int nt = a.n_tasks[0];
-		int t0 = 0, t1 = 0;
 		if (nt > 0) {
 			const double total2 = 2.0 * (double)a.task_cum[nt - 1];
-			const int RG = a.shard_count * a.G, mine = a.shard_index * a.G + (int)blockIdx.x;
+			const int RG = a.shard_count * a.n_workers;
+			const int mine = a.shard_index * a.n_workers + (int)blockIdx.x * TW + warp;
 			auto slot_of = [&](int t) {
 				const double mid2 = 2.0 * (double)a.task_cum[t] - (double)a.task_cost[t];
 				int s = (int)(mid2 / total2 * (double)RG);
@@ -738,39 +899,46 @@ __global__ void __launch_bounds__(TP) k_tiled_rppi(const TiledArgs a) {
 				}
 				return lo;
 			};
-			t0 = lower(mine);
-			t1 = lower(mine + 1);
+			task0 = lower(mine);
+			task1 = lower(mine + 1);
 		}
-		misc[0] = t0;
-		misc[1] = t1;
-		if (blockIdx.x == 0) a.A.stats[6] = (unsigned long long)nt;
 	}
-	for (int e = tid; e < LUT_SIZE; e += blockDim.x) lut_s[e] = a.lut[e];
-	for (int s = 0; s < NS; s++) {
-		sts_v2(acc.a2 + (uint32_t)s * TP * 16u, 0.0, 0.0);
-		if (!UNITW) sts_f64(acc.aw + (uint32_t)s * TP * 8u, 0.0);
-		sts_u32(acc.ac + (uint32_t)s * TP * 4u, 0u);
-	}
-	__syncthreads();
-	const int task0 = misc[0], task1 = misc[1];
 
 	// this warp's accumulator copy in HBM
 	const size_t part = (size_t)(blockIdx.x * TW + warp) * (size_t)a.A.rows * nb;
 	unsigned long long *pcnt = a.A.cnt + part;
 	double *pddw = a.A.ddw + part, *psp = a.A.sp + part, *psc = a.A.sc + part;
 
+	ZParams zp;
+	zp.thr2 = thr2_s;
+	zp.L = L;
+	zp.halfL = halfL;
+	zp.n_2 = P.n_2;
+	zp.periodic = periodic;
+	FlushCtx fc;
+	fc.pcnt = pcnt;
+	fc.pddw = pddw;
+	fc.psp = psp;
+	fc.psc = psc;
+	fc.flags = a.flags;
+	fc.n_2 = P.n_2;
+	fc.nb = nb;
+	fc.J = J;
+	fc.num_jk = P.num_jk;
 	uint32_t phase0 = 0u, phase1 = 0u;  // parity of the two stages of this warp's stream
+	int st_issue = 0;                   // stage the next bulk copy goes to
 	unsigned long long tested = 0, binned = 0, nan_pairs = 0;
-	const double T0 = P.r2_thr[0], TN = P.r2_thr[P.n_r];
-	const double cs = P.L / P.ncu, reach = sqrt(TN) * (1.0 + 1e-6);
+	const double TN = P.r2_thr[P.n_r];
+	const double cs = L / P.ncu, reach = sqrt(TN) * (1.0 + 1e-6);
+	const int n_win = (P.n_r + W_R - 1) / W_R;
 
 	for (int task = task0; task < task1; task++) {
 		const int col = a.task_col[task];
 		const int np = a.task_n[task];
-		const bool active = tid < np;
+		const bool active = lane < np;
 		Prim p;
 		if (active) {
-			p = a.prim[a.task_first[task] + tid];
+			p = a.prim[a.task_first[task] + lane];
 		} else {
 			p.u = p.v = p.l = 0.0;
 			p.w = 0.0;
@@ -781,188 +949,114 @@ __global__ void __launch_bounds__(TP) k_tiled_rppi(const TiledArgs a) {
 			p.orig = -1;
 		}
 		const double pe = p.w * p.e;
-		const int cu0 = col / P.ncv, cv0 = col % P.ncv;
 
-		// ---- neighbour columns of this task, ordered by jackknife (u, v) region to minimise label changes -----------
-		{
-			const bool all_u = 2 * P.ku + 1 >= P.ncu, all_v = 2 * P.kv + 1 >= P.ncv;
-			const int wu = all_u ? P.ncu : 2 * P.ku + 1, wv = all_v ? P.ncv : 2 * P.kv + 1;
-			int my_col = -1, my_key = 0x7fffffff;
-			if (tid < wu * wv) {
-				const int iu = tid / wv, iv = tid % wv;
-				int nu = all_u ? iu : cu0 + iu - P.ku, nv = all_v ? iv : cv0 + iv - P.kv;
-				bool ok = true;
-				if (nu < 0 || nu >= P.ncu) {
-					if (!P.periodic) ok = false;
-					nu = ((nu % P.ncu) + P.ncu) % P.ncu;
-				}
-				if (nv < 0 || nv >= P.ncv) {
-					if (!P.periodic) ok = false;
-					nv = ((nv % P.ncv) + P.ncv) % P.ncv;
-				}
-				if (ok && !all_u && !all_v && !neighbour_offset_ok(iu - P.ku, iv - P.kv, cs, reach)) ok = false;
-				if (ok) {
-					my_col = nu * P.ncv + nv;
-					my_key = ((nu * a.n_side) / P.ncu) * a.n_side + (nv * a.n_side) / P.ncv;
-				}
-			}
-			if (tid < MAX_NEIGH) nkey[tid] = (my_col >= 0) ? my_key : 0x7fffffff;
-			if (tid == 0) misc[2] = 0;
-			__syncthreads();
-			if (my_col >= 0) {
-				int rank = 0;
-				for (int j = 0; j < wu * wv; j++) {
-					const int kj = nkey[j];
-					rank += (kj < my_key || (kj == my_key && j < tid)) ? 1 : 0;
-				}
-				nlist[rank] = my_col;
-				atomicAdd(&misc[2], 1);
-			}
-			__syncthreads();
-		}
-		const int nn = misc[2];
+		// ---- neighbour columns of this task (ordered by jackknife (u, v) region) -----------------------------------
+		const int nn = build_neighbour_list(nlist, col, P.ncu, P.ncv, P.ku, P.kv, periodic, a.n_side, cs, reach);
 
 		for (int s = 0; s < a.nz; s++) {
 			const double zlo = a.slab_lo[s], zhi = a.slab_hi[s];
 			if (!(zlo <= zhi)) continue;  // empty slab (uniform branch)
-			if (tid < nn) {
-				const int64_t c = (int64_t)nlist[tid] * a.nz + s;
-				const int64_t st = a.cell_start[c], en = a.cell_start[c + 1];
-				const CellInfo ci = a.cinfo[c];
-				Desc d;
-				d.start = st;
-				d.n = (int)(en - st);
-				d.label = ci.label;
-				d.nlab = ci.nlab;
-				d.pad = 0;
-				d.umin = ci.umin;
-				d.umax = ci.umax;
-				d.vmin = ci.vmin;
-				d.vmax = ci.vmax;
-				desc[tid] = d;
-			}
-			__syncthreads();
 
-			ZWindow zw = z_window(p.l, zlo, zhi, P);
+			ZWindow zw = z_window(p.l, zlo, zhi, zp);
 			if (!active) zw.dead = true;
 			if (active && zw.err) atomicExch(&a.flags[1], 1);
-			const double tn_lane = zw.dead ? -1.0 : TN;  // dead lanes never pass the range test
+			if (!__any_sync(0xffffffffu, !zw.dead)) continue;
 			const bool warp_zg = __any_sync(0xffffffffu, !zw.dead && zw.gen);
 			const unsigned key = zw.dead ? 0xffffffffu
 										 : (((unsigned)p.jk << 16) | ((unsigned)(zw.b0 + 1) << 8) | (unsigned)(zw.b1 + 1));
-			const bool warp_live = __any_sync(0xffffffffu, !zw.dead);
 
-			// ---- flush: fixed-order warp reduction of the private slots into this warp's accumulator copy -------------
-			auto flush = [&](int jkD) {
-				unsigned todo = __ballot_sync(0xffffffffu, !zw.dead);
-				while (todo) {
-					const int leader = __ffs(todo) - 1;
-					const unsigned k = __shfl_sync(0xffffffffu, key, leader);
-					const unsigned grp = __ballot_sync(0xffffffffu, key == k) & todo;
-					const bool in = (grp >> lane) & 1u;
-					unsigned tot_cnt = 0;
-					double tot_sp = 0.0, tot_sc = 0.0, tot_dw = 0.0;
-					for (int sl = 0; sl < NS; sl++) {
-						const uint32_t so = (uint32_t)sl * TP;
-						const unsigned c = in ? lds_u32(acc.ac + so * 4u) : 0u;
-						const unsigned csum = __reduce_add_sync(0xffffffffu, c);
-						if (csum == 0u) continue;
-						double v0 = 0.0, v1 = 0.0;
-						if (in) lds_v2(v0, v1, acc.a2 + so * 16u);
-						const double xs = warp_sum(v0 * pe);
-						const double ys = warp_sum(v1 * pe);
-						const double zs = UNITW ? (double)csum : warp_sum(in ? lds_f64(acc.aw + so * 8u) * p.w : 0.0);
-						if (lane == sl) {
-							tot_cnt = csum;
-							tot_sp = xs;
-							tot_sc = ys;
-							tot_dw = zs;
+			for (int q = 0; q < n_win; q++) {
+				// ---- accumulation window q: r bins [ra, rb] counted from the top ------------------------------------------
+				const int rb = P.n_r - 1 - q * W_R, ra = (rb - W_R + 1 > 0) ? rb - W_R + 1 : 0;
+				RWindow rw;
+				rw.ra = ra;
+				rw.lo_b = __double_as_longlong(P.r2_thr[ra]);
+				rw.hi_b = __double_as_longlong(P.r2_thr[rb + 1]);
+				const double win_hi = P.r2_thr[rb + 1];
+				const long long hi_b_lane = zw.dead ? 0ll : rw.hi_b;  // dead lanes never pass the range test
+
+				auto flush = [&](int jkD) {
+					binned += flush_slots<UNITW>(fc, acc, key, zw.dead, pe, p.w, ra, rb, jkD);
+				};
+
+				// ---- chunk generator over the neighbour cells of this slab (32 cell descriptors at a time, one per lane,
+				// read through shuffles); a single call site keeps the kernel small enough for the instruction cache -------
+				int g_base = 0;
+				unsigned g_nonempty = 0u;
+				long long d_start = 0;
+				int d_n = 0, d_label = -1, d_nlab = 0;
+				double d_umin = 0.0, d_umax = 0.0, d_vmin = 0.0, d_vmax = 0.0;
+				long long g_pos = 0, g_run_end = 0, g_cell_end = 0;
+				int g_label = -1, g_nlab = 1;
+				bool g_xyw = false;
+				auto next_chunk = [&](Chunk &c) -> bool {
+					for (;;) {
+						if (g_pos < g_run_end) {
+							// split the rest of the run into equal chunks (66 -> 22 + 22 + 22, not 32 + 32 + 2)
+							const int rest = (int)(g_run_end - g_pos), nch = (rest + CH - 1) / CH;
+							c.start = g_pos;
+							c.n = (rest + nch - 1) / nch;
+							c.label = g_label;
+							c.xyw = g_xyw;
+							g_pos += c.n;
+							return true;
 						}
-					}
-					if (lane < NS && tot_cnt) {
-						const int kb0 = (int)((k >> 8) & 0xffu) - 1, kb1 = (int)(k & 0xffu) - 1, kjk = (int)(k >> 16);
-						const int b2 = (lane & 1) ? kb1 : kb0;
-						if (b2 < 0) {
-							atomicExch(&a.flags[1], 1);
-						} else {
-							const size_t bin = (size_t)(lane >> 1) * P.n_2 + b2;
-							const size_t ia = (size_t)kjk * nb + bin;
-							pcnt[ia] += tot_cnt;
-							pddw[ia] += tot_dw;
-							psp[ia] += tot_sp;
-							psc[ia] += tot_sc;
-							if (P.num_jk > 0 && jkD != kjk) {
-								const size_t ib = (size_t)(J + jkD) * nb + bin;
-								pcnt[ib] += tot_cnt;
-								pddw[ib] += tot_dw;
-								psp[ib] += tot_sp;
+						if (g_pos < g_cell_end) {  // next label run of a cell cut by a jackknife face
+							g_label = a.cand_jk[g_pos];
+							long long qq = g_pos + 1;
+							while (qq < g_cell_end && a.cand_jk[qq] == g_label) qq++;
+							g_run_end = qq;
+							continue;
+						}
+						if (!g_nonempty) {  // next batch of descriptors
+							if (g_base >= nn) return false;
+							d_n = 0;
+							if (g_base + lane < nn) {
+								const int64_t cc = (int64_t)nlist[g_base + lane] * a.nz + s;
+								const int64_t c0 = a.cell_start[cc], c1 = a.cell_start[cc + 1];
+								const CellInfo ci = a.cinfo[cc];
+								d_start = c0;
+								d_n = (int)(c1 - c0);
+								d_label = ci.label;
+								d_nlab = ci.nlab;
+								d_umin = ci.umin;
+								d_umax = ci.umax;
+								d_vmin = ci.vmin;
+								d_vmax = ci.vmax;
 							}
-							binned += tot_cnt;
+							g_nonempty = __ballot_sync(0xffffffffu, d_n > 0);
+							g_base += 32;
+							continue;
 						}
-					}
-					todo &= ~grp;
-				}
-				__syncwarp();
-				for (int sl = 0; sl < NS; sl++) {
-					sts_v2(acc.a2 + (uint32_t)sl * TP * 16u, 0.0, 0.0);
-					if (!UNITW) sts_f64(acc.aw + (uint32_t)sl * TP * 8u, 0.0);
-					sts_u32(acc.ac + (uint32_t)sl * TP * 4u, 0u);
-				}
-			};
-
-			// ---- chunk iterator over the neighbour cells of this slab ---------------------------------------------------
-			int it_e = -1;
-			long long it_pos = 0, it_sub_end = 0, it_cell_end = 0;
-			int it_label = -1;
-			bool it_go = false, it_xyw = false;  // verdict of the per-warp cull for the current cell
-			auto next_chunk = [&](Chunk &c) -> bool {
-				for (;;) {
-					if (it_pos < it_sub_end) {
-						c.start = it_pos;
-						c.n = (int)((it_sub_end - it_pos < CH) ? (it_sub_end - it_pos) : CH);
-						c.label = it_label;
-						c.desc = it_xyw ? 1 : 0;
-						it_pos += c.n;
-						return true;
-					}
-					if (it_sub_end < it_cell_end) {  // next label run of a mixed cell (rare)
-						it_pos = it_sub_end;
-						it_label = a.cand_jk[it_pos];
-						long long q = it_pos + 1;
-						while (q < it_cell_end && a.cand_jk[q] == it_label) q++;
-						it_sub_end = q;
-						continue;
-					}
-					it_e++;
-					if (it_e >= nn) return false;
-					const Desc &d = desc[it_e];
-					if (d.n == 0) continue;
-					// per-warp culling against the cell's bounding box: can any lane have a pair within reach?
-					{
-						double ulo = __dsub_rn(p.u, d.umax), uhi = __dsub_rn(p.u, d.umin);
-						double vlo = __dsub_rn(p.v, d.vmax), vhi = __dsub_rn(p.v, d.vmin);
+						const int e = __ffs(g_nonempty) - 1;
+						g_nonempty &= g_nonempty - 1u;
+						const double umin = __shfl_sync(0xffffffffu, d_umin, e), umax = __shfl_sync(0xffffffffu, d_umax, e);
+						const double vmin = __shfl_sync(0xffffffffu, d_vmin, e), vmax = __shfl_sync(0xffffffffu, d_vmax, e);
+						// per-warp culling against the cell's bounding box: can any lane have a pair in this window?
+						double ulo = __dsub_rn(p.u, umax), uhi = __dsub_rn(p.u, umin);
+						double vlo = __dsub_rn(p.v, vmax), vhi = __dsub_rn(p.v, vmin);
 						bool xyw = false, nocull = false;
-						if (P.periodic) {
-							if (!(ulo >= -P.halfL && uhi <= P.halfL)) {
+						if (periodic) {
+							if (!(ulo >= -halfL && uhi <= halfL)) {
 								xyw = true;
-								if (ulo > P.halfL) {
-									ulo = __dsub_rn(ulo, P.L);
-									uhi = __dsub_rn(uhi, P.L);
-								} else if (uhi < -P.halfL) {
-									ulo = __dadd_rn(ulo, P.L);
-									uhi = __dadd_rn(uhi, P.L);
+								if (ulo > halfL) {
+									ulo = __dsub_rn(ulo, L);
+									uhi = __dsub_rn(uhi, L);
+								} else if (uhi < -halfL) {
+									ulo = __dadd_rn(ulo, L);
+									uhi = __dadd_rn(uhi, L);
 								} else {
 									nocull = true;
 								}
 							}
-							if (!(vlo >= -P.halfL && vhi <= P.halfL)) {
+							if (!(vlo >= -halfL && vhi <= halfL)) {
 								xyw = true;
-								if (vlo > P.halfL) {
-									vlo = __dsub_rn(vlo, P.L);
-									vhi = __dsub_rn(vhi, P.L);
-								} else if (vhi < -P.halfL) {
-									vlo = __dadd_rn(vlo, P.L);
-									vhi = __dadd_rn(vhi, P.L);
+								if (vlo > halfL) {
+									vlo = __dsub_rn(vlo, L);
+									vhi = __dsub_rn(vhi, L);
+								} else if (vhi < -halfL) {
+									vlo = __dadd_rn(vlo, L);
+									vhi = __dadd_rn(vhi, L);
 								} else {
 									nocull = true;
 								}
@@ -971,77 +1065,78 @@ __global__ void __launch_bounds__(TP) k_tiled_rppi(const TiledArgs a) {
 						const double mu = ulo > 0.0 ? ulo : (uhi < 0.0 ? -uhi : 0.0);
 						const double mv = vlo > 0.0 ? vlo : (vhi < 0.0 ? -vhi : 0.0);
 						const double dmin2 = __dadd_rn(__dmul_rn(mu, mu), __dmul_rn(mv, mv));
-						const bool need = !zw.dead && (nocull || dmin2 < TN);
-						it_go = __any_sync(0xffffffffu, need);
-						it_xyw = __any_sync(0xffffffffu, !zw.dead && xyw);
+						const bool need = !zw.dead && (nocull || dmin2 < win_hi);
+						if (!__any_sync(0xffffffffu, need)) continue;  // never even staged
+						g_xyw = __any_sync(0xffffffffu, !zw.dead && xyw);
+						g_pos = __shfl_sync(0xffffffffu, d_start, e);
+						g_cell_end = g_pos + __shfl_sync(0xffffffffu, d_n, e);
+						g_label = __shfl_sync(0xffffffffu, d_label, e);
+						g_nlab = __shfl_sync(0xffffffffu, d_nlab, e);
+						g_run_end = g_cell_end;
+						if (g_nlab > 1) {
+							g_label = a.cand_jk[g_pos];
+							long long qq = g_pos + 1;
+							while (qq < g_cell_end && a.cand_jk[qq] == g_label) qq++;
+							g_run_end = qq;
+						}
 					}
-					if (!it_go) continue;  // no lane of this warp can reach the cell: it is never even staged
-					it_pos = d.start;
-					it_cell_end = d.start + d.n;
-					if (d.nlab <= 1) {
-						it_label = d.label;
-						it_sub_end = it_cell_end;
-					} else {
-						it_label = a.cand_jk[it_pos];
-						long long q = it_pos + 1;
-						while (q < it_cell_end && a.cand_jk[q] == it_label) q++;
-						it_sub_end = q;
-					}
-				}
-			};
-			auto issue = [&](const Chunk &c, int st) {
-				if (lane == 0) {
-					const uint32_t bytes = (uint32_t)c.n * (uint32_t)sizeof(Cand);
-					mbar_expect_tx(&my_full[st], bytes);
-					bulk_load(my_ring + (size_t)st * CH, a.cand + c.start, bytes, &my_full[st]);
-				}
-			};
+				};
 
-			if (warp_live) {
-				Chunk cur, nxt;
-				bool have = next_chunk(cur);
-				int st = 0, cur_label = -1;
-				if (have) issue(cur, st);
-				while (have) {
-					const bool have_n = next_chunk(nxt);
-					if (have_n) issue(nxt, st ^ 1);
-					if (cur.label != cur_label) {
+				// ---- software pipeline: issue the bulk copy of chunk k+1, then work on chunk k ----------------------------
+				Chunk pend, nxt;
+				pend.n = 0;
+				pend.label = -1;
+				int pend_st = 0, cur_label = -1;
+				bool more = true;
+				while (more || pend.n > 0) {
+					bool got = false;
+					if (more) {
+						got = next_chunk(nxt);
+						more = got;
+					}
+					if (got && lane == 0) {
+						const uint32_t bytes = (uint32_t)nxt.n * (uint32_t)sizeof(Cand);
+						mbar_expect_tx(&my_full[st_issue], bytes);
+						bulk_load(my_ring + (size_t)st_issue * CH, a.cand + nxt.start, bytes, &my_full[st_issue]);
+					}
+					// a label change (or the end of the window: pend.n == 0) flushes the private slots
+					const int lab = (pend.n > 0) ? pend.label : -2;
+					if (lab != cur_label) {
 						if (cur_label >= 0) flush(cur_label);
-						cur_label = cur.label;
+						cur_label = lab;
 					}
-					if (st == 0) {
-						mbar_wait(&my_full[0], phase0);
-						phase0 ^= 1u;
+					if (pend.n > 0) {
+						if (pend_st == 0) {
+							mbar_wait(&my_full[0], phase0);
+							phase0 ^= 1u;
+						} else {
+							mbar_wait(&my_full[1], phase1);
+							phase1 ^= 1u;
+						}
+						if (!zw.dead) tested += (unsigned long long)pend.n;
+						const uint32_t cb = my_ring_u32 + (uint32_t)pend_st * (uint32_t)(CH * sizeof(Cand));
+						unsigned susp;
+						if (!pend.xyw && !warp_zg)  // the common case: no periodic image, no range edge in this chunk
+							susp = pair_loop<UNITW, false, false>(cb, pend.n, periodic, L, halfL, p.u, p.v, p.l, p.a0, p.a1, rw,
+																  hi_b_lane, zw, lut_u32, a.lut_hi0, a.lut_shift, acc);
+						else  // compare-and-wrap everything per pair
+							susp = pair_loop<UNITW, true, true>(cb, pend.n, periodic, L, halfL, p.u, p.v, p.l, p.a0, p.a1, rw,
+																hi_b_lane, zw, lut_u32, a.lut_hi0, a.lut_shift, acc);
+						if (__any_sync(0xffffffffu, susp != 0u))
+							slow_pairs<UNITW>(susp, cb, periodic, L, halfL, p.u, p.v, p.l, p.a0, p.a1, zw.t_split, ra, lut_u32,
+											  a.lut_hi0, a.lut_shift, acc, nan_pairs);
+						__syncwarp();  // every lane is done with the stage before it is refilled
+					}
+					if (got) {
+						pend = nxt;
+						pend_st = st_issue;
+						st_issue ^= 1;
 					} else {
-						mbar_wait(&my_full[1], phase1);
-						phase1 ^= 1u;
+						pend.n = 0;
 					}
-					if (!zw.dead) tested += (unsigned long long)cur.n;
-					const uint32_t cb = my_ring_u32 + (uint32_t)st * (uint32_t)(CH * sizeof(Cand));
-					unsigned susp;
-					if (!cur.desc && !warp_zg)
-						susp = pair_loop<UNITW, false, false>(cb, cur.n, P, p.u, p.v, p.l, p.a0, p.a1, T0, tn_lane, zw, lut_u32,
-															  a.lut_hi0, a.lut_shift, acc);
-					else if (!cur.desc)
-						susp = pair_loop<UNITW, false, true>(cb, cur.n, P, p.u, p.v, p.l, p.a0, p.a1, T0, tn_lane, zw, lut_u32,
-															 a.lut_hi0, a.lut_shift, acc);
-					else if (!warp_zg)
-						susp = pair_loop<UNITW, true, false>(cb, cur.n, P, p.u, p.v, p.l, p.a0, p.a1, T0, tn_lane, zw, lut_u32,
-															 a.lut_hi0, a.lut_shift, acc);
-					else
-						susp = pair_loop<UNITW, true, true>(cb, cur.n, P, p.u, p.v, p.l, p.a0, p.a1, T0, tn_lane, zw, lut_u32,
-															a.lut_hi0, a.lut_shift, acc);
-					if (__any_sync(0xffffffffu, susp != 0u))
-						slow_pairs<UNITW>(susp, cb, P.periodic, P.L, P.halfL, p.u, p.v, p.l, p.a0, p.a1, zw.t_split, lut_u32,
-										  a.lut_hi0, a.lut_shift, acc, nan_pairs);
-					__syncwarp();  // every lane is done with the stage before it is refilled
-					st ^= 1;
-					cur = nxt;
-					have = have_n;
 				}
-				if (cur_label >= 0) flush(cur_label);
+				if (cur_label >= 0) flush(cur_label);  // (normally already flushed by the drain iteration)
 			}
-			__syncthreads();  // desc[] is rewritten for the next slab
 		}
 	}
 
@@ -1097,16 +1192,15 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &g, const DevPara
 	cb = w.cub_bytes;
 	MIA_CUDA_CHECK(cub::DeviceScan::InclusiveSum(w.cub_tmp, cb, w.task_cost, w.task_cum, cfg.max_tasks, st));
 
-	// ---- launch: one CTA per work slot of equal estimated cost.  The slot count is fixed (SLOTS_PER_SM per SM), NOT
-	// derived from occupancy: the grouping of the fp64 sums, hence every output bit, is the same for the weighted and
-	// the unit-weight kernel variants, which is what lets w = 0.5 scale the results by exactly 1/4. ---------------------
-	const size_t smem = tiled_smem_bytes(P.n_r, unit_w);
+	// ---- launch.  The number of worker warps is fixed (SLOTS_PER_SM CTAs per SM), NOT derived from occupancy: the
+	// grouping of the fp64 sums, hence every output bit, is the same for the weighted and the unit-weight kernel variants,
+	// which is what lets w = 0.5 scale the results by exactly 1/4 (reference tests/test_weights.py:34-35). ---------------
+	const size_t smem = tiled_smem_bytes(unit_w);
 	if (unit_w) {
 		MIA_CUDA_CHECK(cudaFuncSetAttribute(k_tiled_rppi<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	} else {
 		MIA_CUDA_CHECK(cudaFuncSetAttribute(k_tiled_rppi<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	}
-	const int Gc = cfg.n_slots;
 	TiledArgs a;
 	a.P = P;
 	a.cand = G.cand;
@@ -1129,13 +1223,13 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &g, const DevPara
 	a.A = A;
 	a.nz = cfg.nz;
 	a.n_side = cfg.n_side;
-	a.G = Gc;
+	a.n_workers = cfg.n_ctas * TW;
 	a.shard_index = shard.index;
 	a.shard_count = shard.count;
 	a.max_tasks = cfg.max_tasks;
 	a.flags = flags;
-	if (unit_w) k_tiled_rppi<true><<<Gc, TP, smem, st>>>(a);
-	else k_tiled_rppi<false><<<Gc, TP, smem, st>>>(a);
+	if (unit_w) k_tiled_rppi<true><<<cfg.n_ctas, TP, smem, st>>>(a);
+	else k_tiled_rppi<false><<<cfg.n_ctas, TP, smem, st>>>(a);
 	MIA_CUDA_CHECK(cudaGetLastError());
 	return 0;
 }
