@@ -34,11 +34,11 @@ namespace mia {
 
 constexpr int TP = 128;          // threads per CTA
 constexpr int TW = TP / 32;      // warps per CTA (independent workers)
-constexpr int CH = 32;           // candidates per staged chunk (<= 32: the suspect mask is one word)
+constexpr int CH = 64;           // candidates per staged chunk
 constexpr int STAGES = 2;        // per-warp double buffering
 constexpr int MAX_NEIGH = 128;   // neighbour columns per task
 constexpr int LUT_SIZE = 256;
-constexpr int W_R = 3;           // r bins per accumulation window
+constexpr int W_R = 5;           // r bins per accumulation window
 constexpr int NSLOT = 2 * W_R;   // private histogram slots per thread
 constexpr int SLOTS_PER_SM = 6;  // CTAs launched per SM; fixed, so that results do not depend on occupancy
 
@@ -135,7 +135,7 @@ inline bool build_lut(const mia_params *p, TiledConfig &cfg) {
 }
 
 inline size_t tiled_smem_bytes(bool unit_w) {
-	const size_t fixed = sizeof(Cand) * TW * STAGES * CH + sizeof(LutEntry) * LUT_SIZE + sizeof(int) * TW * MAX_NEIGH + 256 + 768;
+	const size_t fixed = sizeof(Cand) * TW * STAGES * CH + sizeof(int) * TW * MAX_NEIGH + 256 + 768;
 	const size_t per_slot = (size_t)TP * (8 + 8 + 4 + (unit_w ? 0 : 8));
 	return fixed + per_slot * NSLOT;
 }
@@ -550,26 +550,31 @@ struct PrivAcc {
 	uint32_t a2, ac, aw;
 };
 
-// One accumulation window of r bins [ra, ra + W_R): squared-separation limits as bit patterns.
+// One accumulation window of r bins [ra, ra + W_R): its squared-separation limits and interior thresholds.
 struct RWindow {
-	long long lo_b, hi_b;  // pairs with lo <= r_p^2 < hi belong to the window
+	double lo, hi;        // pairs with lo <= r_p^2 < hi belong to the window
+	double thr[W_R - 1];  // interior thresholds (+inf when the window has fewer bins): r bin = ra + #{thr <= r_p^2}
 	int ra;
 };
 
 // One staged chunk (n <= 32 candidates at shared address cb) against this thread's shape galaxy.
-//   XYW : compare-and-wrap the projected separations per pair (lanes whose column pair crosses the periodic boundary)
-//   ZG  : compare-and-wrap + range-check the line-of-sight separation per pair (slab straddles +-L/2 or the Pi range)
-//         otherwise the lane-constant image shift is added (exactly the reference's `sep -= L` / `sep += L`)
-// Returns a bit mask of candidates whose |cos| is within 1e-11 of 1: they are NOT accumulated here but re-evaluated
-// with the reference's exact operation sequence by slow_pairs() (its NaN rule, measure_w_box_jk.py:416-417).
-template <bool UNITW, bool XYW, bool ZG>
-__device__ __forceinline__ unsigned pair_loop(uint32_t cb, int n, int periodic, double L, double halfL, double pu,
-											  double pv, double pl, double a0, double a1, const RWindow &rw,
-											  long long hi_b_lane, const ZWindow &zw, uint32_t lut, int lut_hi0,
-											  int lut_shift, const PrivAcc &acc) {
-	// squared separations are non-negative doubles: their bit patterns order like the values, so every comparison of
-	// r_p^2 against a threshold is done on the INTEGER pipe and the FP64 pipe (the bound of this kernel) is spared
-	unsigned suspects = 0u;
+//   MODE 0 : no pair of the chunk takes a different periodic image than its lane's constant line-of-sight shift
+//            (exactly the reference's `sep -= L` / `sep += L`, measure_w_box_jk.py:403-404), no Pi range edge can be hit
+//   MODE 1 : the line-of-sight separation is wrapped per pair and range-checked (slab straddles +-L/2 or a range edge)
+//   MODE 2 : all three separations are wrapped per pair (the column pair crosses the periodic boundary)
+// Returns true when some candidate has |cos| within 1e-11 of 1 for this lane: those pairs are NOT accumulated here
+// but re-evaluated with the reference's exact operation sequence by slow_pairs() (its NaN rule, :416-417).
+template <bool UNITW, int MODE>
+__device__ __forceinline__ bool pair_loop(uint32_t cb, int n, int periodic, double L, double halfL, double pu, double pv,
+										  double pl, double a0, double a1, const RWindow &rw, double hi_lane,
+										  const ZWindow &zw, const PrivAcc &acc) {
+	// periodic image of one separation, branch-free and exactly the reference's two conditional shifts (:403-404):
+	// |d| > L/2  =>  d -= copysign(L, d)   (after the first shift the second condition can no longer hold)
+	auto wrap = [&](double d) {
+		const double sl = __hiloint2double(__double2hiint(L) | (__double2hiint(d) & 0x80000000), __double2loint(L));
+		return (fabs(d) > halfL) ? __dsub_rn(d, sl) : d;  // sl = copysign(L, d)
+	};
+	bool lane_susp = false;
 	double cu, cv, cl, cw, mu_, mv_, ml_, mw_;  // current candidate and the one after it (prefetch distance 2)
 	lds_v2(cu, cv, cb);
 	lds_v2(cl, cw, cb + 16);
@@ -584,33 +589,23 @@ __device__ __forceinline__ unsigned pair_loop(uint32_t cb, int n, int periodic, 
 		double nu, nv, nl, nw;
 		lds_v2(nu, nv, na);
 		lds_v2(nl, nw, na + 16);
-		double du = __dsub_rn(pu, cu), dv = __dsub_rn(pv, cv);  // shape minus position, :401
-		if (XYW) {
-			du = (du > halfL) ? __dsub_rn(du, L) : du;
-			du = (du < -halfL) ? __dadd_rn(du, L) : du;
-			dv = (dv > halfL) ? __dsub_rn(dv, L) : dv;
-			dv = (dv < -halfL) ? __dadd_rn(dv, L) : dv;
+		double du = __dsub_rn(pu, cu), dv = __dsub_rn(pv, cv), dz = __dsub_rn(pl, cl);  // shape minus position, :401
+		if (MODE == 2 && periodic) {
+			du = wrap(du);
+			dv = wrap(dv);
 		}
-		const double r2 = __dadd_rn(__dmul_rn(du, du), __dmul_rn(dv, dv));  // :407 (before the sqrt)
-		const long long r2b = __double_as_longlong(r2);
-		bool ok = (r2b >= rw.lo_b) && (r2b < hi_b_lane);
-		double dz = __dsub_rn(pl, cl);
-		if (ZG) {
-			if (periodic) {
-				dz = (dz > halfL) ? __dsub_rn(dz, L) : dz;
-				dz = (dz < -halfL) ? __dadd_rn(dz, L) : dz;
-			}
-			ok = ok && (dz >= zw.t_lo) && (dz < zw.t_hi);
+		if (MODE >= 1) {
+			if (periodic) dz = wrap(dz);
 		} else {
 			dz = __dadd_rn(dz, zw.shift);
 		}
-		// rejected pairs may index anywhere: the unsigned clamp keeps the load in bounds
-		const unsigned idx = min((unsigned)(__double2hiint(r2) - lut_hi0) >> lut_shift, (unsigned)(LUT_SIZE - 1));
-		long long lthr, lbase;
-		asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lthr), "=l"(lbase) : "r"(lut + idx * 16u));
-		int rrel = (int)lbase + ((r2b >= lthr) ? 1 : 0) - rw.ra;  // r bin relative to the window
-		rrel = min(max(rrel, 0), W_R - 1);                         // (only rejected pairs are ever clamped)
-		const uint32_t so = (uint32_t)(2 * rrel + ((dz >= zw.t_split) ? 1 : 0)) * (uint32_t)TP;
+		const double r2 = __dadd_rn(__dmul_rn(du, du), __dmul_rn(dv, dv));  // :407 (before the sqrt)
+		bool ok = (r2 >= rw.lo) && (r2 < hi_lane);
+		if (MODE >= 1) ok = ok && (dz >= zw.t_lo) && (dz < zw.t_hi);
+		int slot = (dz >= zw.t_split) ? 1 : 0;
+#pragma unroll
+		for (int k = 0; k < W_R - 1; k++) slot += (r2 >= rw.thr[k]) ? 2 : 0;
+		const uint32_t so = (uint32_t)slot * (uint32_t)TP;
 		// private slots: loads first, the arithmetic below hides their latency
 		double s0, s1, sw = 0.0;
 		lds_v2(s0, s1, acc.a2 + so * 16u);
@@ -631,7 +626,7 @@ __device__ __forceinline__ unsigned pair_loop(uint32_t cb, int n, int periodic, 
 		double gp = fma(cr * cr, inv2, -1.0);  // cos 2phi = 2 cos^2 - 1
 		double gc = (cr * fabs(sr)) * inv2;    // sin 2phi = 2 cos phi |sin phi|   (phi in [0, pi])
 		const bool susp = ok && (gp >= 1.0 - 1e-11);  // |cos| ~ 1: the reference's NaN rule may apply -> exact path
-		suspects |= (susp ? 1u : 0u) << j;
+		lane_susp = lane_susp || susp;
 		ok = ok && !susp;
 		if (!UNITW) {
 			gp *= cw;
@@ -649,14 +644,17 @@ __device__ __forceinline__ unsigned pair_loop(uint32_t cb, int n, int periodic, 
 		ml_ = nl;
 		mw_ = nw;
 	}
-	return suspects;
+	return lane_susp;
 }
 
-// Rare path: the candidates flagged by pair_loop, with the reference's exact cos (and its NaN rule).
+// Rare path: rescan the chunk for the pairs pair_loop skipped (|cos| ~ 1), with the reference's exact operation
+// sequence for the separation, cos and its NaN rule.
 template <bool UNITW>
-__device__ __noinline__ void slow_pairs(unsigned suspects, uint32_t cb, int periodic, double L, double halfL, double pu,
-										double pv, double pl, double a0, double a1, double t_split, int ra, uint32_t lut,
-										int lut_hi0, int lut_shift, PrivAcc acc, unsigned long long &nan_pairs) {
+__device__ __noinline__ void slow_pairs(bool lane_susp, uint32_t cb, int n, int periodic, double L, double halfL, double pu,
+										double pv, double pl, double a0, double a1, const RWindow rw, double w_hi, double t_lo,
+										double t_hi, double t_split, PrivAcc acc, unsigned long long &nan_pairs) {
+	const double w_lo = rw.lo;
+	if (!lane_susp) return;
 	auto sep = [&](double s_, double c_) {  // measure_w_box_jk.py:401-404
 		double d = __dsub_rn(s_, c_);
 		if (periodic) {
@@ -665,25 +663,32 @@ __device__ __noinline__ void slow_pairs(unsigned suspects, uint32_t cb, int peri
 		}
 		return d;
 	};
-	while (suspects) {
-		const int j = __ffs(suspects) - 1;
-		suspects &= suspects - 1u;
+	for (int j = 0; j < n; j++) {
 		double cu, cv, cl, cw;
 		lds_v2(cu, cv, cb + (uint32_t)j * (uint32_t)sizeof(Cand));
 		lds_v2(cl, cw, cb + (uint32_t)j * (uint32_t)sizeof(Cand) + 16);
 		const double du = sep(pu, cu), dv = sep(pv, cv), dz = sep(pl, cl);
 		const double r2 = __dadd_rn(__dmul_rn(du, du), __dmul_rn(dv, dv));
+		if (!((r2 >= w_lo) && (r2 < w_hi) && (dz >= t_lo) && (dz < t_hi))) continue;
+		// the same (approximate) test pair_loop used to skip the pair
+		const double cr = fma(du, a0, __dmul_rn(dv, a1));
+		double y;
+		asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r2));
+		{
+			const double e = fma(-r2, y, 1.0);
+			y = fma(y, fma(e, e, e), y);
+		}
+		const double inv2 = __hiloint2double(__double2hiint(y) + 0x00100000, __double2loint(y));
+		if (!(fma(cr * cr, inv2, -1.0) >= 1.0 - 1e-11)) continue;
 		const double rp = __dsqrt_rn(r2);
 		const double c = __dadd_rn(__dmul_rn(__ddiv_rn(du, rp), a0), __dmul_rn(__ddiv_rn(dv, rp), a1));
 		double gp = 0.0, gc = 0.0;
 		if (fabs(c) <= 1.0) shape_projection(c, gp, gc);
 		else nan_pairs++;
-		const int idx = (__double2hiint(r2) - lut_hi0) >> lut_shift;
-		double lthr;
-		int lbase;
-		lds_lut(lthr, lbase, lut + (uint32_t)idx * 16u);
-		const int rrel = lbase + ((r2 >= lthr) ? 1 : 0) - ra;
-		const uint32_t so = (uint32_t)(2 * rrel + ((dz >= t_split) ? 1 : 0)) * (uint32_t)TP;
+		int slot = (dz >= t_split) ? 1 : 0;
+#pragma unroll
+		for (int k = 0; k < W_R - 1; k++) slot += (r2 >= rw.thr[k]) ? 2 : 0;
+		const uint32_t so = (uint32_t)slot * (uint32_t)TP;
 		double s0, s1;
 		lds_v2(s0, s1, acc.a2 + so * 16u);
 		const unsigned c0 = lds_u32(acc.ac + so * 4u);
@@ -847,12 +852,11 @@ __global__ void __launch_bounds__(TP, 4) k_tiled_rppi(const TiledArgs a) {
 
 	// ---- shared memory carve-up ------------------------------------------------------------------------------------
 	Cand *ring = reinterpret_cast<Cand *>(smem);  // [warp][stage][CH]: every warp runs its own double-buffered stream
-	LutEntry *lut_s = reinterpret_cast<LutEntry *>(smem + sizeof(Cand) * TW * STAGES * CH);
-	int *nlist_all = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(lut_s) + sizeof(LutEntry) * LUT_SIZE);
+	int *nlist_all = reinterpret_cast<int *>(smem + sizeof(Cand) * TW * STAGES * CH);
 	uint64_t *full = reinterpret_cast<uint64_t *>(nlist_all + TW * MAX_NEIGH);  // [warp][stage]
 	double *thr2_s = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(full) + 256);
 	unsigned char *accbase = reinterpret_cast<unsigned char *>(thr2_s) + 768;
-	const uint32_t lut_u32 = smem_u32(lut_s), acc_u32 = smem_u32(accbase);
+	const uint32_t acc_u32 = smem_u32(accbase);
 	Cand *my_ring = ring + (size_t)warp * STAGES * CH;
 	uint64_t *my_full = full + warp * STAGES;
 	int *nlist = nlist_all + warp * MAX_NEIGH;
@@ -867,7 +871,6 @@ __global__ void __launch_bounds__(TP, 4) k_tiled_rppi(const TiledArgs a) {
 		mbar_fence_init();
 		if (blockIdx.x == 0) a.A.stats[6] = (unsigned long long)a.n_tasks[0];
 	}
-	for (int e = tid; e < LUT_SIZE; e += blockDim.x) lut_s[e] = a.lut[e];
 	for (int e = tid; e <= P.n_2; e += blockDim.x) thr2_s[e] = P.thr2[e];
 #pragma unroll
 	for (int s = 0; s < NSLOT; s++) {
@@ -970,10 +973,12 @@ __global__ void __launch_bounds__(TP, 4) k_tiled_rppi(const TiledArgs a) {
 				const int rb = P.n_r - 1 - q * W_R, ra = (rb - W_R + 1 > 0) ? rb - W_R + 1 : 0;
 				RWindow rw;
 				rw.ra = ra;
-				rw.lo_b = __double_as_longlong(P.r2_thr[ra]);
-				rw.hi_b = __double_as_longlong(P.r2_thr[rb + 1]);
-				const double win_hi = P.r2_thr[rb + 1];
-				const long long hi_b_lane = zw.dead ? 0ll : rw.hi_b;  // dead lanes never pass the range test
+				rw.lo = P.r2_thr[ra];
+				rw.hi = P.r2_thr[rb + 1];
+#pragma unroll
+				for (int k = 0; k < W_R - 1; k++) rw.thr[k] = (ra + 1 + k <= rb) ? P.r2_thr[ra + 1 + k] : INFINITY;
+				const double win_hi = rw.hi;
+				const double hi_lane = zw.dead ? -1.0 : rw.hi;  // dead lanes never pass the range test
 
 				auto flush = [&](int jkD) {
 					binned += flush_slots<UNITW>(fc, acc, key, zw.dead, pe, p.w, ra, rb, jkD);
@@ -1115,16 +1120,16 @@ __global__ void __launch_bounds__(TP, 4) k_tiled_rppi(const TiledArgs a) {
 						}
 						if (!zw.dead) tested += (unsigned long long)pend.n;
 						const uint32_t cb = my_ring_u32 + (uint32_t)pend_st * (uint32_t)(CH * sizeof(Cand));
-						unsigned susp;
-						if (!pend.xyw && !warp_zg)  // the common case: no periodic image, no range edge in this chunk
-							susp = pair_loop<UNITW, false, false>(cb, pend.n, periodic, L, halfL, p.u, p.v, p.l, p.a0, p.a1, rw,
-																  hi_b_lane, zw, lut_u32, a.lut_hi0, a.lut_shift, acc);
-						else  // compare-and-wrap everything per pair
-							susp = pair_loop<UNITW, true, true>(cb, pend.n, periodic, L, halfL, p.u, p.v, p.l, p.a0, p.a1, rw,
-																hi_b_lane, zw, lut_u32, a.lut_hi0, a.lut_shift, acc);
-						if (__any_sync(0xffffffffu, susp != 0u))
-							slow_pairs<UNITW>(susp, cb, periodic, L, halfL, p.u, p.v, p.l, p.a0, p.a1, zw.t_split, ra, lut_u32,
-											  a.lut_hi0, a.lut_shift, acc, nan_pairs);
+						bool susp;
+						if (pend.xyw)
+							susp = pair_loop<UNITW, 2>(cb, pend.n, periodic, L, halfL, p.u, p.v, p.l, p.a0, p.a1, rw, hi_lane, zw, acc);
+						else if (warp_zg)
+							susp = pair_loop<UNITW, 1>(cb, pend.n, periodic, L, halfL, p.u, p.v, p.l, p.a0, p.a1, rw, hi_lane, zw, acc);
+						else  // the common case: no periodic image or range edge inside this chunk
+							susp = pair_loop<UNITW, 0>(cb, pend.n, periodic, L, halfL, p.u, p.v, p.l, p.a0, p.a1, rw, hi_lane, zw, acc);
+						if (__any_sync(0xffffffffu, susp))
+							slow_pairs<UNITW>(susp, cb, pend.n, periodic, L, halfL, p.u, p.v, p.l, p.a0, p.a1, rw, hi_lane, zw.t_lo,
+											  zw.t_hi, zw.t_split, acc, nan_pairs);
 						__syncwarp();  // every lane is done with the stage before it is refilled
 					}
 					if (got) {
