@@ -3,7 +3,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmia_b200.so")
+LIB_PATH = os.environ.get("MIA_LIB_PATH", os.path.join(_HERE, "lib", "libmia_b200.so"))
 PEAKS_PATH = os.path.join(_HERE, "lib", "libmia_peaks.so")
 CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "mia_b200.h")

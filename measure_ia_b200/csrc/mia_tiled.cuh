@@ -34,11 +34,26 @@ namespace mia {
 
 constexpr int TP = 128;          // threads per CTA
 constexpr int TW = TP / 32;      // warps per CTA (independent workers)
-constexpr int CH = 64;           // candidates per staged chunk
+// Tuning constants (measured on B200, cfg2: profiles/r01_tuning.md)
+#ifndef MIA_CH
+#define MIA_CH 96
+#endif
+#ifndef MIA_W_R
+#define MIA_W_R 5
+#endif
+#ifndef MIA_UNROLL
+#define MIA_UNROLL 4
+#endif
+#define MIA_PRAGMA(x) _Pragma(#x)
+#define MIA_UNROLL_PRAGMA(n) MIA_PRAGMA(unroll n)
+#ifndef MIA_MIN_CTAS
+#define MIA_MIN_CTAS 3
+#endif
+constexpr int CH = MIA_CH;       // candidates per staged chunk
 constexpr int STAGES = 2;        // per-warp double buffering
 constexpr int MAX_NEIGH = 128;   // neighbour columns per task
 constexpr int LUT_SIZE = 256;
-constexpr int W_R = 5;           // r bins per accumulation window
+constexpr int W_R = MIA_W_R;     // r bins per accumulation window
 constexpr int NSLOT = 2 * W_R;   // private histogram slots per thread
 constexpr int SLOTS_PER_SM = 6;  // CTAs launched per SM; fixed, so that results do not depend on occupancy
 
@@ -583,7 +598,7 @@ __device__ __forceinline__ bool pair_loop(uint32_t cb, int n, int periodic, doub
 		lds_v2(mu_, mv_, a1_);
 		lds_v2(ml_, mw_, a1_ + 16);
 	}
-#pragma unroll 2
+	MIA_UNROLL_PRAGMA(MIA_UNROLL)
 	for (int j = 0; j < n; j++) {
 		const uint32_t na = cb + (uint32_t)((j + 2 < n) ? (j + 2) : (n - 1)) * (uint32_t)sizeof(Cand);
 		double nu, nv, nl, nw;
@@ -841,7 +856,7 @@ struct Chunk {
 };
 
 template <bool UNITW>
-__global__ void __launch_bounds__(TP, 4) k_tiled_rppi(const TiledArgs a) {
+__global__ void __launch_bounds__(TP, MIA_MIN_CTAS) k_tiled_rppi(const TiledArgs a) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	const DevParams &P = a.P;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
