@@ -32,7 +32,6 @@ WORKLOADS = {
 	"small": (100_000, 205.0, "w", 27, 10, 8),
 }
 FLOP_PER_PAIR = {"w": 64.0, "multipoles": 80.0}  # algorithmic FP64 work per binned pair
-MY_KERNELS_PER_STEP = 9  # 2x make_keys, 2x gather, 2x cell_start, pair kernel, finalize, copy_stats (CUB sort excluded)
 
 
 def sample_clocks(stop, out):
@@ -173,11 +172,16 @@ def main():
 	th.start()
 	ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
 	wall0 = time.perf_counter()
+	kernel_ms, build_ms, reduce_ms = [], [], []
 	for k in range(args.steps):
 		flush.zero_()  # L2 flush between timed iterations (outside the per-step events)
 		ev[k][0].record()
 		out = step()
 		ev[k][1].record()
+		# phase times measured by the library with CUDA events on the launching stream (include/mia_b200.h, timings_host)
+		build_ms.append(ops.LAST_TIMINGS_MS[0])
+		kernel_ms.append(ops.LAST_TIMINGS_MS[1])
+		reduce_ms.append(ops.LAST_TIMINGS_MS[2])
 	barrier()
 	wall = time.perf_counter() - wall0
 	stop.set()
@@ -203,7 +207,9 @@ def main():
 				   "parallelism": f"shape-sample shards x{world}" if world > 1 else "single GPU",
 				   "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA events)",
 				   "wall_s_timed_region": wall, "thresholds_clean": bool(clean)},
-		"gpu_launches": MY_KERNELS_PER_STEP * args.steps,
+		"gpu_launches": int(stats[7].item()) * args.steps,
+		"phases_ms": {"cell_list_build": sum(build_ms) / len(build_ms), "pair_kernel": sum(kernel_ms) / len(kernel_ms),
+					  "reductions": sum(reduce_ms) / len(reduce_ms)},
 	}
 
 	if rank == 0:
@@ -220,16 +226,18 @@ def main():
 		scratch = torch.empty(blocks * 256, dtype=torch.float64, device=dev)
 		torch.cuda.synchronize(dev)
 		fp64_peak = float(peaks.mia_peak_fp64_tflops(5, 4096, scratch.data_ptr(), blocks))
-		# kernel-only time: the pair kernel dominates the step; measured as step time minus a step with zero shapes
-		achieved = pairs / world * FLOP_PER_PAIR[kind] / (total_ms / args.steps * 1e-3) / 1e12
+		# duration of the dominant (pair) kernel alone, CUDA events on its stream, average over the timed steps
+		t_kernel = sum(kernel_ms) / len(kernel_ms) * 1e-3
+		achieved = pairs / world * FLOP_PER_PAIR[kind] / t_kernel / 1e12
 		hbm_bytes = 96.0 * N
 		line["roofline"] = {
 			"bound": "fp64-alu", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
 			"frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": None,
-			"note": ("pair loop is FP64-issue bound (SURVEY.md 8(d)): achieved = binned pairs x %d flop / step time "
-					 "(whole step incl. cell build, so a lower bound for the kernel); peak = dependent-free DFMA rate "
-					 "measured live by libmia_peaks.so; algorithmic HBM bytes per step = %.3g (%.2e B/pair), "
-					 "HBM peak %s GB/s (MEASURED_PEAKS.json) is not the limiter" % (
+			"kernel_ms": t_kernel * 1e3,
+			"note": ("pair loop is FP64-issue bound (SURVEY.md 8(d)): achieved = binned pairs x %d flop / pair-kernel time "
+					 "(CUDA events around the kernel on its stream); peak = dependent-free DFMA rate measured live by "
+					 "libmia_peaks.so (MEASURED_PEAKS.json carries no FP64 figure); algorithmic HBM bytes per step = %.3g "
+					 "(%.2e B/pair), HBM peak %s GB/s (MEASURED_PEAKS.json) is not the limiter" % (
 						 int(FLOP_PER_PAIR[kind]), hbm_bytes, hbm_bytes / max(pairs, 1), _hbm_peak())),
 		}
 

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MIA_ABI_VERSION 1
+#define MIA_ABI_VERSION 2
 #define MIA_MAX_BINS 64 /* per axis */
 
 enum { MIA_GEOM_RPPI = 0, MIA_GEOM_RMU = 1 };
@@ -62,6 +62,10 @@ typedef struct mia_params {
 	const double *r2_thr_host;
 	/* thr2_host[b], b = 0..n_2 : same for the second axis (Pi, or mu_r = Pi / r); use -inf / +inf for "no limit". */
 	const double *thr2_host;
+	/* optional HOST pointer to 4 floats, filled when the call returns: milliseconds (CUDA events on `stream`) spent in
+	 * [0] the cell-list build (keys, radix sort, gather, offsets, task table), [1] the pair kernel, [2] the fixed-order
+	 * reductions, [3] the whole call.  NULL = do not time. */
+	float *timings_host;
 } mia_params;
 
 /* One catalogue.  pos is row-major [n][3] in the caller's column order.  axis / e are only read for the shape sample:
@@ -89,7 +93,8 @@ typedef struct mia_hist {
 	double *dd_jk_w;      /* -> DD_jk      */
 	double *spd_jk;       /* -> Splus_D_jk */
 	uint64_t *stats;      /* [8]: 0 candidate pairs tested, 1 pairs binned, 2 |c|>1 pairs (NaN rule), 3 window errors,
-	                                4 kernel used (MIA_KERNEL_*), 5 cells, 6 tiles/CTA tasks, 7 reserved */
+	                                4 kernel used (MIA_KERNEL_*), 5 cells, 6 warp tasks, 7 kernels launched by the library
+	                                (its own kernels; the CUB radix-sort / scan launches are not counted) */
 } mia_hist;
 
 /* Shard of the shape sample handled by this call (multi-GPU: rank r of w takes the r-th of w work-balanced slices of

@@ -568,8 +568,9 @@ def combine_across_ranks(dd_count, dd_w, spd, scd, jk_count, jk_w, spd_jk, stats
 	jk_count = ints[n0:n0 + n1].view_as(jk_count)
 	stats_sum = ints[n0 + n1:].view_as(stats)
 	floats = torch.cat([t.flatten() for t in (dd_w, spd, scd, jk_w, spd_jk)])
-	gathered = torch.empty((world, floats.numel()), dtype=floats.dtype, device=floats.device)
-	dist.all_gather_into_tensor(gathered, floats)
+	flat = torch.empty(world * floats.numel(), dtype=floats.dtype, device=floats.device)
+	dist.all_gather_into_tensor(flat, floats)
+	gathered = flat.view(world, floats.numel())
 	if floats.is_cuda:
 		total = ops.combine_partials(gathered)
 	else:  # gloo tests of the host logic

@@ -199,12 +199,12 @@ __global__ void k_reduce_partials(unsigned long long *__restrict__ cnt, double *
 }
 
 __global__ void k_copy_stats(const unsigned long long *in, uint64_t *out, unsigned long long kernel,
-							 unsigned long long cells, unsigned long long tasks) {
+							 unsigned long long cells, unsigned long long tasks, unsigned long long launches) {
 	if (threadIdx.x < 4) out[threadIdx.x] = in[threadIdx.x];
 	if (threadIdx.x == 4) out[4] = kernel;
 	if (threadIdx.x == 5) out[5] = cells;
 	if (threadIdx.x == 6) out[6] = tasks ? tasks : in[6];
-	if (threadIdx.x == 7) out[7] = 0;
+	if (threadIdx.x == 7) out[7] = launches;
 }
 
 __global__ void k_combine(const double *__restrict__ parts, int n_parts, int64_t n, double *__restrict__ out) {
@@ -284,6 +284,15 @@ int mia_paircount(const mia_params *params, const mia_sample *D, const mia_sampl
 	A.rows = pl.rows;
 	int *flags = (int *)(ws + pl.off_flags);
 
+	// optional phase timing with CUDA events on the caller's stream
+	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+	const bool timed = params->timings_host != nullptr;
+	if (timed) {
+		for (int i = 0; i < 4; i++) MIA_CUDA_CHECK(cudaEventCreate(&ev[i]));
+		MIA_CUDA_CHECK(cudaEventRecord(ev[0], st));
+	}
+	unsigned long long n_launches = 0;
+
 	// zero accumulators, stats and flags (contiguous region from off_cnt to off_tiled)
 	MIA_CUDA_CHECK(cudaMemsetAsync(ws + pl.off_cnt, 0, pl.off_tiled - pl.off_cnt, st));
 
@@ -312,6 +321,7 @@ int mia_paircount(const mia_params *params, const mia_sample *D, const mia_sampl
 	k_cell_start<<<(unsigned)((nS + 1 + T - 1) / T), T, 0, st>>>(sc.keys_out, nS, pl.g.jk_rows, ncell, prim_cell_start);
 	MIA_CUDA_CHECK(cudaGetLastError());
 
+	n_launches += (nD > 0 ? 2 : 0) + (nS > 0 ? 2 : 0) + 2;  // make_keys, gather (x2 samples) + 2 x cell_start
 	Grid G;
 	G.cand = cand;
 	G.cand_jk = cand_jk;
@@ -323,6 +333,7 @@ int mia_paircount(const mia_params *params, const mia_sample *D, const mia_sampl
 	const int64_t s_begin = nS * shard.index / shard.count, s_end = nS * (shard.index + 1) / shard.count;
 	unsigned long long n_tasks = 0;
 
+	if (timed && pl.kernel == MIA_KERNEL_GENERAL) MIA_CUDA_CHECK(cudaEventRecord(ev[1], st));
 	if (pl.kernel == MIA_KERNEL_GENERAL) {
 		if (s_end > s_begin && nD > 0) {
 			const int TB = 128;
@@ -339,11 +350,15 @@ int mia_paircount(const mia_params *params, const mia_sample *D, const mia_sampl
 			}
 			MIA_CUDA_CHECK(cudaGetLastError());
 			n_tasks = blocks;
+			n_launches += 1;
 		}
+		if (timed) MIA_CUDA_CHECK(cudaEventRecord(ev[2], st));
 	} else {
 		const bool unit_w = (D->weight == nullptr && S->weight == nullptr);
-		rc = tiled_launch(pl.tiled, pl.g, P, G, prim, prim_cell_start, nS, unit_w, shard, A, ws + pl.off_tiled, flags, st);
+		rc = tiled_launch(pl.tiled, pl.g, P, G, prim, prim_cell_start, nS, unit_w, shard, A, ws + pl.off_tiled, flags, st,
+						  timed ? ev[1] : nullptr, timed ? ev[2] : nullptr);
 		if (rc) return rc;
+		n_launches += 1 /* cell_info */ + 2 /* col_chunks, fill_tasks */ + 1 /* pair kernel */ + 1 /* reduce_partials */;
 		if (pl.n_partials > 1) {
 			const size_t n_el = (size_t)pl.rows * pl.nb;
 			k_reduce_partials<<<(unsigned)((n_el + 127) / 128), 128, 0, st>>>(A.cnt, A.ddw, A.sp, A.sc, pl.n_partials, n_el);
@@ -356,14 +371,24 @@ int mia_paircount(const mia_params *params, const mia_sample *D, const mia_sampl
 	k_finalize<<<(pl.nb + 127) / 128, 128, 0, st>>>(A.cnt, A.ddw, A.sp, A.sc, 1, J, pl.nb, params->num_jk, *out);
 	MIA_CUDA_CHECK(cudaGetLastError());
 	if (out->stats) {
+		n_launches += 2;  // finalize + copy_stats
 		k_copy_stats<<<1, 32, 0, st>>>(A.stats, out->stats, (unsigned long long)pl.kernel, (unsigned long long)ncell,
-									   n_tasks);
+									   n_tasks, n_launches);
 		MIA_CUDA_CHECK(cudaGetLastError());
 	}
 	// range / window flags are checked synchronously: a wrong answer must never be returned silently
 	int h_flags[8];
 	MIA_CUDA_CHECK(cudaMemcpyAsync(h_flags, flags, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+	if (timed) MIA_CUDA_CHECK(cudaEventRecord(ev[3], st));
 	MIA_CUDA_CHECK(cudaStreamSynchronize(st));
+	if (timed) {
+		float *t = params->timings_host;
+		cudaEventElapsedTime(&t[0], ev[0], ev[1]);
+		cudaEventElapsedTime(&t[1], ev[1], ev[2]);
+		cudaEventElapsedTime(&t[2], ev[2], ev[3]);
+		cudaEventElapsedTime(&t[3], ev[0], ev[3]);
+		for (int i = 0; i < 4; i++) cudaEventDestroy(ev[i]);
+	}
 	if (h_flags[0]) return MIA_ERR_RANGE;
 	if (h_flags[1]) return MIA_ERR_WINDOW;
 	return MIA_OK;

@@ -1194,10 +1194,14 @@ inline int tiled_prepare_candidates(const TiledConfig &cfg, const GridDims &g, c
 
 inline int tiled_launch(const TiledConfig &cfg, const GridDims &g, const DevParams &P, const Grid &G, const Prim *prim,
 						const int64_t *prim_cell_start, int64_t nS, bool unit_w, mia_shard shard, const Accum &A, void *ws,
-						int *flags, cudaStream_t st) {
+						int *flags, cudaStream_t st, cudaEvent_t ev_before = nullptr, cudaEvent_t ev_after = nullptr) {
 	TiledWorkspace w = carve_tiled(cfg, g, ws);
 	const int64_t ncol = (int64_t)g.ncu * g.ncv;
-	if (nS == 0 || G.n_cand == 0) return 0;
+	if (nS == 0 || G.n_cand == 0) {
+		if (ev_before) MIA_CUDA_CHECK(cudaEventRecord(ev_before, st));
+		if (ev_after) MIA_CUDA_CHECK(cudaEventRecord(ev_after, st));
+		return 0;
+	}
 	// ---- task table -------------------------------------------------------------------------------------------------------
 	MIA_CUDA_CHECK(cudaMemsetAsync(w.task_cost, 0, sizeof(unsigned long long) * cfg.max_tasks, st));
 	k_col_chunks<<<(unsigned)((ncol + 1 + 255) / 256), 256, 0, st>>>(prim_cell_start, ncol, cfg.nz, w.col_chunks);
@@ -1248,9 +1252,11 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &g, const DevPara
 	a.shard_count = shard.count;
 	a.max_tasks = cfg.max_tasks;
 	a.flags = flags;
+	if (ev_before) MIA_CUDA_CHECK(cudaEventRecord(ev_before, st));
 	if (unit_w) k_tiled_rppi<true><<<cfg.n_ctas, TP, smem, st>>>(a);
 	else k_tiled_rppi<false><<<cfg.n_ctas, TP, smem, st>>>(a);
 	MIA_CUDA_CHECK(cudaGetLastError());
+	if (ev_after) MIA_CUDA_CHECK(cudaEventRecord(ev_after, st));
 	return 0;
 }
 

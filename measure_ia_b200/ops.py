@@ -14,7 +14,7 @@ import torch
 
 from .build import LIB_PATH
 
-MIA_ABI_VERSION = 1
+MIA_ABI_VERSION = 2
 GEOM_RPPI, GEOM_RMU = 0, 1
 KERNEL_AUTO, KERNEL_GENERAL, KERNEL_TILED = 0, 1, 2
 KERNEL_NAMES = {"auto": KERNEL_AUTO, "general": KERNEL_GENERAL, "tiled": KERNEL_TILED}
@@ -25,7 +25,7 @@ class MiaParams(ctypes.Structure):
 		("abi_version", ctypes.c_int32), ("geometry", ctypes.c_int32), ("n_r", ctypes.c_int32), ("n_2", ctypes.c_int32),
 		("los", ctypes.c_int32), ("periodic", ctypes.c_int32), ("num_jk", ctypes.c_int32), ("kernel", ctypes.c_int32),
 		("boxsize", ctypes.c_double), ("r_search", ctypes.c_double), ("rp2_cut", ctypes.c_double),
-		("r2_thr_host", ctypes.c_void_p), ("thr2_host", ctypes.c_void_p),
+		("r2_thr_host", ctypes.c_void_p), ("thr2_host", ctypes.c_void_p), ("timings_host", ctypes.c_void_p),
 	]
 
 
@@ -84,12 +84,16 @@ def check(rc):
 		raise RuntimeError(f"libmia_b200: {load_library().mia_strerror(rc).decode()} (code {rc})")
 
 
-def make_params(geometry, n_r, n_2, los, periodic, num_jk, kernel, boxsize, r_search, rp2_cut, r2_thr, thr2):
+LAST_TIMINGS_MS = [0.0, 0.0, 0.0, 0.0]  # [cell-list build, pair kernel, reductions, whole call] of the last paircount call
+_timing_buf = (ctypes.c_float * 4)()
+
+
+def make_params(geometry, n_r, n_2, los, periodic, num_jk, kernel, boxsize, r_search, rp2_cut, r2_thr, thr2, timings=None):
 	"""r2_thr / thr2: CPU float64 tensors (kept alive by the caller for the duration of the call)."""
 	assert r2_thr.dtype == torch.float64 and thr2.dtype == torch.float64 and not r2_thr.is_cuda and not thr2.is_cuda
 	assert r2_thr.numel() == n_r + 1 and thr2.numel() == n_2 + 1
 	return MiaParams(MIA_ABI_VERSION, geometry, n_r, n_2, los, 1 if periodic else 0, num_jk, kernel, boxsize, r_search,
-					 rp2_cut, r2_thr.data_ptr(), thr2.data_ptr())
+					 rp2_cut, r2_thr.data_ptr(), thr2.data_ptr(), ctypes.addressof(timings) if timings is not None else None)
 
 
 def _dev_ptr(t: Optional[torch.Tensor], dtype, shape_tail=None):
@@ -116,7 +120,8 @@ def paircount(pos_d: torch.Tensor, weight_d: Optional[torch.Tensor], jk_d: Optio
 	lib = load_library()
 	dev = pos_d.device
 	n_r, n_2 = r2_thr.numel() - 1, thr2.numel() - 1
-	params = make_params(geometry, n_r, n_2, los, periodic, num_jk, kernel, boxsize, r_search, rp2_cut, r2_thr, thr2)
+	params = make_params(geometry, n_r, n_2, los, periodic, num_jk, kernel, boxsize, r_search, rp2_cut, r2_thr, thr2,
+						 _timing_buf)
 	f64, i32, i64 = torch.float64, torch.int32, torch.int64
 	D = MiaSample(pos_d.shape[0], _dev_ptr(pos_d, f64), _dev_ptr(weight_d, f64), _dev_ptr(jk_d, i32), None, None)
 	S = MiaSample(pos_s.shape[0], _dev_ptr(pos_s, f64), _dev_ptr(weight_s, f64), _dev_ptr(jk_s, i32),
@@ -138,6 +143,7 @@ def paircount(pos_d: torch.Tensor, weight_d: Optional[torch.Tensor], jk_d: Optio
 		rc = lib.mia_paircount(ctypes.byref(params), ctypes.byref(D), ctypes.byref(S), MiaShard(shard_index, shard_count),
 							   ctypes.byref(H), ws.data_ptr(), ws_bytes, stream)
 	check(rc)
+	LAST_TIMINGS_MS[:] = list(_timing_buf)
 	return [dd_count, dd_w, spd, scd, jk_count, jk_w, spd_jk, stats]
 
 

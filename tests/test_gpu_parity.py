@@ -103,8 +103,8 @@ def _host_call(torch, oracle, data, geom, num_jk, boxsize, n_r, n_2, kernel=0, s
 	L = round(num_jk ** (1 / 3)) if num_jk else 0
 	jk = box._jackknife_labels(pos, L).astype(np.int32) if num_jk else None
 	r2_thr, thr2, rp2_cut, _ = box._thresholds_for(geom, None)
-	P = ops.MiaParams(1, 0 if geom == "rppi" else 1, n_r, n_2, int(data["LOS"]), 1, num_jk, kernel, boxsize,
-					  float(box.r_bins[-1]), rp2_cut, r2_thr.ctypes.data, thr2.ctypes.data)
+	P = ops.MiaParams(ops.MIA_ABI_VERSION, 0 if geom == "rppi" else 1, n_r, n_2, int(data["LOS"]), 1, num_jk, kernel, boxsize,
+					  float(box.r_bins[-1]), rp2_cut, r2_thr.ctypes.data, thr2.ctypes.data, None)
 	ptr = lambda a: a.ctypes.data if a is not None else None  # noqa: E731
 	D = ops.MiaSample(len(pos), ptr(pos), ptr(w), ptr(jk), None, None)
 	S = ops.MiaSample(len(pos_s), ptr(pos_s), ptr(w_s), ptr(jk), ptr(axis), ptr(e))

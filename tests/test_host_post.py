@@ -200,7 +200,7 @@ def test_library_exports_every_declared_symbol():
 	assert declared == set(ops.EXPORTS), declared ^ set(ops.EXPORTS)
 	for sym in declared:
 		assert hasattr(lib, sym), sym
-	assert ops.load_library().mia_abi_version() == 1
+	assert ops.load_library().mia_abi_version() == ops.MIA_ABI_VERSION
 	assert ops.load_library().mia_strerror(-3).decode().startswith("a coordinate")
 
 
