@@ -259,7 +259,7 @@ def main():
 		if world > 1:
 			dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
 		nb = n_r * n_2
-		h2d = N * (24 + 16 + 8 + (4 if num_jk else 0))
+		h2d = N * (24 + 16 + 8 + 8)  # Position, Axis_Direction, q, weight (jackknife labels are computed on the device)
 		d2h = nb * 8 * 4 + num_jk * nb * 8 * 3 + 64
 		line["e2e"] = {"value": pairs * e2e_steps / float(e2e_t.item()), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
 					   "d2h_bytes_per_step": d2h, "wall_s_per_call": float(e2e_t.item()) / e2e_steps,

@@ -351,6 +351,86 @@ class MeasureIABox(MeasureIABase):
 			self._thresholds[key] = (r2_thr, thr2, calib.rp_cut_threshold(rp_cut), clean)
 		return self._thresholds[key]
 
+	# ---- input preparation on the device (same semantics as _prepare / _jackknife_labels / _responsivity) ---------------
+	def _prepare_device(self, masks, ellipticity, L_subboxes, dev):
+		"""Upload the raw catalogue once and do the whole preparation with fp64 torch ops on the GPU: mask selection,
+		axis normalisation, e(q), jackknife labels (strict-inequality rule, label 0 on faces), responsivities and the
+		per-region counts.  At 1e6-1e7 galaxies the numpy versions cost as much as the pair kernel itself
+		(SURVEY.md 8(f)-1); sqrt and division are IEEE-exact on the device, so axis / e / labels are bit-identical."""
+		import torch
+		d = self.data
+		f64 = torch.float64
+
+		def up(a, dtype=f64):
+			return torch.from_numpy(np.ascontiguousarray(a)).to(dev).to(dtype)
+
+		same = masks is None and d["Position"] is d["Position_shape_sample"] and d["weight"] is d["weight_shape_sample"]
+		pos = up(d["Position"])
+		pos_s = pos if same else up(d["Position_shape_sample"])
+		axis_v, q = up(d["Axis_Direction"]), up(d["q"])
+		w = up(d["weight"])
+		w_s = w if same else up(d["weight_shape_sample"])
+		if masks is not None:
+			# quirk kept from the reference (measure_w_box_jk.py:338-347): without explicit weight masks the FIRST
+			# sum(mask) weights are used, and the fabricated masks are stored in the caller's dict
+			if "weight" not in masks:
+				m = np.ones(self.Num_position, dtype=bool)
+				m[sum(masks["Position"]):self.Num_position] = 0
+				masks["weight"] = m
+			if "weight_shape_sample" not in masks:
+				m = np.ones(self.Num_shape, dtype=bool)
+				m[sum(masks["Position_shape_sample"]):self.Num_shape] = 0
+				masks["weight_shape_sample"] = m
+			mk = lambda k: torch.from_numpy(np.ascontiguousarray(masks[k], dtype=bool)).to(dev)  # noqa: E731
+			pos, pos_s = pos[mk("Position")], pos_s[mk("Position_shape_sample")]
+			axis_v, q = axis_v[mk("Axis_Direction")], q[mk("q")]
+			w, w_s = w[mk("weight")], w_s[mk("weight_shape_sample")]
+		axis_len = torch.sqrt(axis_v[:, 0] * axis_v[:, 0] + axis_v[:, 1] * axis_v[:, 1])
+		axis = (axis_v / axis_len[:, None]).contiguous()
+		if ellipticity == "distortion":
+			e = (1 - q * q) / (1 + q * q)
+		elif ellipticity == "ellipticity":
+			e = (1 - q) / (1 + q)
+		else:
+			raise ValueError("Invalid value for ellipticity. Choose 'distortion' or 'ellipticity'.")
+		num_box = L_subboxes ** 3 if L_subboxes else 0
+
+		def labels(p):
+			n = int(L_subboxes)
+			bounds = torch.from_numpy(np.arange(0, n + 1) * (self.L_0p5 * 2.0 / n)).to(dev)  # i * L_sub, as the reference
+			inside = torch.ones(p.shape[0], dtype=torch.bool, device=dev)
+			lab = torch.zeros(p.shape[0], dtype=torch.int64, device=dev)
+			for dim in range(3):
+				x = p[:, dim].contiguous()
+				i = torch.bucketize(x, bounds, right=True) - 1
+				ic = i.clamp(0, n - 1)
+				inside &= (i >= 0) & (i < n) & (x > bounds[ic]) & (x < bounds[ic + 1])
+				lab = lab * n + ic
+			return torch.where(inside, lab, torch.zeros_like(lab)).to(torch.int32)
+
+		jk_p = jk_s = None
+		t = w_s * (1 - e * e / 2.0)
+		R = float((t.sum() / w_s.sum()).item()) if t.numel() else float("nan")
+		R_jk = n_p_k = n_s_k = None
+		if num_box:
+			jk_p = labels(pos)
+			jk_s = jk_p if same else labels(pos_s)
+			js = jk_s.to(torch.int64)
+			tk = torch.zeros(num_box, dtype=f64, device=dev).index_add_(0, js, t)
+			wk = torch.zeros(num_box, dtype=f64, device=dev).index_add_(0, js, w_s)
+			tk, wk = tk.cpu().numpy(), wk.cpu().numpy()
+			R_jk = np.empty(num_box)
+			with np.errstate(invalid="ignore", divide="ignore"):
+				for k in range(num_box):
+					R_jk[k] = np.delete(tk, k).sum() / np.delete(wk, k).sum()
+			n_p_k = pos.shape[0] - torch.bincount(jk_p.to(torch.int64), minlength=num_box).cpu().numpy()
+			n_s_k = pos_s.shape[0] - torch.bincount(js, minlength=num_box).cpu().numpy()
+		unit_p = bool((w == 1.0).all().item())
+		unit_s = unit_p if same else bool((w_s == 1.0).all().item())
+		return dict(pos=pos.contiguous(), pos_s=pos_s.contiguous(), axis=axis, e=e.contiguous(),
+					w=None if unit_p else w.contiguous(), w_s=None if unit_s else w_s.contiguous(), jk_p=jk_p, jk_s=jk_s,
+					same=same, R=R, R_jk=R_jk, n_p_k=n_p_k, n_s_k=n_s_k, Np=int(pos.shape[0]), Ns=int(pos_s.shape[0]))
+
 	# ---- the pair loop: ONE operator call replaces the reference's twelve variants -----------------------------------------
 	def _pair_sums(self, geom, masks, L_subboxes, ellipticity, rp_cut=None):
 		import torch
@@ -358,45 +438,25 @@ class MeasureIABox(MeasureIABase):
 		from . import ops
 
 		t0 = time.perf_counter()
-		pos, pos_s, axis, e, w, w_s, same = self._prepare(masks, ellipticity)
-		num_box = L_subboxes ** 3 if L_subboxes else 0
-		jk_p = jk_s = None
-		if num_box:
-			jk_p = self._jackknife_labels(pos, L_subboxes)
-			jk_s = jk_p if same else self._jackknife_labels(pos_s, L_subboxes)
-		R, R_jk = self._responsivity(w_s, e, jk_s, num_box)
-		r2_thr, thr2, rp2_cut, clean = self._thresholds_for(geom, rp_cut)
+		if ellipticity not in ("distortion", "ellipticity"):
+			raise ValueError("Invalid value for ellipticity. Choose 'distortion' or 'ellipticity'.")
 		if not torch.cuda.is_available():
 			raise RuntimeError("measure_ia_b200 needs a CUDA device: the pair-count operator has no CPU fallback")
 		dev = torch.device(self.device) if self.device is not None else torch.device("cuda", torch.cuda.current_device())
+		num_box = L_subboxes ** 3 if L_subboxes else 0
+		r2_thr, thr2, rp2_cut, clean = self._thresholds_for(geom, rp_cut)
+		P = self._prepare_device(masks, ellipticity, L_subboxes, dev)
+		torch.cuda.synchronize(dev)
 		t1 = time.perf_counter()
-
-		def up(a, dtype=None):
-			if a is None:
-				return None
-			t = torch.from_numpy(np.ascontiguousarray(a))
-			if dtype is not None:
-				t = t.to(dtype)
-			return t.to(dev, non_blocking=False)
-
-		unit_p, unit_s = bool(np.all(w == 1.0)), bool(np.all(w_s == 1.0))
-		d_pos = up(pos)
-		d_w = None if unit_p else up(w)
-		d_jk = up(jk_p, torch.int32)
-		if same:
-			d_pos_s, d_w_s, d_jk_s = d_pos, d_w, d_jk
-		else:
-			d_pos_s, d_w_s, d_jk_s = up(pos_s), (None if unit_s else up(w_s)), up(jk_s, torch.int32)
-		d_axis, d_e = up(axis), up(e)
 
 		rank, world = 0, 1
 		if torch.distributed.is_available() and torch.distributed.is_initialized():
 			rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
 		kernel = ops.KERNEL_NAMES[self.kernel]
 		out = torch.ops.measure_ia_b200.paircount(
-			d_pos, d_w, d_jk, d_pos_s, d_w_s, d_jk_s, d_axis, d_e, torch.from_numpy(r2_thr), torch.from_numpy(thr2),
-			ops.GEOM_RPPI if geom == "rppi" else ops.GEOM_RMU, int(self.data["LOS"]), bool(self.periodicity), num_box,
-			float(self.boxsize), float(self.r_bins[-1]), float(rp2_cut), kernel, rank, world)
+			P["pos"], P["w"], P["jk_p"], P["pos_s"], P["w_s"], P["jk_s"], P["axis"], P["e"], torch.from_numpy(r2_thr),
+			torch.from_numpy(thr2), ops.GEOM_RPPI if geom == "rppi" else ops.GEOM_RMU, int(self.data["LOS"]),
+			bool(self.periodicity), num_box, float(self.boxsize), float(self.r_bins[-1]), float(rp2_cut), kernel, rank, world)
 		dd_count, dd_w, spd, scd, jk_count, jk_w, spd_jk, stats = out
 		if world > 1:
 			dd_count, dd_w, spd, scd, jk_count, jk_w, spd_jk, stats = combine_across_ranks(
@@ -405,11 +465,13 @@ class MeasureIABox(MeasureIABase):
 		t2 = time.perf_counter()
 		res = dict(count=dd_count.cpu().numpy(), DD=dd_w.cpu().numpy(), SpD_raw=spd.cpu().numpy(),
 				   ScD_raw=scd.cpu().numpy(), count_jk=jk_count.cpu().numpy(), DD_jk=jk_w.cpu().numpy(),
-				   SpD_jk=spd_jk.cpu().numpy(), R=R, R_jk=R_jk, jk_p=jk_p, jk_s=jk_s, Np=len(pos), Ns=len(pos_s))
+				   SpD_jk=spd_jk.cpu().numpy(), R=P["R"], R_jk=P["R_jk"], n_p_k=P["n_p_k"], n_s_k=P["n_s_k"], Np=P["Np"],
+				   Ns=P["Ns"])
 		st = stats.cpu().numpy()
 		self.last_stats = dict(tested=int(st[0]), binned=int(st[1]), nan_rule=int(st[2]), kernel=int(st[4]),
-							   cells=int(st[5]), tasks=int(st[6]), thresholds_clean=bool(clean), rank=rank, world=world,
-							   t_prep=t1 - t0, t_device=t2 - t1)
+							   cells=int(st[5]), tasks=int(st[6]), launches=int(st[7]), thresholds_clean=bool(clean),
+							   rank=rank, world=world, t_prep=t1 - t0, t_device=t2 - t1,
+							   phases_ms=dict(zip(("build", "pairs", "reduce", "total"), ops.LAST_TIMINGS_MS)))
 		return res
 
 	# ---- results -> the reference's HDF5 layout (measure_w_box_jk.py:498-539, measure_w_box.py:387-407) ------------------
@@ -471,8 +533,11 @@ class MeasureIABox(MeasureIABase):
 				if num_box:
 					R_jk = res["R_jk"]
 					vol_jk = L3 * (num_box - 1) / num_box
-					n_p_k = res["Np"] - np.bincount(res["jk_p"], minlength=num_box)
-					n_s_k = res["Ns"] - np.bincount(res["jk_s"], minlength=num_box)
+					if res.get("n_p_k") is not None:
+						n_p_k, n_s_k = res["n_p_k"], res["n_s_k"]
+					else:
+						n_p_k = res["Np"] - np.bincount(res["jk_p"], minlength=num_box)
+						n_s_k = res["Ns"] - np.bincount(res["jk_s"], minlength=num_box)
 					gp = create_group_hdf5(f, f"{snap}/{top}/xi_g_plus/{jk_group_name}")
 					gg = create_group_hdf5(f, f"{snap}/{top}/xi_gg/{jk_group_name}")
 					for i in range(num_box):

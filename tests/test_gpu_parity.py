@@ -206,3 +206,35 @@ def test_empty_and_tiny_inputs(torch_cuda, oracle, tmp_path):
 			run("All", "both", 8, temp_file_path=False)
 			want = oracle.measure(data, kind, num_jk=8, boxsize=50.0, num_bins_r=4, num_bins_pi=4)
 			assert np.array_equal(box.last_result["count"], want["__meta__/count"])
+
+
+def test_device_preparation_matches_host(torch_cuda):
+	"""The torch/GPU input preparation (box._prepare_device) against the numpy restatement of the reference's host code
+	(box._prepare, _jackknife_labels, _responsivity): labels, axis and e bit-identical, responsivities to rounding."""
+	import torch
+	from measure_ia_b200 import MeasureIABox
+	from measure_ia_b200.synthetic import uniform_box
+	data = uniform_box(50000, 90.0, seed=17, n_shape=30000, weights=True)
+	data["Position"][:40, 0] = 30.0  # points exactly on jackknife faces keep label 0
+	data["Position"][40:60, 2] = 0.0
+	data["Position_shape_sample"][:25, 1] = 60.0
+	rng = np.random.default_rng(3)
+	masks = {"Position": rng.random(50000) < 0.8, "Position_shape_sample": rng.random(30000) < 0.7}
+	masks["Axis_Direction"] = masks["q"] = masks["Position_shape_sample"]
+	for use_masks in (None, masks):
+		box = MeasureIABox(data, None, boxsize=90.0)
+		m_host = None if use_masks is None else dict(use_masks)
+		m_dev = None if use_masks is None else dict(use_masks)
+		pos, pos_s, axis, e, w, w_s, same = box._prepare(m_host, "distortion")
+		jk_p, jk_s = box._jackknife_labels(pos, 3), box._jackknife_labels(pos_s, 3)
+		R, R_jk = box._responsivity(w_s, e, jk_s, 27)
+		P = box._prepare_device(m_dev, "distortion", 3, torch.device("cuda", 0))
+		assert np.array_equal(P["pos"].cpu().numpy(), pos) and np.array_equal(P["pos_s"].cpu().numpy(), pos_s)
+		assert np.array_equal(P["axis"].cpu().numpy(), axis) and np.array_equal(P["e"].cpu().numpy(), e)
+		assert np.array_equal(P["w"].cpu().numpy(), w) and np.array_equal(P["w_s"].cpu().numpy(), w_s)
+		assert np.array_equal(P["jk_p"].cpu().numpy(), jk_p) and np.array_equal(P["jk_s"].cpu().numpy(), jk_s)
+		assert (jk_p[:40] == 0).all() or use_masks is not None
+		np.testing.assert_allclose(P["R"], R, rtol=1e-13)
+		np.testing.assert_allclose(P["R_jk"], R_jk, rtol=1e-13)
+		assert np.array_equal(P["n_p_k"], len(pos) - np.bincount(jk_p, minlength=27))
+		assert np.array_equal(P["n_s_k"], len(pos_s) - np.bincount(jk_s, minlength=27))
