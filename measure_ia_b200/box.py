@@ -416,13 +416,14 @@ class MeasureIABox(MeasureIABase):
 			jk_p = labels(pos)
 			jk_s = jk_p if same else labels(pos_s)
 			js = jk_s.to(torch.int64)
-			tk = torch.zeros(num_box, dtype=f64, device=dev).index_add_(0, js, t)
-			wk = torch.zeros(num_box, dtype=f64, device=dev).index_add_(0, js, w_s)
-			tk, wk = tk.cpu().numpy(), wk.cpu().numpy()
-			R_jk = np.empty(num_box)
+			# per realisation: the same ratio over the shapes NOT in region k (measure_w_box_jk.py:463-466).  Masked
+			# torch.sum calls (fixed reduction tree) instead of index_add_/bincount-with-weights, whose atomics would make
+			# the last bit of R_jk vary from run to run
+			zero = torch.zeros((), dtype=f64, device=dev)
+			num = torch.stack([torch.where(js != k, t, zero).sum() for k in range(num_box)])
+			den = torch.stack([torch.where(js != k, w_s, zero).sum() for k in range(num_box)])
 			with np.errstate(invalid="ignore", divide="ignore"):
-				for k in range(num_box):
-					R_jk[k] = np.delete(tk, k).sum() / np.delete(wk, k).sum()
+				R_jk = num.cpu().numpy() / den.cpu().numpy()
 			n_p_k = pos.shape[0] - torch.bincount(jk_p.to(torch.int64), minlength=num_box).cpu().numpy()
 			n_s_k = pos_s.shape[0] - torch.bincount(js, minlength=num_box).cpu().numpy()
 		unit_p = bool((w == 1.0).all().item())

@@ -238,3 +238,37 @@ def test_device_preparation_matches_host(torch_cuda):
 		np.testing.assert_allclose(P["R_jk"], R_jk, rtol=1e-13)
 		assert np.array_equal(P["n_p_k"], len(pos) - np.bincount(jk_p, minlength=27))
 		assert np.array_equal(P["n_s_k"], len(pos_s) - np.bincount(jk_s, minlength=27))
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_clustered_weighted_default_bins_vs_oracle(torch_cuda, oracle, tmp_path, kernel):
+	"""Constructor-default 8 x 20 bins, half of the galaxies in Gaussian blobs (load balance, dense cells that split into
+	many chunks), weights, cross-correlation of two different samples, 64 jackknife regions."""
+	from measure_ia_b200 import MeasureIABox
+	from measure_ia_b200.synthetic import uniform_box
+	data = uniform_box(120000, 300.0, seed=55, n_shape=60000, weights=True, clustered=0.5)
+	out = str(tmp_path / "c.hdf5")
+	box = MeasureIABox(data, out, boxsize=300.0)
+	box.kernel = kernel
+	box.measure_xi_w("All", "both", num_jk=64, temp_file_path=False)
+	want = oracle.measure(data, "w", num_jk=64, boxsize=300.0, n_threads=oracle.max_threads())
+	count = want.pop("__meta__/count")
+	want.pop("__meta__/n_tested")
+	assert np.array_equal(box.last_result["count"], count)
+	pu.assert_datasets_match(read_all(out), want, exact_counts=False, label=f"clustered[{kernel}]: ")
+	if kernel == "auto":
+		assert box.last_stats["kernel"] == 2
+
+
+def test_tiled_kernel_is_bit_reproducible(torch_cuda):
+	"""Two runs of the tiled kernel give identical bits for every fp64 sum (fixed accumulation order)."""
+	from measure_ia_b200 import MeasureIABox
+	from measure_ia_b200.synthetic import uniform_box
+	data = uniform_box(60000, 205.0, seed=61, weights=True)
+	box = MeasureIABox(data, None, boxsize=205.0, num_bins_r=10, num_bins_pi=8)
+	box.kernel = "tiled"
+	box.measure_xi_w("a", "both", 27, temp_file_path=False)
+	first = {k: np.array(v) for k, v in box.last_result.items() if isinstance(v, np.ndarray)}
+	box.measure_xi_w("a", "both", 27, temp_file_path=False)
+	for k, v in first.items():
+		assert np.array_equal(v, box.last_result[k]), k
