@@ -191,6 +191,12 @@ def main():
 	if world > 1:
 		dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
 	total_ms = float(t_total.item())
+	per_rank = torch.tensor([sum(step_ms) / args.steps, sum(kernel_ms) / len(kernel_ms)], dtype=torch.float64, device=dev)
+	if world > 1:
+		allr = torch.empty(world * 2, dtype=torch.float64, device=dev)
+		dist.all_gather_into_tensor(allr, per_rank)
+		per_rank = allr
+	per_rank = per_rank.view(-1, 2).cpu().tolist()
 	dd_count, stats = out[0], out[7]
 	pairs = int(dd_count.sum().item())
 	tested = int(stats[0].item())
@@ -208,6 +214,7 @@ def main():
 				   "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA events)",
 				   "wall_s_timed_region": wall, "thresholds_clean": bool(clean)},
 		"gpu_launches": int(stats[7].item()) * args.steps,
+		"per_rank_ms": [{"step": a, "pair_kernel": b} for a, b in per_rank],
 		"phases_ms": {"cell_list_build": sum(build_ms) / len(build_ms), "pair_kernel": sum(kernel_ms) / len(kernel_ms),
 					  "reductions": sum(reduce_ms) / len(reduce_ms)},
 	}

@@ -5,11 +5,12 @@ Drop-in for ``measureia.MeasureIABox.measure_xi_w`` / ``measure_xi_multipoles`` 
 the pair-count ops, so that the light-weight pieces (``h5lite``, ``SimInfo``, ``synthetic``) import anywhere.
 """
 
-__all__ = ["MeasureIABox", "MeasureIABase", "SimInfo", "ReadData", "write_dataset_hdf5", "create_group_hdf5"]
+__all__ = ["MeasureIABox", "MeasureIABase", "MeasureJackknife", "SimInfo", "ReadData", "write_dataset_hdf5",
+		   "create_group_hdf5"]
 
 
 def __getattr__(name):
-	if name in ("MeasureIABox", "MeasureIABase"):
+	if name in ("MeasureIABox", "MeasureIABase", "MeasureJackknife"):
 		from . import box
 		return getattr(box, name)
 	if name == "SimInfo":

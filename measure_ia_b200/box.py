@@ -21,6 +21,7 @@ import numpy as np
 
 from . import calib
 from .io import create_group_hdf5, open_file, write_dataset_hdf5
+from .jackknife import JackknifeCombinationMixin
 from .sim_info import SimInfo
 
 
@@ -272,7 +273,12 @@ class MeasureIABase(SimInfo):
 			return covs, stds
 
 
-class MeasureIABox(MeasureIABase):
+class MeasureJackknife(MeasureIABase, JackknifeCombinationMixin):
+	"""Covariance combination on an existing output file: ``MeasureJackknife(None, out.hdf5, ...)`` as in the reference
+	(measure_jackknife.py:33-57).  Only the periodic-box combination methods are provided (light-cone jackknife: out of scope)."""
+
+
+class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 	"""Drop-in for ``measureia.MeasureIABox`` (measure_IA.py:10-262) running the pair loop on a B200."""
 
 	def __init__(self, data, output_file_name, simulation=None, snapshot=None, separation_limits=[0.1, 20.0],

@@ -212,42 +212,68 @@ class Group:
 		return f'<h5lite group "{self.name}" ({len(self._children)} members)>'
 
 
+_OPEN_FILES = {}  # realpath -> shared state of every handle currently open on that file in this process
+
+
 class File(Group):
-	"""``h5lite.File(name, mode)`` with modes 'r', 'r+', 'a', 'w' (h5py semantics)."""
+	"""``h5lite.File(name, mode)`` with modes 'r', 'r+', 'a', 'w' (h5py semantics).
+
+	Handles opened on the same path share one in-memory tree (as handles of one process share one file in libhdf5), so a
+	handle that is never closed -- the reference leaks one in ``measure_jackknife.py:603`` -- cannot overwrite later
+	changes with a stale copy when it is finally collected."""
 
 	def __init__(self, filename, mode="r"):
 		super().__init__("/", None)
 		self.filename = str(filename)
 		self.mode = mode
-		self._dirty = False
 		self._open = True
+		key = os.path.realpath(self.filename)
 		exists = os.path.exists(self.filename)
-		if mode in ("r", "r+") and not exists:
+		if mode in ("r", "r+") and not exists and key not in _OPEN_FILES:
 			raise FileNotFoundError(f"Unable to open file (unable to open file: name = '{self.filename}')")
 		if mode == "w-" and exists:
 			raise FileExistsError(self.filename)
-		if mode in ("r", "r+", "a") and exists and os.path.getsize(self.filename) > 0:
-			with open(self.filename, "rb") as fh:
-				_Reader(fh.read()).read_into(self)
-			self._dirty = False
-		elif mode in ("w", "w-", "a", "x"):
-			self._dirty = True  # a new (possibly empty) file must still be written
-		else:
+		if mode not in ("r", "r+", "a", "w", "w-", "x"):
 			raise ValueError(f"invalid mode {mode!r}")
+		shared = _OPEN_FILES.get(key)
+		if shared is not None and mode in ("r", "r+", "a"):
+			self._shared = shared
+			self._children = shared["children"]
+			shared["open"] += 1
+		else:
+			self._shared = {"children": self._children, "dirty": False, "open": 1, "key": key}
+			_OPEN_FILES[key] = self._shared
+			if mode in ("r", "r+", "a") and exists and os.path.getsize(self.filename) > 0:
+				with open(self.filename, "rb") as fh:
+					_Reader(fh.read()).read_into(self)
+				self._shared["dirty"] = False
+			else:
+				self._shared["dirty"] = True  # a new (possibly empty) file must still be written
+
+	@property
+	def _dirty(self):
+		return self._shared["dirty"]
+
+	@_dirty.setter
+	def _dirty(self, value):
+		self._shared["dirty"] = value
 
 	def flush(self):
-		if self.mode != "r" and self._dirty:
+		if self._shared["dirty"] and (self.mode != "r" or self._shared["open"] > 1):
 			blob = _Writer().serialise(self)
 			tmp = self.filename + ".h5lite.tmp"
 			with open(tmp, "wb") as fh:
 				fh.write(blob)
 			os.replace(tmp, self.filename)
-			self._dirty = False
+			self._shared["dirty"] = False
 
 	def close(self):
 		if self._open:
 			self.flush()
 			self._open = False
+			self._shared["open"] -= 1
+			if self._shared["open"] <= 0 and _OPEN_FILES.get(self._shared["key"]) is self._shared:
+				del _OPEN_FILES[self._shared["key"]]
 
 	def __enter__(self):
 		return self

@@ -103,6 +103,41 @@ def generate(name):
 		  f"({os.path.getsize(path) // 1024} KiB)")
 
 
+def generate_covariance_fixture():
+	"""BASELINE.json config 5 post-step: three projections of one box (dataset names LOS_x / LOS_y / LOS_z), jackknife
+	realisations by the reference's measure_xi_w / measure_xi_multipoles, then the unmodified
+	MeasureJackknife.create_full_cov_matrix_projections / measure_covariance_multiple_datasets on the same file."""
+	import tempfile
+	from measure_ia_b200 import h5lite
+	measureia = run_reference.load_reference()
+	tmp = tempfile.mkdtemp(prefix="mia_cov_")
+	out = os.path.join(tmp, "cov.hdf5")
+	devnull, stdout = open(os.devnull, "w"), sys.stdout
+	sys.stdout = devnull
+	try:
+		for los, name in enumerate(("LOS_x", "LOS_y", "LOS_z")):
+			data = uniform_box(1500, 100.0, seed=40 + los, los=los)
+			box = measureia.MeasureIABox(data, out, None, 7, [0.5, 15.0], 5, 6, None, 100.0, True, 1)
+			box.measure_xi_w(name, "both", num_jk=8, temp_file_path=tmp + "/")
+			box.measure_xi_multipoles(name, "both", num_jk=8, temp_file_path=tmp + "/")
+		jk = measureia.MeasureJackknife(None, out, None, 7, [0.5, 15.0], 5, 6, None, 100.0)
+		for corr in ("w_g_plus", "w_gg", "multipoles_g_plus", "multipoles_gg"):
+			jk.create_full_cov_matrix_projections(corr, ["LOS_x", "LOS_y", "LOS_z"], num_box=8)
+	finally:
+		sys.stdout = stdout
+		devnull.close()
+	# the reference never closes the handle it opened in create_full_cov_matrix_projections (:603); flush it
+	import gc
+	gc.collect()
+	f = h5lite.File(out, "r")
+	flat = run_reference._flatten(f)
+	f.close()
+	keep = {k: v for k, v in flat.items() if k.split("/")[1] in ("w_g_plus", "w_gg", "multipoles_g_plus", "multipoles_gg")}
+	path = os.path.join(GOLDEN, "cov_projections.npz")
+	np.savez_compressed(path, **{k.replace("/", "|"): v for k, v in keep.items()})
+	print(f"covariance fixture: {len(keep)} datasets -> {os.path.relpath(path, _REPO)} ({os.path.getsize(path) // 1024} KiB)")
+
+
 def decode_reference_hdf5():
 	from measure_ia_b200 import h5lite
 	src = "/root/reference/tests/data/processed/TNG300"
@@ -117,9 +152,11 @@ def decode_reference_hdf5():
 
 if __name__ == "__main__":
 	os.makedirs(GOLDEN, exist_ok=True)
-	names = sys.argv[1:] or list(CONFIGS) + ["hdf5"]
+	names = sys.argv[1:] or list(CONFIGS) + ["hdf5", "cov"]
 	for n in names:
 		if n == "hdf5":
 			decode_reference_hdf5()
+		elif n == "cov":
+			generate_covariance_fixture()
 		else:
 			generate(n)
