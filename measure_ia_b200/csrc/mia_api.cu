@@ -81,7 +81,7 @@ int make_plan(const mia_params *p, int64_t nD, int64_t nS, Plan &pl) {
 	} else {
 		pl.n_partials = pl.tiled.n_partials;
 	}
-	const uint64_t nkeys = (uint64_t)pl.g.ncell() * (uint64_t)J;
+	const uint64_t nkeys = (uint64_t)pl.g.ncell() * 4ull * (uint64_t)J;  // x4: the shape sample's sub-cell ordering
 	if (nkeys > (1ull << 31)) return MIA_ERR_UNSUPPORTED;
 	pl.key_bits = ilog2_ceil(nkeys > 1 ? nkeys : 2);
 	const int64_t nmax = nD > nS ? nD : nS;
@@ -97,7 +97,7 @@ int make_plan(const mia_params *p, int64_t nD, int64_t nS, Plan &pl) {
 	pl.off_cand_jk = take(sizeof(int32_t) * (size_t)nD);
 	pl.off_prim = take(sizeof(Prim) * (size_t)nS);
 	pl.off_cell_start = take(sizeof(int64_t) * (size_t)(pl.g.ncell() + 1));
-	pl.off_prim_cell_start = take(sizeof(int64_t) * (size_t)(pl.g.ncell() + 1));
+	pl.off_prim_cell_start = take(sizeof(int64_t) * (size_t)(pl.g.ncell() * 4 + 1));
 	pl.off_keys_in = take(sizeof(uint32_t) * (size_t)nmax);
 	pl.off_keys_out = take(sizeof(uint32_t) * (size_t)nmax);
 	pl.off_idx_in = take(sizeof(int32_t) * (size_t)nmax);
@@ -312,13 +312,16 @@ int mia_paircount(const mia_params *params, const mia_sample *D, const mia_sampl
 		if (rc) return rc;
 	}
 	// ---- shape sample -> sorted primaries ---------------------------------------------------------------------------
-	rc = sort_by_cell(S->pos, S->jk, nS, nl0, nl1, los, pl.g, params->boxsize, sc, pl.key_bits, flags, st);
+	GridDims g_prim = pl.g;
+	g_prim.sub = (pl.kernel == MIA_KERNEL_TILED) ? 2 : 1;
+	rc = sort_by_cell(S->pos, S->jk, nS, nl0, nl1, los, g_prim, params->boxsize, sc, pl.key_bits, flags, st);
 	if (rc) return rc;
 	if (nS > 0) {
 		k_gather_prim<<<(unsigned)((nS + T - 1) / T), T, 0, st>>>(S->pos, S->weight, S->jk, S->axis, S->e, sc.idx_out, nS,
 																   nl0, nl1, los, prim);
 	}
-	k_cell_start<<<(unsigned)((nS + 1 + T - 1) / T), T, 0, st>>>(sc.keys_out, nS, pl.g.jk_rows, ncell, prim_cell_start);
+	k_cell_start<<<(unsigned)((nS + 1 + T - 1) / T), T, 0, st>>>(sc.keys_out, nS, pl.g.jk_rows, g_prim.nsorted_cells(),
+																 prim_cell_start);
 	MIA_CUDA_CHECK(cudaGetLastError());
 
 	n_launches += (nD > 0 ? 2 : 0) + (nS > 0 ? 2 : 0) + 2;  // make_keys, gather (x2 samples) + 2 x cell_start
@@ -355,7 +358,7 @@ int mia_paircount(const mia_params *params, const mia_sample *D, const mia_sampl
 		if (timed) MIA_CUDA_CHECK(cudaEventRecord(ev[2], st));
 	} else {
 		const bool unit_w = (D->weight == nullptr && S->weight == nullptr);
-		rc = tiled_launch(pl.tiled, pl.g, P, G, prim, prim_cell_start, nS, unit_w, shard, A, ws + pl.off_tiled, flags, st,
+		rc = tiled_launch(pl.tiled, g_prim, P, G, prim, prim_cell_start, nS, unit_w, shard, A, ws + pl.off_tiled, flags, st,
 						  timed ? ev[1] : nullptr, timed ? ev[2] : nullptr);
 		if (rc) return rc;
 		n_launches += 1 /* cell_info */ + 2 /* col_chunks, fill_tasks */ + 1 /* pair kernel */ + 1 /* reduce_partials */;

@@ -18,7 +18,9 @@ struct GridDims {
 	int ncu, ncv, ncl;
 	double inv_cu, inv_cv, inv_cl;
 	int jk_rows;  // max(num_jk, 1)
+	int sub;      // shape sample only: each cell's galaxies are ordered by sub x sub projected sub-cell (compact warps)
 	int64_t ncell() const { return (int64_t)ncu * ncv * ncl; }
+	int64_t nsorted_cells() const { return ncell() * (sub > 1 ? sub * sub : 1); }
 };
 
 __global__ void k_make_keys(const double *__restrict__ pos, const int32_t *__restrict__ jk, int64_t n, int nl0, int nl1,
@@ -31,6 +33,12 @@ __global__ void k_make_keys(const double *__restrict__ pos, const int32_t *__res
 	if (!(u >= 0.0 && u < L && v >= 0.0 && v < L && l >= 0.0 && l < L)) atomicExch(range_err, 1);
 	int cu = cell_index(u, g.inv_cu, g.ncu), cv = cell_index(v, g.inv_cv, g.ncv), cl = cell_index(l, g.inv_cl, g.ncl);
 	uint32_t cell = (uint32_t)((cu * g.ncv + cv) * g.ncl + cl);
+	if (g.sub > 1) {
+		int su = (int)((u * g.inv_cu - cu) * g.sub), sv = (int)((v * g.inv_cv - cv) * g.sub);
+		su = su < 0 ? 0 : (su >= g.sub ? g.sub - 1 : su);
+		sv = sv < 0 ? 0 : (sv >= g.sub ? g.sub - 1 : sv);
+		cell = cell * (uint32_t)(g.sub * g.sub) + (uint32_t)(su * g.sub + sv);
+	}
 	uint32_t lab = jk ? (uint32_t)jk[i] : 0u;
 	keys[i] = cell * (uint32_t)g.jk_rows + lab;
 	idx[i] = (int32_t)i;

@@ -294,7 +294,7 @@ __global__ void k_cell_info(const Cand *__restrict__ cand, const int32_t *__rest
 	info[c] = ci;
 }
 
-__global__ void k_col_chunks(const int64_t *__restrict__ prim_cell_start, int64_t ncol, int nz,
+__global__ void k_col_chunks(const int64_t *__restrict__ prim_cell_start, int64_t ncol, int nzs,
 							 int32_t *__restrict__ col_chunks) {
 	const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
 	if (c > ncol) return;
@@ -302,7 +302,7 @@ __global__ void k_col_chunks(const int64_t *__restrict__ prim_cell_start, int64_
 		col_chunks[c] = 0;
 		return;
 	}
-	const int64_t n = prim_cell_start[(c + 1) * nz] - prim_cell_start[c * nz];
+	const int64_t n = prim_cell_start[(c + 1) * nzs] - prim_cell_start[c * nzs];  // nzs = cells of the shape sort per column
 	col_chunks[c] = (int32_t)((n + 31) / 32);
 }
 
@@ -313,7 +313,7 @@ __device__ __forceinline__ bool neighbour_offset_ok(int ou, int ov, double cs, d
 
 // One warp task = up to 32 consecutive shape galaxies of one column; cost = shapes x candidates in reach.
 __global__ void k_fill_tasks(const int64_t *__restrict__ prim_cell_start, const int64_t *__restrict__ cell_start,
-							 const int32_t *__restrict__ task_off, int ncu, int ncv, int nz, int k, int periodic,
+							 const int32_t *__restrict__ task_off, int ncu, int ncv, int nz, int nzs, int k, int periodic,
 							 double cs, double reach, int32_t *__restrict__ task_col, int64_t *__restrict__ task_first,
 							 int32_t *__restrict__ task_n, unsigned long long *__restrict__ task_cost,
 							 int32_t *__restrict__ n_tasks) {
@@ -321,7 +321,7 @@ __global__ void k_fill_tasks(const int64_t *__restrict__ prim_cell_start, const 
 	const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
 	if (c == 0) n_tasks[0] = task_off[ncol];
 	if (c >= ncol) return;
-	const int64_t p0 = prim_cell_start[c * nz], p1 = prim_cell_start[(c + 1) * nz];
+	const int64_t p0 = prim_cell_start[c * nzs], p1 = prim_cell_start[(c + 1) * nzs];
 	if (p1 <= p0) return;
 	const int cu = (int)(c / ncv), cv = (int)(c % ncv);
 	const bool all_u = 2 * k + 1 >= ncu, all_v = 2 * k + 1 >= ncv;
@@ -418,7 +418,11 @@ struct ZParams {
 
 struct ZWindow {
 	double t_split, t_lo, t_hi;
-	double shift;  // 0, -L or +L: the periodic image every pair of this lane with this slab takes (when not `gen`)
+	double shift;  // 0, -L or +L: the periodic image every pair of this lane with this slab takes
+	// slab straddling +-L/2 for this lane: a pair takes the image `wadd` iff (d > wthr) != wflip, else `shift` (= 0).
+	// "d < -L/2" is written as !(d > nextbelow(-L/2)), so one comparison serves both directions.
+	double wthr, wadd;
+	bool wflip;
 	int b0, b1;
 	bool gen, dead, err;
 };
@@ -430,6 +434,9 @@ __device__ __noinline__ ZWindow z_window(double pl, double zlo, double zhi, cons
 	w.t_lo = -INFINITY;
 	w.t_hi = INFINITY;
 	w.shift = 0.0;
+	w.wthr = INFINITY;
+	w.wadd = 0.0;
+	w.wflip = false;
 	w.b0 = w.b1 = -1;
 	w.gen = false;
 	w.dead = false;
@@ -470,12 +477,18 @@ __device__ __noinline__ ZWindow z_window(double pl, double zlo, double zhi, cons
 	} else {
 		// part A: values close to +L/2, part B: values close to -L/2 (one of them wrapped)
 		double a_lo, b_hi;
-		if (hi > P.halfL) {
+		if (hi > P.halfL) {  // pairs with d > L/2 wrap down
 			a_lo = lo;
 			b_hi = __dsub_rn(hi, P.L);
-		} else {
+			w.wthr = P.halfL;
+			w.wadd = -P.L;
+			w.wflip = false;
+		} else {  // pairs with d < -L/2 wrap up
 			a_lo = __dadd_rn(lo, P.L);
 			b_hi = hi;
+			w.wthr = __longlong_as_double(__double_as_longlong(-P.halfL) + 1);  // next double below -L/2
+			w.wadd = P.L;
+			w.wflip = true;
 		}
 		const int ea_a = ebin2(a_lo, P.thr2, P.n_2), eb_a = ebin2(P.halfL, P.thr2, P.n_2);
 		const int ea_b = ebin2(-P.halfL, P.thr2, P.n_2), eb_b = ebin2(b_hi, P.thr2, P.n_2);
@@ -572,17 +585,18 @@ struct RWindow {
 	int ra;
 };
 
-// One staged chunk (n <= 32 candidates at shared address cb) against this thread's shape galaxy.
-//   MODE 0 : no pair of the chunk takes a different periodic image than its lane's constant line-of-sight shift
-//            (exactly the reference's `sep -= L` / `sep += L`, measure_w_box_jk.py:403-404), no Pi range edge can be hit
-//   MODE 1 : the line-of-sight separation is wrapped per pair and range-checked (slab straddles +-L/2 or a range edge)
-//   MODE 2 : all three separations are wrapped per pair (the column pair crosses the periodic boundary)
+// One staged chunk (n candidates at shared address cb) against this thread's shape galaxy.
+//   XYS : the projected separations take the lane-constant periodic image (su, sv) (column pair across the box edge)
+//   ZW  : the line-of-sight separation is wrapped per pair with the lane's one-sided rule (slab straddling +-L/2) and
+//         range-checked against the Pi axis; otherwise only the lane-constant image shift is added
+//   GEN : everything compared and wrapped per pair (tiny boxes, where a column pair can straddle +-L/2 as well)
+// All of these are exactly the reference's `sep -= L` / `sep += L` (measure_w_box_jk.py:403-404): x + 0.0 == x.
 // Returns true when some candidate has |cos| within 1e-11 of 1 for this lane: those pairs are NOT accumulated here
 // but re-evaluated with the reference's exact operation sequence by slow_pairs() (its NaN rule, :416-417).
-template <bool UNITW, int MODE>
+template <bool UNITW, bool XYS, bool ZW, bool GEN>
 __device__ __forceinline__ bool pair_loop(uint32_t cb, int n, int periodic, double L, double halfL, double pu, double pv,
-										  double pl, double a0, double a1, const RWindow &rw, double hi_lane,
-										  const ZWindow &zw, const PrivAcc &acc) {
+										  double pl, double a0, double a1, double su, double sv, const RWindow &rw,
+										  double hi_lane, const ZWindow &zw, const PrivAcc &acc) {
 	// periodic image of one separation, branch-free and exactly the reference's two conditional shifts (:403-404):
 	// |d| > L/2  =>  d -= copysign(L, d)   (after the first shift the second condition can no longer hold)
 	auto wrap = [&](double d) {
@@ -605,18 +619,23 @@ __device__ __forceinline__ bool pair_loop(uint32_t cb, int n, int periodic, doub
 		lds_v2(nu, nv, na);
 		lds_v2(nl, nw, na + 16);
 		double du = __dsub_rn(pu, cu), dv = __dsub_rn(pv, cv), dz = __dsub_rn(pl, cl);  // shape minus position, :401
-		if (MODE == 2 && periodic) {
-			du = wrap(du);
-			dv = wrap(dv);
-		}
-		if (MODE >= 1) {
-			if (periodic) dz = wrap(dz);
+		if (GEN) {
+			if (periodic) {
+				du = wrap(du);
+				dv = wrap(dv);
+				dz = wrap(dz);
+			}
 		} else {
-			dz = __dadd_rn(dz, zw.shift);
+			if (XYS) {
+				du = __dadd_rn(du, su);
+				dv = __dadd_rn(dv, sv);
+			}
+			if (ZW) dz = __dadd_rn(dz, ((dz > zw.wthr) != zw.wflip) ? zw.wadd : zw.shift);
+			else dz = __dadd_rn(dz, zw.shift);
 		}
 		const double r2 = __dadd_rn(__dmul_rn(du, du), __dmul_rn(dv, dv));  // :407 (before the sqrt)
 		bool ok = (r2 >= rw.lo) && (r2 < hi_lane);
-		if (MODE >= 1) ok = ok && (dz >= zw.t_lo) && (dz < zw.t_hi);
+		if (ZW || GEN) ok = ok && (dz >= zw.t_lo) && (dz < zw.t_hi);
 		int slot = (dz >= zw.t_split) ? 1 : 0;
 #pragma unroll
 		for (int k = 0; k < W_R - 1; k++) slot += (r2 >= rw.thr[k]) ? 2 : 0;
@@ -852,7 +871,7 @@ __device__ __noinline__ int build_neighbour_list(int *nlist, int col, int ncu, i
 struct Chunk {
 	long long start;
 	int n, label;
-	bool xyw;
+	int xy;  // 0: no periodic image in the projected axes, 1: lane-constant image shifts, 2: per-pair wrap needed
 };
 
 template <bool UNITW>
@@ -1008,7 +1027,8 @@ __global__ void __launch_bounds__(TP, MIA_MIN_CTAS) k_tiled_rppi(const TiledArgs
 				double d_umin = 0.0, d_umax = 0.0, d_vmin = 0.0, d_vmax = 0.0;
 				long long g_pos = 0, g_run_end = 0, g_cell_end = 0;
 				int g_label = -1, g_nlab = 1;
-				bool g_xyw = false;
+				int g_xy = 0;
+				double g_su = 0.0, g_sv = 0.0;  // this lane's projected image shifts for the current cell
 				auto next_chunk = [&](Chunk &c) -> bool {
 					for (;;) {
 						if (g_pos < g_run_end) {
@@ -1017,7 +1037,7 @@ __global__ void __launch_bounds__(TP, MIA_MIN_CTAS) k_tiled_rppi(const TiledArgs
 							c.start = g_pos;
 							c.n = (rest + nch - 1) / nch;
 							c.label = g_label;
-							c.xyw = g_xyw;
+							c.xy = g_xy;
 							g_pos += c.n;
 							return true;
 						}
@@ -1055,28 +1075,31 @@ __global__ void __launch_bounds__(TP, MIA_MIN_CTAS) k_tiled_rppi(const TiledArgs
 						// per-warp culling against the cell's bounding box: can any lane have a pair in this window?
 						double ulo = __dsub_rn(p.u, umax), uhi = __dsub_rn(p.u, umin);
 						double vlo = __dsub_rn(p.v, vmax), vhi = __dsub_rn(p.v, vmin);
-						bool xyw = false, nocull = false;
+						bool nocull = false;
+						double su = 0.0, sv = 0.0;
 						if (periodic) {
 							if (!(ulo >= -halfL && uhi <= halfL)) {
-								xyw = true;
-								if (ulo > halfL) {
+								if (ulo > halfL) {  // every pair of this lane with the cell wraps down
 									ulo = __dsub_rn(ulo, L);
 									uhi = __dsub_rn(uhi, L);
+									su = -L;
 								} else if (uhi < -halfL) {
 									ulo = __dadd_rn(ulo, L);
 									uhi = __dadd_rn(uhi, L);
+									su = L;
 								} else {
-									nocull = true;
+									nocull = true;  // the cell straddles +-L/2 for this lane (tiny boxes only)
 								}
 							}
 							if (!(vlo >= -halfL && vhi <= halfL)) {
-								xyw = true;
 								if (vlo > halfL) {
 									vlo = __dsub_rn(vlo, L);
 									vhi = __dsub_rn(vhi, L);
+									sv = -L;
 								} else if (vhi < -halfL) {
 									vlo = __dadd_rn(vlo, L);
 									vhi = __dadd_rn(vhi, L);
+									sv = L;
 								} else {
 									nocull = true;
 								}
@@ -1087,7 +1110,10 @@ __global__ void __launch_bounds__(TP, MIA_MIN_CTAS) k_tiled_rppi(const TiledArgs
 						const double dmin2 = __dadd_rn(__dmul_rn(mu, mu), __dmul_rn(mv, mv));
 						const bool need = !zw.dead && (nocull || dmin2 < win_hi);
 						if (!__any_sync(0xffffffffu, need)) continue;  // never even staged
-						g_xyw = __any_sync(0xffffffffu, !zw.dead && xyw);
+						g_xy = __any_sync(0xffffffffu, !zw.dead && nocull) ? 2
+							   : (__any_sync(0xffffffffu, !zw.dead && (su != 0.0 || sv != 0.0)) ? 1 : 0);
+						g_su = su;
+						g_sv = sv;
 						g_pos = __shfl_sync(0xffffffffu, d_start, e);
 						g_cell_end = g_pos + __shfl_sync(0xffffffffu, d_n, e);
 						g_label = __shfl_sync(0xffffffffu, d_label, e);
@@ -1104,6 +1130,7 @@ __global__ void __launch_bounds__(TP, MIA_MIN_CTAS) k_tiled_rppi(const TiledArgs
 
 				// ---- software pipeline: issue the bulk copy of chunk k+1, then work on chunk k ----------------------------
 				Chunk pend, nxt;
+				double pend_su = 0.0, pend_sv = 0.0, nxt_su = 0.0, nxt_sv = 0.0;  // per-lane image shifts of the chunk's cell
 				pend.n = 0;
 				pend.label = -1;
 				int pend_st = 0, cur_label = -1;
@@ -1113,6 +1140,8 @@ __global__ void __launch_bounds__(TP, MIA_MIN_CTAS) k_tiled_rppi(const TiledArgs
 					if (more) {
 						got = next_chunk(nxt);
 						more = got;
+						nxt_su = g_su;
+						nxt_sv = g_sv;
 					}
 					if (got && lane == 0) {
 						const uint32_t bytes = (uint32_t)nxt.n * (uint32_t)sizeof(Cand);
@@ -1136,12 +1165,21 @@ __global__ void __launch_bounds__(TP, MIA_MIN_CTAS) k_tiled_rppi(const TiledArgs
 						if (!zw.dead) tested += (unsigned long long)pend.n;
 						const uint32_t cb = my_ring_u32 + (uint32_t)pend_st * (uint32_t)(CH * sizeof(Cand));
 						bool susp;
-						if (pend.xyw)
-							susp = pair_loop<UNITW, 2>(cb, pend.n, periodic, L, halfL, p.u, p.v, p.l, p.a0, p.a1, rw, hi_lane, zw, acc);
+						if (pend.xy == 2)  // tiny boxes: a column pair straddles +-L/2
+							susp = pair_loop<UNITW, false, false, true>(cb, pend.n, periodic, L, halfL, p.u, p.v, p.l, p.a0, p.a1, 0.0,
+																		 0.0, rw, hi_lane, zw, acc);
+						else if (pend.xy == 1 && warp_zg)
+							susp = pair_loop<UNITW, true, true, false>(cb, pend.n, periodic, L, halfL, p.u, p.v, p.l, p.a0, p.a1,
+																		pend_su, pend_sv, rw, hi_lane, zw, acc);
+						else if (pend.xy == 1)
+							susp = pair_loop<UNITW, true, false, false>(cb, pend.n, periodic, L, halfL, p.u, p.v, p.l, p.a0, p.a1,
+																		 pend_su, pend_sv, rw, hi_lane, zw, acc);
 						else if (warp_zg)
-							susp = pair_loop<UNITW, 1>(cb, pend.n, periodic, L, halfL, p.u, p.v, p.l, p.a0, p.a1, rw, hi_lane, zw, acc);
-						else  // the common case: no periodic image or range edge inside this chunk
-							susp = pair_loop<UNITW, 0>(cb, pend.n, periodic, L, halfL, p.u, p.v, p.l, p.a0, p.a1, rw, hi_lane, zw, acc);
+							susp = pair_loop<UNITW, false, true, false>(cb, pend.n, periodic, L, halfL, p.u, p.v, p.l, p.a0, p.a1, 0.0,
+																		 0.0, rw, hi_lane, zw, acc);
+						else  // the common case: no periodic image in the projected axes, constant one along the line of sight
+							susp = pair_loop<UNITW, false, false, false>(cb, pend.n, periodic, L, halfL, p.u, p.v, p.l, p.a0, p.a1,
+																		  0.0, 0.0, rw, hi_lane, zw, acc);
 						if (__any_sync(0xffffffffu, susp))
 							slow_pairs<UNITW>(susp, cb, pend.n, periodic, L, halfL, p.u, p.v, p.l, p.a0, p.a1, rw, hi_lane, zw.t_lo,
 											  zw.t_hi, zw.t_split, acc, nan_pairs);
@@ -1149,6 +1187,8 @@ __global__ void __launch_bounds__(TP, MIA_MIN_CTAS) k_tiled_rppi(const TiledArgs
 					}
 					if (got) {
 						pend = nxt;
+						pend_su = nxt_su;
+						pend_sv = nxt_sv;
 						pend_st = st_issue;
 						st_issue ^= 1;
 					} else {
@@ -1204,13 +1244,14 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &g, const DevPara
 	}
 	// ---- task table -------------------------------------------------------------------------------------------------------
 	MIA_CUDA_CHECK(cudaMemsetAsync(w.task_cost, 0, sizeof(unsigned long long) * cfg.max_tasks, st));
-	k_col_chunks<<<(unsigned)((ncol + 1 + 255) / 256), 256, 0, st>>>(prim_cell_start, ncol, cfg.nz, w.col_chunks);
+	const int nzs = cfg.nz * (g.sub > 1 ? g.sub * g.sub : 1);
+	k_col_chunks<<<(unsigned)((ncol + 1 + 255) / 256), 256, 0, st>>>(prim_cell_start, ncol, nzs, w.col_chunks);
 	MIA_CUDA_CHECK(cudaGetLastError());
 	size_t cb = w.cub_bytes;
 	MIA_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, cb, w.col_chunks, w.task_off, (int)(ncol + 1), st));
 	const double cs = P.L / g.ncu, reach = sqrt(P.r2_thr[P.n_r]) * (1.0 + 1e-6);
 	k_fill_tasks<<<(unsigned)((ncol + 255) / 256), 256, 0, st>>>(prim_cell_start, G.cell_start, w.task_off, g.ncu, g.ncv,
-																 cfg.nz, P.ku, P.periodic, cs, reach, w.task_col,
+																 cfg.nz, nzs, P.ku, P.periodic, cs, reach, w.task_col,
 																 w.task_first, w.task_n, w.task_cost, w.n_tasks);
 	MIA_CUDA_CHECK(cudaGetLastError());
 	cb = w.cub_bytes;
