@@ -15,6 +15,8 @@ namespace {
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
+constexpr int RED_GROUPS = 32;  // groups of accumulator copies summed in parallel (stage 1 of the final reduction)
+
 struct Plan {
 	// grid
 	GridDims g;
@@ -27,7 +29,8 @@ struct Plan {
 	TiledConfig tiled;
 	// workspace offsets
 	size_t off_cand, off_cand_jk, off_prim, off_cell_start, off_prim_cell_start, off_keys_in, off_keys_out, off_idx_in,
-		off_idx_out, off_cub, cub_bytes, off_cnt, off_ddw, off_sp, off_sc, off_stats, off_flags, off_tiled, total;
+		off_idx_out, off_cub, cub_bytes, off_red_cnt, off_red_f, off_cnt, off_ddw, off_sp, off_sc, off_stats, off_flags,
+		off_tiled, total;
 };
 
 int ilog2_ceil(uint64_t x) {
@@ -105,6 +108,8 @@ int make_plan(const mia_params *p, int64_t nD, int64_t nS, Plan &pl) {
 	pl.cub_bytes = cub_sort_bytes(nmax > 0 ? nmax : 1);
 	pl.off_cub = take(pl.cub_bytes);
 	const size_t acc = (size_t)pl.n_partials * pl.rows * pl.nb;
+	pl.off_red_cnt = take(pl.n_partials > 1 ? sizeof(unsigned long long) * RED_GROUPS * (size_t)pl.rows * pl.nb : 0);
+	pl.off_red_f = take(pl.n_partials > 1 ? sizeof(double) * 3 * RED_GROUPS * (size_t)pl.rows * pl.nb : 0);
 	pl.off_cnt = take(sizeof(unsigned long long) * acc);
 	pl.off_ddw = take(sizeof(double) * acc);
 	pl.off_sp = take(sizeof(double) * acc);
@@ -178,19 +183,44 @@ __global__ void k_finalize(const unsigned long long *__restrict__ cnt, const dou
 	out.scd[b] = t_sc;
 }
 
-// Sum the accumulator copies (one per warp of the tiled kernel) into copy 0, in copy order: fixed => reproducible.
-__global__ void k_reduce_partials(unsigned long long *__restrict__ cnt, double *__restrict__ ddw, double *__restrict__ sp,
-								  double *__restrict__ sc, int n_partials, size_t n_el) {
+// Sum the accumulator copies (one per worker warp of the tiled kernel) into copy 0 in a fixed order, in two stages:
+// RED_GROUPS consecutive ranges of copies are summed in parallel into a scratch block, then the group sums are added in
+// group order.  Fixed association => reproducible bits.
+__global__ void k_reduce_partials_stage1(const unsigned long long *__restrict__ cnt, const double *__restrict__ ddw,
+										 const double *__restrict__ sp, const double *__restrict__ sc, int n_partials,
+										 size_t n_el, unsigned long long *__restrict__ g_cnt, double *__restrict__ g_f) {
 	const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+	const int g = blockIdx.y;
 	if (e >= n_el) return;
+	const int per = (n_partials + RED_GROUPS - 1) / RED_GROUPS;
+	const int p0 = g * per, p1 = (p0 + per < n_partials) ? p0 + per : n_partials;
 	unsigned long long c = 0;
 	double a = 0.0, b = 0.0, d = 0.0;
-	for (int p = 0; p < n_partials; p++) {
+	for (int p = p0; p < p1; p++) {
 		const size_t i = (size_t)p * n_el + e;
 		c += cnt[i];
 		a += ddw[i];
 		b += sp[i];
 		d += sc[i];
+	}
+	g_cnt[(size_t)g * n_el + e] = c;
+	g_f[((size_t)g * 3 + 0) * n_el + e] = a;
+	g_f[((size_t)g * 3 + 1) * n_el + e] = b;
+	g_f[((size_t)g * 3 + 2) * n_el + e] = d;
+}
+
+__global__ void k_reduce_partials_stage2(unsigned long long *__restrict__ cnt, double *__restrict__ ddw,
+										 double *__restrict__ sp, double *__restrict__ sc, size_t n_el,
+										 const unsigned long long *__restrict__ g_cnt, const double *__restrict__ g_f) {
+	const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+	if (e >= n_el) return;
+	unsigned long long c = 0;
+	double a = 0.0, b = 0.0, d = 0.0;
+	for (int g = 0; g < RED_GROUPS; g++) {
+		c += g_cnt[(size_t)g * n_el + e];
+		a += g_f[((size_t)g * 3 + 0) * n_el + e];
+		b += g_f[((size_t)g * 3 + 1) * n_el + e];
+		d += g_f[((size_t)g * 3 + 2) * n_el + e];
 	}
 	cnt[e] = c;
 	ddw[e] = a;
@@ -361,10 +391,14 @@ int mia_paircount(const mia_params *params, const mia_sample *D, const mia_sampl
 		rc = tiled_launch(pl.tiled, g_prim, P, G, prim, prim_cell_start, nS, unit_w, shard, A, ws + pl.off_tiled, flags, st,
 						  timed ? ev[1] : nullptr, timed ? ev[2] : nullptr);
 		if (rc) return rc;
-		n_launches += 1 /* cell_info */ + 2 /* col_chunks, fill_tasks */ + 1 /* pair kernel */ + 1 /* reduce_partials */;
+		n_launches += 1 /* cell_info */ + 2 /* col_chunks, fill_tasks */ + 1 /* pair kernel */ + 2 /* reduce_partials */;
 		if (pl.n_partials > 1) {
 			const size_t n_el = (size_t)pl.rows * pl.nb;
-			k_reduce_partials<<<(unsigned)((n_el + 127) / 128), 128, 0, st>>>(A.cnt, A.ddw, A.sp, A.sc, pl.n_partials, n_el);
+			unsigned long long *g_cnt = (unsigned long long *)(ws + pl.off_red_cnt);
+			double *g_f = (double *)(ws + pl.off_red_f);
+			const dim3 grid1((unsigned)((n_el + 127) / 128), RED_GROUPS);
+			k_reduce_partials_stage1<<<grid1, 128, 0, st>>>(A.cnt, A.ddw, A.sp, A.sc, pl.n_partials, n_el, g_cnt, g_f);
+			k_reduce_partials_stage2<<<(unsigned)((n_el + 127) / 128), 128, 0, st>>>(A.cnt, A.ddw, A.sp, A.sc, n_el, g_cnt, g_f);
 			MIA_CUDA_CHECK(cudaGetLastError());
 		}
 	}

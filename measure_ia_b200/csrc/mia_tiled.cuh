@@ -55,6 +55,7 @@ constexpr int MAX_NEIGH = 128;   // neighbour columns per task
 constexpr int LUT_SIZE = 256;
 constexpr int W_R = MIA_W_R;     // r bins per accumulation window
 constexpr int NSLOT = 2 * W_R;   // private histogram slots per thread
+constexpr int MAX_SPLIT = 8;     // a warp task may be cut into up to 8 line-of-sight parts when tasks are scarce
 constexpr int SLOTS_PER_SM = 6;  // CTAs launched per SM; fixed, so that results do not depend on occupancy
 
 struct LutEntry {
@@ -91,6 +92,7 @@ struct TiledArgs {
 	const int32_t *task_col;
 	const int64_t *task_first;
 	const int32_t *task_n;
+	const int32_t *task_slab;  // [2 * task]: first and one-past-last slab of the task
 	const unsigned long long *task_cost, *task_cum;
 	const int32_t *n_tasks;
 	const LutEntry *lut;
@@ -199,7 +201,7 @@ inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g,
 	cfg.num_sms = sms;
 	cfg.n_ctas = sms * SLOTS_PER_SM;
 	cfg.n_partials = cfg.n_ctas * TW;
-	cfg.max_tasks = (int)(nS / 32 + (int64_t)nc * nc + 1);
+	cfg.max_tasks = (int)((nS / 32 + (int64_t)nc * nc + 1) * MAX_SPLIT);
 	(void)nD;
 	return true;
 }
@@ -207,7 +209,7 @@ inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g,
 struct TiledWorkspace {
 	CellInfo *cinfo;
 	double *slab_lo, *slab_hi;
-	int32_t *col_chunks, *task_off, *task_col, *task_n, *n_tasks;
+	int32_t *col_chunks, *task_off, *task_col, *task_n, *task_slab, *n_tasks;
 	int64_t *task_first;
 	unsigned long long *task_cost, *task_cum;
 	LutEntry *lut;
@@ -241,6 +243,7 @@ inline TiledWorkspace carve_tiled(const TiledConfig &cfg, const GridDims &g, voi
 	w.task_off = (int32_t *)take(sizeof(int32_t) * (ncol + 1));
 	w.task_col = (int32_t *)take(sizeof(int32_t) * cfg.max_tasks);
 	w.task_n = (int32_t *)take(sizeof(int32_t) * cfg.max_tasks);
+	w.task_slab = (int32_t *)take(sizeof(int32_t) * 2 * cfg.max_tasks);
 	w.n_tasks = (int32_t *)take(sizeof(int32_t) * 4);
 	w.task_first = (int64_t *)take(sizeof(int64_t) * cfg.max_tasks);
 	w.task_cost = (unsigned long long *)take(sizeof(unsigned long long) * cfg.max_tasks);
@@ -294,7 +297,7 @@ __global__ void k_cell_info(const Cand *__restrict__ cand, const int32_t *__rest
 	info[c] = ci;
 }
 
-__global__ void k_col_chunks(const int64_t *__restrict__ prim_cell_start, int64_t ncol, int nzs,
+__global__ void k_col_chunks(const int64_t *__restrict__ prim_cell_start, int64_t ncol, int nzs, int split,
 							 int32_t *__restrict__ col_chunks) {
 	const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
 	if (c > ncol) return;
@@ -303,7 +306,7 @@ __global__ void k_col_chunks(const int64_t *__restrict__ prim_cell_start, int64_
 		return;
 	}
 	const int64_t n = prim_cell_start[(c + 1) * nzs] - prim_cell_start[c * nzs];  // nzs = cells of the shape sort per column
-	col_chunks[c] = (int32_t)((n + 31) / 32);
+	col_chunks[c] = (int32_t)((n + 31) / 32) * split;
 }
 
 __device__ __forceinline__ bool neighbour_offset_ok(int ou, int ov, double cs, double reach) {
@@ -313,10 +316,10 @@ __device__ __forceinline__ bool neighbour_offset_ok(int ou, int ov, double cs, d
 
 // One warp task = up to 32 consecutive shape galaxies of one column; cost = shapes x candidates in reach.
 __global__ void k_fill_tasks(const int64_t *__restrict__ prim_cell_start, const int64_t *__restrict__ cell_start,
-							 const int32_t *__restrict__ task_off, int ncu, int ncv, int nz, int nzs, int k, int periodic,
-							 double cs, double reach, int32_t *__restrict__ task_col, int64_t *__restrict__ task_first,
-							 int32_t *__restrict__ task_n, unsigned long long *__restrict__ task_cost,
-							 int32_t *__restrict__ n_tasks) {
+							 const int32_t *__restrict__ task_off, int ncu, int ncv, int nz, int nzs, int split, int k,
+							 int periodic, double cs, double reach, int32_t *__restrict__ task_col,
+							 int64_t *__restrict__ task_first, int32_t *__restrict__ task_n, int32_t *__restrict__ task_slab,
+							 unsigned long long *__restrict__ task_cost, int32_t *__restrict__ n_tasks) {
 	const int64_t ncol = (int64_t)ncu * ncv;
 	const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
 	if (c == 0) n_tasks[0] = task_off[ncol];
@@ -344,12 +347,16 @@ __global__ void k_fill_tasks(const int64_t *__restrict__ prim_cell_start, const 
 		}
 	}
 	int t = task_off[c];
-	for (int64_t p = p0; p < p1; p += 32, t++) {
+	for (int64_t p = p0; p < p1; p += 32) {
 		const int n = (int)((p1 - p < 32) ? (p1 - p) : 32);
-		task_col[t] = (int32_t)c;
-		task_first[t] = p;
-		task_n[t] = n;
-		task_cost[t] = (unsigned long long)n * W + 1ull;
+		for (int part = 0; part < split; part++, t++) {  // the same 32 shapes against consecutive ranges of slabs
+			task_col[t] = (int32_t)c;
+			task_first[t] = p;
+			task_n[t] = n;
+			task_slab[2 * t] = (int)((long long)nz * part / split);
+			task_slab[2 * t + 1] = (int)((long long)nz * (part + 1) / split);
+			task_cost[t] = (unsigned long long)n * W / (unsigned long long)split + 1ull;
+		}
 	}
 }
 
@@ -990,7 +997,8 @@ __global__ void __launch_bounds__(TP, MIA_MIN_CTAS) k_tiled_rppi(const TiledArgs
 		// ---- neighbour columns of this task (ordered by jackknife (u, v) region) -----------------------------------
 		const int nn = build_neighbour_list(nlist, col, P.ncu, P.ncv, P.ku, P.kv, periodic, a.n_side, cs, reach);
 
-		for (int s = 0; s < a.nz; s++) {
+		const int slab0 = a.task_slab[2 * task], slab1 = a.task_slab[2 * task + 1];
+		for (int s = slab0; s < slab1; s++) {
 			const double zlo = a.slab_lo[s], zhi = a.slab_hi[s];
 			if (!(zlo <= zhi)) continue;  // empty slab (uniform branch)
 
@@ -1245,14 +1253,20 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &g, const DevPara
 	// ---- task table -------------------------------------------------------------------------------------------------------
 	MIA_CUDA_CHECK(cudaMemsetAsync(w.task_cost, 0, sizeof(unsigned long long) * cfg.max_tasks, st));
 	const int nzs = cfg.nz * (g.sub > 1 ? g.sub * g.sub : 1);
-	k_col_chunks<<<(unsigned)((ncol + 1 + 255) / 256), 256, 0, st>>>(prim_cell_start, ncol, nzs, w.col_chunks);
+	// when there are few tasks per worker warp (small catalogues, many GPUs) cut each task along the line of sight
+	const double tasks_est = (double)nS / 32.0 + 0.5 * (double)ncol;
+	const double want = 8.0 * (double)cfg.n_ctas * TW * (double)shard.count;
+	int split = (int)ceil(want / (tasks_est > 1.0 ? tasks_est : 1.0));
+	split = split < 1 ? 1 : (split > MAX_SPLIT ? MAX_SPLIT : split);
+	if (split > cfg.nz) split = cfg.nz;
+	k_col_chunks<<<(unsigned)((ncol + 1 + 255) / 256), 256, 0, st>>>(prim_cell_start, ncol, nzs, split, w.col_chunks);
 	MIA_CUDA_CHECK(cudaGetLastError());
 	size_t cb = w.cub_bytes;
 	MIA_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, cb, w.col_chunks, w.task_off, (int)(ncol + 1), st));
 	const double cs = P.L / g.ncu, reach = sqrt(P.r2_thr[P.n_r]) * (1.0 + 1e-6);
 	k_fill_tasks<<<(unsigned)((ncol + 255) / 256), 256, 0, st>>>(prim_cell_start, G.cell_start, w.task_off, g.ncu, g.ncv,
-																 cfg.nz, nzs, P.ku, P.periodic, cs, reach, w.task_col,
-																 w.task_first, w.task_n, w.task_cost, w.n_tasks);
+																 cfg.nz, nzs, split, P.ku, P.periodic, cs, reach, w.task_col,
+																 w.task_first, w.task_n, w.task_slab, w.task_cost, w.n_tasks);
 	MIA_CUDA_CHECK(cudaGetLastError());
 	cb = w.cub_bytes;
 	MIA_CUDA_CHECK(cub::DeviceScan::InclusiveSum(w.cub_tmp, cb, w.task_cost, w.task_cum, cfg.max_tasks, st));
@@ -1278,6 +1292,7 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &g, const DevPara
 	a.task_col = w.task_col;
 	a.task_first = w.task_first;
 	a.task_n = w.task_n;
+	a.task_slab = w.task_slab;
 	a.task_cost = w.task_cost;
 	a.task_cum = w.task_cum;
 	a.n_tasks = w.n_tasks;
