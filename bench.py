@@ -239,7 +239,7 @@ def main():
 		hbm_bytes = 96.0 * N
 		line["roofline"] = {
 			"bound": "fp64-alu", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-			"frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": None,
+			"frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": _ncu_traffic(args.workload),
 			"kernel_ms": t_kernel * 1e3,
 			"note": ("pair loop is FP64-issue bound (SURVEY.md 8(d)): achieved = binned pairs x %d flop / pair-kernel time "
 					 "(CUDA events around the kernel on its stream); peak = dependent-free DFMA rate measured live by "
@@ -292,6 +292,14 @@ def main():
 		print(json.dumps(line))
 	if world > 1:
 		dist.destroy_process_group()
+
+
+def _ncu_traffic(workload):
+	"""DRAM bytes per launch of the pair kernel from the committed ncu capture (profiles/r01_traffic.json), or None."""
+	try:
+		return json.load(open(os.path.join(_REPO, "profiles", "r01_traffic.json")))[workload]["traffic"]
+	except Exception:  # noqa: BLE001
+		return None
 
 
 def _hbm_peak():
