@@ -8,6 +8,7 @@
 #include "mia_general.cuh"
 #include "mia_grid.cuh"
 #include "mia_tiled.cuh"
+#include "mia_tiled_rmu.cuh"
 
 using namespace mia;
 
@@ -71,7 +72,9 @@ int make_plan(const mia_params *p, int64_t nD, int64_t nS, Plan &pl) {
 	pl.g.jk_rows = J;
 	pl.kernel = p->kernel;
 	if (pl.kernel == MIA_KERNEL_AUTO || pl.kernel == MIA_KERNEL_TILED) {
-		if (plan_tiled(p, nD, nS, pl.g, pl.ku, pl.kv, pl.kl, pl.tiled)) {
+		// the tiled grids are fine (cells ~ r_max / 4): their sort keys must fit 31 bits
+		if (plan_tiled(p, nD, nS, pl.g, pl.ku, pl.kv, pl.kl, pl.tiled) &&
+			(uint64_t)pl.g.ncell() * 4ull * (uint64_t)J <= (1ull << 31)) {
 			pl.kernel = MIA_KERNEL_TILED;
 		} else {
 			if (pl.kernel == MIA_KERNEL_TILED) return MIA_ERR_UNSUPPORTED;
@@ -391,7 +394,8 @@ int mia_paircount(const mia_params *params, const mia_sample *D, const mia_sampl
 		rc = tiled_launch(pl.tiled, g_prim, P, G, prim, prim_cell_start, nS, unit_w, shard, A, ws + pl.off_tiled, flags, st,
 						  timed ? ev[1] : nullptr, timed ? ev[2] : nullptr);
 		if (rc) return rc;
-		n_launches += 1 /* cell_info */ + 2 /* col_chunks, fill_tasks */ + 1 /* pair kernel */ + 2 /* reduce_partials */;
+		n_launches += 1 /* cell_info */ + 2 /* col_chunks, fill_tasks */ + 1 /* pair kernel */ + 2 /* reduce_partials */ +
+					  (params->geometry == MIA_GEOM_RMU ? 1 : 0) /* col_info */;
 		if (pl.n_partials > 1) {
 			const size_t n_el = (size_t)pl.rows * pl.nb;
 			unsigned long long *g_cnt = (unsigned long long *)(ws + pl.off_red_cnt);

@@ -70,7 +70,14 @@ struct CellInfo {
 	int nlab;   // number of label runs in the cell (1 = uniform)
 };
 
+// Bounding box of a whole column in the projected axes ((r, mu_r) kernel)
+struct ColInfo {
+	double umin, umax, vmin, vmax;
+};
+
 struct TiledConfig {
+	int geom;        // MIA_GEOM_*
+	int w_r;         // (r, mu_r): r bins per accumulation window
 	int n_partials;  // accumulator copies = worker warps
 	int n_ctas;
 	int num_sms;
@@ -87,6 +94,7 @@ struct TiledArgs {
 	const int32_t *cand_jk;
 	const int64_t *cell_start;
 	const CellInfo *cinfo;
+	const ColInfo *colinfo;  // (r, mu_r) kernel only
 	const double *slab_lo, *slab_hi;
 	const Prim *prim;
 	const int32_t *task_col;
@@ -99,8 +107,14 @@ struct TiledArgs {
 	int lut_hi0, lut_shift, lut_n;
 	Accum A;
 	int nz, n_side, n_workers, shard_index, shard_count, max_tasks;
+	int w_r;  // (r, mu_r) kernel only
 	int *flags;
 };
+
+// defined in mia_tiled_rmu.cuh
+inline bool rmu_supported(const mia_params *p, int &w_r);
+inline size_t tiled_rmu_smem_bytes(bool unit_w);
+inline int launch_rmu(const TiledArgs &a, bool unit_w, bool los2, int n_ctas, size_t smem, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------------------------
 // planning (host)
@@ -159,28 +173,41 @@ inline size_t tiled_smem_bytes(bool unit_w) {
 
 inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g, int &ku, int &kv, int &kl,
 					   TiledConfig &cfg) {
-	if (p->geometry != MIA_GEOM_RPPI) return false;
 	const double L = p->boxsize, reach = p->r_search * (1.0 + 1e-6);
-	// slabs thinner than the narrowest Pi bin
-	double dmin = INFINITY;
-	for (int b = 0; b < p->n_2; b++) {
-		const double lo = p->thr2_host[b], hi = p->thr2_host[b + 1];
-		if (!std::isfinite(lo) || !std::isfinite(hi) || !(hi > lo)) return false;
-		dmin = fmin(dmin, hi - lo);
-	}
-	const double nz_d = floor(L / (dmin * (1.0 - 1e-9))) + 1.0;
-	if (!(nz_d >= 1.0) || nz_d > 512.0) return false;
-	const int nz = (int)nz_d;
+	int n_side = 1;
+	while ((n_side + 1) * (n_side + 1) * (n_side + 1) <= (p->num_jk > 0 ? p->num_jk : 1)) n_side++;
+	cfg.n_side = n_side;
+	cfg.geom = p->geometry;
+	cfg.w_r = 0;
 	// columns: about a quarter of the search radius wide
 	int nc = (int)floor(L / (reach / 4.0));
 	if (nc > 2048) nc = 2048;
 	if (nc < 1) nc = 1;
+	int nz;
+	if (p->geometry == MIA_GEOM_RPPI) {
+		// slabs thinner than the narrowest Pi bin
+		double dmin = INFINITY;
+		for (int b = 0; b < p->n_2; b++) {
+			const double lo = p->thr2_host[b], hi = p->thr2_host[b + 1];
+			if (!std::isfinite(lo) || !std::isfinite(hi) || !(hi > lo)) return false;
+			dmin = fmin(dmin, hi - lo);
+		}
+		const double nz_d = floor(L / (dmin * (1.0 - 1e-9))) + 1.0;
+		if (!(nz_d >= 1.0) || nz_d > 512.0) return false;
+		nz = (int)nz_d;
+		if (!build_lut(p, cfg)) return false;
+	} else {
+		// (r, mu_r): 3-D search with cubic cells aligned with the jackknife sub-boxes (a cell then carries one label)
+		if (!rmu_supported(p, cfg.w_r)) return false;
+		if (n_side > 1 && nc >= 2 * n_side) nc = nc / n_side * n_side;
+		nz = nc > 512 ? 512 / n_side * n_side : nc;
+		if (nz < 1) nz = 1;
+	}
 	const double cs = L / nc;
 	int k = (int)ceil(reach / cs);
 	if (k < 1) k = 1;
 	const bool all_mode = (2 * k + 1 >= nc);
 	if (all_mode ? ((long long)nc * nc > MAX_NEIGH) : ((2 * k + 1) * (2 * k + 1) > MAX_NEIGH)) return false;
-	if (!build_lut(p, cfg)) return false;
 	g.ncu = g.ncv = nc;
 	g.ncl = nz;
 	g.inv_cu = g.inv_cv = nc / L;
@@ -188,9 +215,6 @@ inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g,
 	ku = kv = k;
 	kl = nz;  // all slabs
 	cfg.nz = nz;
-	int n_side = 1;
-	while ((n_side + 1) * (n_side + 1) * (n_side + 1) <= (p->num_jk > 0 ? p->num_jk : 1)) n_side++;
-	cfg.n_side = n_side;
 	int dev = 0, sms = 148;
 	if (cudaGetDevice(&dev) == cudaSuccess) {
 		int v = 0;
@@ -208,6 +232,7 @@ inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g,
 
 struct TiledWorkspace {
 	CellInfo *cinfo;
+	ColInfo *colinfo;
 	double *slab_lo, *slab_hi;
 	int32_t *col_chunks, *task_off, *task_col, *task_n, *task_slab, *n_tasks;
 	int64_t *task_first;
@@ -237,6 +262,7 @@ inline TiledWorkspace carve_tiled(const TiledConfig &cfg, const GridDims &g, voi
 	};
 	const int64_t ncell = g.ncell(), ncol = (int64_t)g.ncu * g.ncv;
 	w.cinfo = (CellInfo *)take(sizeof(CellInfo) * ncell);
+	w.colinfo = (ColInfo *)take(cfg.geom == MIA_GEOM_RMU ? sizeof(ColInfo) * ncol : 0);
 	w.slab_lo = (double *)take(sizeof(double) * cfg.nz);
 	w.slab_hi = (double *)take(sizeof(double) * cfg.nz);
 	w.col_chunks = (int32_t *)take(sizeof(int32_t) * (ncol + 1));
@@ -295,6 +321,22 @@ __global__ void k_cell_info(const Cand *__restrict__ cand, const int32_t *__rest
 		atomicMax(&slab_hi[s], (unsigned long long)__double_as_longlong(lmax + 0.0));
 	}
 	info[c] = ci;
+}
+
+__global__ void k_col_info(const CellInfo *__restrict__ cinfo, int64_t ncol, int nz, ColInfo *__restrict__ out) {
+	const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+	if (c >= ncol) return;
+	ColInfo o;
+	o.umin = o.vmin = INFINITY;
+	o.umax = o.vmax = -INFINITY;
+	for (int s = 0; s < nz; s++) {
+		const CellInfo ci = cinfo[c * nz + s];
+		o.umin = fmin(o.umin, ci.umin);
+		o.umax = fmax(o.umax, ci.umax);
+		o.vmin = fmin(o.vmin, ci.vmin);
+		o.vmax = fmax(o.vmax, ci.vmax);
+	}
+	out[c] = o;
 }
 
 __global__ void k_col_chunks(const int64_t *__restrict__ prim_cell_start, int64_t ncol, int nzs, int split,
@@ -1235,7 +1277,13 @@ inline int tiled_prepare_candidates(const TiledConfig &cfg, const GridDims &g, c
 																 (unsigned long long *)w.slab_lo,
 																 (unsigned long long *)w.slab_hi);
 	MIA_CUDA_CHECK(cudaGetLastError());
-	MIA_CUDA_CHECK(cudaMemcpyAsync(w.lut, cfg.lut, sizeof(LutEntry) * LUT_SIZE, cudaMemcpyHostToDevice, st));
+	if (cfg.geom == MIA_GEOM_RMU) {
+		const int64_t ncol = (int64_t)g.ncu * g.ncv;
+		k_col_info<<<(unsigned)((ncol + 127) / 128), 128, 0, st>>>(w.cinfo, ncol, cfg.nz, w.colinfo);
+		MIA_CUDA_CHECK(cudaGetLastError());
+	} else {
+		MIA_CUDA_CHECK(cudaMemcpyAsync(w.lut, cfg.lut, sizeof(LutEntry) * LUT_SIZE, cudaMemcpyHostToDevice, st));
+	}
 	(void)P;
 	return 0;
 }
@@ -1259,6 +1307,7 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &g, const DevPara
 	int split = (int)ceil(want / (tasks_est > 1.0 ? tasks_est : 1.0));
 	split = split < 1 ? 1 : (split > MAX_SPLIT ? MAX_SPLIT : split);
 	if (split > cfg.nz) split = cfg.nz;
+	if (cfg.geom == MIA_GEOM_RMU) split = 1;  // a warp's shapes are local along the line of sight: nothing to cut
 	k_col_chunks<<<(unsigned)((ncol + 1 + 255) / 256), 256, 0, st>>>(prim_cell_start, ncol, nzs, split, w.col_chunks);
 	MIA_CUDA_CHECK(cudaGetLastError());
 	size_t cb = w.cub_bytes;
@@ -1274,13 +1323,17 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &g, const DevPara
 	// ---- launch.  The number of worker warps is fixed (SLOTS_PER_SM CTAs per SM), NOT derived from occupancy: the
 	// grouping of the fp64 sums, hence every output bit, is the same for the weighted and the unit-weight kernel variants,
 	// which is what lets w = 0.5 scale the results by exactly 1/4 (reference tests/test_weights.py:34-35). ---------------
-	const size_t smem = tiled_smem_bytes(unit_w);
-	if (unit_w) {
+	const bool rmu = cfg.geom == MIA_GEOM_RMU;
+	const size_t smem = rmu ? tiled_rmu_smem_bytes(unit_w) : tiled_smem_bytes(unit_w);
+	if (rmu) {
+	} else if (unit_w) {
 		MIA_CUDA_CHECK(cudaFuncSetAttribute(k_tiled_rppi<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	} else {
 		MIA_CUDA_CHECK(cudaFuncSetAttribute(k_tiled_rppi<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	}
 	TiledArgs a;
+	a.colinfo = w.colinfo;
+	a.w_r = cfg.w_r;
 	a.P = P;
 	a.cand = G.cand;
 	a.cand_jk = G.cand_jk;
@@ -1309,8 +1362,14 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &g, const DevPara
 	a.max_tasks = cfg.max_tasks;
 	a.flags = flags;
 	if (ev_before) MIA_CUDA_CHECK(cudaEventRecord(ev_before, st));
-	if (unit_w) k_tiled_rppi<true><<<cfg.n_ctas, TP, smem, st>>>(a);
-	else k_tiled_rppi<false><<<cfg.n_ctas, TP, smem, st>>>(a);
+	if (rmu) {
+		const int rc = launch_rmu(a, unit_w, P.los == 2, cfg.n_ctas, smem, st);
+		if (rc) return rc;
+	} else if (unit_w) {
+		k_tiled_rppi<true><<<cfg.n_ctas, TP, smem, st>>>(a);
+	} else {
+		k_tiled_rppi<false><<<cfg.n_ctas, TP, smem, st>>>(a);
+	}
 	MIA_CUDA_CHECK(cudaGetLastError());
 	if (ev_after) MIA_CUDA_CHECK(cudaEventRecord(ev_after, st));
 	return 0;
