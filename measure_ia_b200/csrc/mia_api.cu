@@ -347,6 +347,12 @@ int mia_paircount(const mia_params *params, const mia_sample *D, const mia_sampl
 	// ---- shape sample -> sorted primaries ---------------------------------------------------------------------------
 	GridDims g_prim = pl.g;
 	g_prim.sub = (pl.kernel == MIA_KERNEL_TILED) ? 2 : 1;
+	if (pl.kernel == MIA_KERNEL_TILED && pl.tiled.ratio > 1) {  // (r, mu_r): the shape sample is sorted on coarser columns
+		g_prim.ncu /= pl.tiled.ratio;
+		g_prim.ncv /= pl.tiled.ratio;
+		g_prim.inv_cu = g_prim.ncu / params->boxsize;
+		g_prim.inv_cv = g_prim.ncv / params->boxsize;
+	}
 	rc = sort_by_cell(S->pos, S->jk, nS, nl0, nl1, los, g_prim, params->boxsize, sc, pl.key_bits, flags, st);
 	if (rc) return rc;
 	if (nS > 0) {
@@ -391,7 +397,7 @@ int mia_paircount(const mia_params *params, const mia_sample *D, const mia_sampl
 		if (timed) MIA_CUDA_CHECK(cudaEventRecord(ev[2], st));
 	} else {
 		const bool unit_w = (D->weight == nullptr && S->weight == nullptr);
-		rc = tiled_launch(pl.tiled, g_prim, P, G, prim, prim_cell_start, nS, unit_w, shard, A, ws + pl.off_tiled, flags, st,
+		rc = tiled_launch(pl.tiled, pl.g, g_prim, P, G, prim, prim_cell_start, nS, unit_w, shard, A, ws + pl.off_tiled, flags, st,
 						  timed ? ev[1] : nullptr, timed ? ev[2] : nullptr);
 		if (rc) return rc;
 		n_launches += 1 /* cell_info */ + 2 /* col_chunks, fill_tasks */ + 1 /* pair kernel */ + 2 /* reduce_partials */ +

@@ -78,6 +78,9 @@ struct ColInfo {
 struct TiledConfig {
 	int geom;        // MIA_GEOM_*
 	int w_r;         // (r, mu_r): r bins per accumulation window
+	int ratio;       // (r, mu_r): a shape column is ratio x ratio candidate columns wide
+	int hsplit;      // (r, mu_r): a warp works on 32 / hsplit shape galaxies, hsplit candidates at a time
+	int n_lr;        // (r, mu_r): line-of-sight regions (= jackknife sub-boxes per side when the slabs are aligned with them)
 	int n_partials;  // accumulator copies = worker warps
 	int n_ctas;
 	int num_sms;
@@ -95,6 +98,7 @@ struct TiledArgs {
 	const int64_t *cell_start;
 	const CellInfo *cinfo;
 	const ColInfo *colinfo;  // (r, mu_r) kernel only
+	const int32_t *colreg;   // (r, mu_r) kernel only: [column][region] the one label of the region's candidates, -1 several, -2 none
 	const double *slab_lo, *slab_hi;
 	const Prim *prim;
 	const int32_t *task_col;
@@ -107,7 +111,7 @@ struct TiledArgs {
 	int lut_hi0, lut_shift, lut_n;
 	Accum A;
 	int nz, n_side, n_workers, shard_index, shard_count, max_tasks;
-	int w_r;  // (r, mu_r) kernel only
+	int w_r, ratio, hsplit, n_lr;  // (r, mu_r) kernel only
 	int *flags;
 };
 
@@ -115,6 +119,10 @@ struct TiledArgs {
 inline bool rmu_supported(const mia_params *p, int &w_r);
 inline size_t tiled_rmu_smem_bytes(bool unit_w);
 inline int launch_rmu(const TiledArgs &a, bool unit_w, bool los2, int n_ctas, size_t smem, cudaStream_t st);
+inline bool plan_rmu_grid(const mia_params *p, int n_side, TiledConfig &cfg, int &nc, int &nz, int &k);
+inline int rmu_fill_tasks(const TiledArgs &a, const int64_t *prim_cell_start, const int64_t *cell_start, const int32_t *task_off,
+						  int ncol_s, int nzs, int k, int32_t *task_col, int64_t *task_first, int32_t *task_n,
+						  int32_t *task_slab, unsigned long long *task_cost, int32_t *n_tasks, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------------------------
 // planning (host)
@@ -179,6 +187,9 @@ inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g,
 	cfg.n_side = n_side;
 	cfg.geom = p->geometry;
 	cfg.w_r = 0;
+	cfg.ratio = 1;
+	cfg.hsplit = 1;
+	cfg.n_lr = 1;
 	// columns: about a quarter of the search radius wide
 	int nc = (int)floor(L / (reach / 4.0));
 	if (nc > 2048) nc = 2048;
@@ -199,15 +210,17 @@ inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g,
 	} else {
 		// (r, mu_r): 3-D search with cubic cells aligned with the jackknife sub-boxes (a cell then carries one label)
 		if (!rmu_supported(p, cfg.w_r)) return false;
-		if (n_side > 1 && nc >= 2 * n_side) nc = nc / n_side * n_side;
-		nz = nc > 512 ? 512 / n_side * n_side : nc;
-		if (nz < 1) nz = 1;
 	}
-	const double cs = L / nc;
-	int k = (int)ceil(reach / cs);
-	if (k < 1) k = 1;
-	const bool all_mode = (2 * k + 1 >= nc);
-	if (all_mode ? ((long long)nc * nc > MAX_NEIGH) : ((2 * k + 1) * (2 * k + 1) > MAX_NEIGH)) return false;
+	int k;
+	if (p->geometry == MIA_GEOM_RMU) {
+		if (!plan_rmu_grid(p, n_side, cfg, nc, nz, k)) return false;
+	} else {
+		const double cs = L / nc;
+		k = (int)ceil(reach / cs);
+		if (k < 1) k = 1;
+		const bool all_mode = (2 * k + 1 >= nc);
+		if (all_mode ? ((long long)nc * nc > MAX_NEIGH) : ((2 * k + 1) * (2 * k + 1) > MAX_NEIGH)) return false;
+	}
 	g.ncu = g.ncv = nc;
 	g.ncl = nz;
 	g.inv_cu = g.inv_cv = nc / L;
@@ -225,7 +238,7 @@ inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g,
 	cfg.num_sms = sms;
 	cfg.n_ctas = sms * SLOTS_PER_SM;
 	cfg.n_partials = cfg.n_ctas * TW;
-	cfg.max_tasks = (int)((nS / 32 + (int64_t)nc * nc + 1) * MAX_SPLIT);
+	cfg.max_tasks = (int)((nS / (32 / cfg.hsplit) + (int64_t)nc * nc + 1) * MAX_SPLIT);
 	(void)nD;
 	return true;
 }
@@ -233,6 +246,7 @@ inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g,
 struct TiledWorkspace {
 	CellInfo *cinfo;
 	ColInfo *colinfo;
+	int32_t *colreg;
 	double *slab_lo, *slab_hi;
 	int32_t *col_chunks, *task_off, *task_col, *task_n, *task_slab, *n_tasks;
 	int64_t *task_first;
@@ -263,6 +277,7 @@ inline TiledWorkspace carve_tiled(const TiledConfig &cfg, const GridDims &g, voi
 	const int64_t ncell = g.ncell(), ncol = (int64_t)g.ncu * g.ncv;
 	w.cinfo = (CellInfo *)take(sizeof(CellInfo) * ncell);
 	w.colinfo = (ColInfo *)take(cfg.geom == MIA_GEOM_RMU ? sizeof(ColInfo) * ncol : 0);
+	w.colreg = (int32_t *)take(cfg.geom == MIA_GEOM_RMU ? sizeof(int32_t) * ncol * cfg.n_lr : 0);
 	w.slab_lo = (double *)take(sizeof(double) * cfg.nz);
 	w.slab_hi = (double *)take(sizeof(double) * cfg.nz);
 	w.col_chunks = (int32_t *)take(sizeof(int32_t) * (ncol + 1));
@@ -323,24 +338,54 @@ __global__ void k_cell_info(const Cand *__restrict__ cand, const int32_t *__rest
 	info[c] = ci;
 }
 
-__global__ void k_col_info(const CellInfo *__restrict__ cinfo, int64_t ncol, int nz, ColInfo *__restrict__ out) {
+// (r, mu_r) kernel: per column, the bounding box in the projected axes and, per line-of-sight region, the label its
+// candidates share (-1: several labels, -2: no candidates).  Thread 0 also turns the per-slab coordinate bounds into
+// envelopes (slab_lo[s] = smallest coordinate in slabs >= s, slab_hi[s] = largest in slabs <= s), which are valid
+// bounds for any run of slabs, empty ones included.
+__global__ void k_col_info(const CellInfo *__restrict__ cinfo, int64_t ncol, int nz, int n_lr, ColInfo *__restrict__ out,
+						   int32_t *__restrict__ colreg, double *__restrict__ slab_lo, double *__restrict__ slab_hi) {
 	const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+	if (c == 0) {
+		double cur = INFINITY;
+		for (int s = nz - 1; s >= 0; s--) {
+			const double v = slab_lo[s];
+			if (v == v) cur = fmin(cur, v);  // empty slabs still hold the NaN fill pattern
+			slab_lo[s] = cur;
+		}
+		cur = -INFINITY;
+		for (int s = 0; s < nz; s++) {
+			const double lo = slab_lo[s], v = slab_hi[s];
+			(void)lo;
+			cur = fmax(cur, v);  // empty slabs hold 0.0 <= every coordinate
+			slab_hi[s] = cur;
+		}
+	}
 	if (c >= ncol) return;
 	ColInfo o;
 	o.umin = o.vmin = INFINITY;
 	o.umax = o.vmax = -INFINITY;
-	for (int s = 0; s < nz; s++) {
-		const CellInfo ci = cinfo[c * nz + s];
-		o.umin = fmin(o.umin, ci.umin);
-		o.umax = fmax(o.umax, ci.umax);
-		o.vmin = fmin(o.vmin, ci.vmin);
-		o.vmax = fmax(o.vmax, ci.vmax);
+	const int per = nz / n_lr;
+	for (int r = 0; r < n_lr; r++) {
+		int lab = -2;
+		const int s1 = (r == n_lr - 1) ? nz : (r + 1) * per;
+		for (int s = r * per; s < s1; s++) {
+			const CellInfo ci = cinfo[c * nz + s];
+			if (ci.nlab == 0) continue;
+			o.umin = fmin(o.umin, ci.umin);
+			o.umax = fmax(o.umax, ci.umax);
+			o.vmin = fmin(o.vmin, ci.vmin);
+			o.vmax = fmax(o.vmax, ci.vmax);
+			if (ci.nlab > 1) lab = -1;
+			else if (lab == -2) lab = ci.label;
+			else if (lab != ci.label) lab = -1;
+		}
+		colreg[c * n_lr + r] = lab;
 	}
 	out[c] = o;
 }
 
 __global__ void k_col_chunks(const int64_t *__restrict__ prim_cell_start, int64_t ncol, int nzs, int split,
-							 int32_t *__restrict__ col_chunks) {
+							 int32_t *__restrict__ col_chunks, int spt = 32) {
 	const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
 	if (c > ncol) return;
 	if (c == ncol) {
@@ -348,7 +393,7 @@ __global__ void k_col_chunks(const int64_t *__restrict__ prim_cell_start, int64_
 		return;
 	}
 	const int64_t n = prim_cell_start[(c + 1) * nzs] - prim_cell_start[c * nzs];  // nzs = cells of the shape sort per column
-	col_chunks[c] = (int32_t)((n + 31) / 32) * split;
+	col_chunks[c] = (int32_t)((n + spt - 1) / spt) * split;
 }
 
 __device__ __forceinline__ bool neighbour_offset_ok(int ou, int ov, double cs, double reach) {
@@ -1279,7 +1324,8 @@ inline int tiled_prepare_candidates(const TiledConfig &cfg, const GridDims &g, c
 	MIA_CUDA_CHECK(cudaGetLastError());
 	if (cfg.geom == MIA_GEOM_RMU) {
 		const int64_t ncol = (int64_t)g.ncu * g.ncv;
-		k_col_info<<<(unsigned)((ncol + 127) / 128), 128, 0, st>>>(w.cinfo, ncol, cfg.nz, w.colinfo);
+		k_col_info<<<(unsigned)((ncol + 127) / 128), 128, 0, st>>>(w.cinfo, ncol, cfg.nz, cfg.n_lr, w.colinfo, w.colreg,
+																   w.slab_lo, w.slab_hi);
 		MIA_CUDA_CHECK(cudaGetLastError());
 	} else {
 		MIA_CUDA_CHECK(cudaMemcpyAsync(w.lut, cfg.lut, sizeof(LutEntry) * LUT_SIZE, cudaMemcpyHostToDevice, st));
@@ -1288,10 +1334,10 @@ inline int tiled_prepare_candidates(const TiledConfig &cfg, const GridDims &g, c
 	return 0;
 }
 
-inline int tiled_launch(const TiledConfig &cfg, const GridDims &g, const DevParams &P, const Grid &G, const Prim *prim,
+inline int tiled_launch(const TiledConfig &cfg, const GridDims &gc, const GridDims &g, const DevParams &P, const Grid &G, const Prim *prim,
 						const int64_t *prim_cell_start, int64_t nS, bool unit_w, mia_shard shard, const Accum &A, void *ws,
 						int *flags, cudaStream_t st, cudaEvent_t ev_before = nullptr, cudaEvent_t ev_after = nullptr) {
-	TiledWorkspace w = carve_tiled(cfg, g, ws);
+	TiledWorkspace w = carve_tiled(cfg, gc, ws);  // carved on the candidate grid (gc); g = grid of the shape sort
 	const int64_t ncol = (int64_t)g.ncu * g.ncv;
 	if (nS == 0 || G.n_cand == 0) {
 		if (ev_before) MIA_CUDA_CHECK(cudaEventRecord(ev_before, st));
@@ -1302,20 +1348,31 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &g, const DevPara
 	MIA_CUDA_CHECK(cudaMemsetAsync(w.task_cost, 0, sizeof(unsigned long long) * cfg.max_tasks, st));
 	const int nzs = cfg.nz * (g.sub > 1 ? g.sub * g.sub : 1);
 	// when there are few tasks per worker warp (small catalogues, many GPUs) cut each task along the line of sight
-	const double tasks_est = (double)nS / 32.0 + 0.5 * (double)ncol;
+	const int spt = 32 / cfg.hsplit;  // shape galaxies per warp task
+	const double tasks_est = (double)nS / (double)spt + 0.5 * (double)ncol;
 	const double want = 8.0 * (double)cfg.n_ctas * TW * (double)shard.count;
 	int split = (int)ceil(want / (tasks_est > 1.0 ? tasks_est : 1.0));
 	split = split < 1 ? 1 : (split > MAX_SPLIT ? MAX_SPLIT : split);
 	if (split > cfg.nz) split = cfg.nz;
 	if (cfg.geom == MIA_GEOM_RMU) split = 1;  // a warp's shapes are local along the line of sight: nothing to cut
-	k_col_chunks<<<(unsigned)((ncol + 1 + 255) / 256), 256, 0, st>>>(prim_cell_start, ncol, nzs, split, w.col_chunks);
+	k_col_chunks<<<(unsigned)((ncol + 1 + 255) / 256), 256, 0, st>>>(prim_cell_start, ncol, nzs, split, w.col_chunks, spt);
 	MIA_CUDA_CHECK(cudaGetLastError());
 	size_t cb = w.cub_bytes;
 	MIA_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, cb, w.col_chunks, w.task_off, (int)(ncol + 1), st));
-	const double cs = P.L / g.ncu, reach = sqrt(P.r2_thr[P.n_r]) * (1.0 + 1e-6);
-	k_fill_tasks<<<(unsigned)((ncol + 255) / 256), 256, 0, st>>>(prim_cell_start, G.cell_start, w.task_off, g.ncu, g.ncv,
-																 cfg.nz, nzs, split, P.ku, P.periodic, cs, reach, w.task_col,
-																 w.task_first, w.task_n, w.task_slab, w.task_cost, w.n_tasks);
+	TiledArgs a;
+	a.P = P;
+	a.ratio = cfg.ratio;
+	a.hsplit = cfg.hsplit;
+	if (cfg.geom == MIA_GEOM_RMU) {
+		const int rc = rmu_fill_tasks(a, prim_cell_start, G.cell_start, w.task_off, (int)ncol, nzs, P.ku, w.task_col, w.task_first,
+									  w.task_n, w.task_slab, w.task_cost, w.n_tasks, st);
+		if (rc) return rc;
+	} else {
+		const double cs = P.L / g.ncu, reach = sqrt(P.r2_thr[P.n_r]) * (1.0 + 1e-6);
+		k_fill_tasks<<<(unsigned)((ncol + 255) / 256), 256, 0, st>>>(prim_cell_start, G.cell_start, w.task_off, g.ncu, g.ncv,
+																	 cfg.nz, nzs, split, P.ku, P.periodic, cs, reach, w.task_col,
+																	 w.task_first, w.task_n, w.task_slab, w.task_cost, w.n_tasks);
+	}
 	MIA_CUDA_CHECK(cudaGetLastError());
 	cb = w.cub_bytes;
 	MIA_CUDA_CHECK(cub::DeviceScan::InclusiveSum(w.cub_tmp, cb, w.task_cost, w.task_cum, cfg.max_tasks, st));
@@ -1331,10 +1388,10 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &g, const DevPara
 	} else {
 		MIA_CUDA_CHECK(cudaFuncSetAttribute(k_tiled_rppi<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	}
-	TiledArgs a;
 	a.colinfo = w.colinfo;
+	a.colreg = w.colreg;
+	a.n_lr = cfg.n_lr;
 	a.w_r = cfg.w_r;
-	a.P = P;
 	a.cand = G.cand;
 	a.cand_jk = G.cand_jk;
 	a.cell_start = G.cell_start;

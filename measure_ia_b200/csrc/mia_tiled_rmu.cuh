@@ -31,9 +31,21 @@ constexpr int NS_RMU = 20;   // private slots per thread
 #endif
 constexpr int CH_RMU = MIA_CH_RMU;  // candidates per staged chunk
 constexpr unsigned MU_BAND = 16u;   // half-width of the "too close to a mu edge" band in units of 2^-40 bins
+constexpr int MAX_NEIGH_RMU = 384;  // neighbour (candidate) columns per task
+// Tuning (measured on B200, cfg3: profiles/r01_tuning.md): candidate cells of r_max / DIV, shape columns RATIO x RATIO
+// candidate columns wide (so that 32 / HSPLIT consecutive shapes form a compact blob), HSPLIT candidates per warp step.
+#ifndef MIA_RMU_DIV
+#define MIA_RMU_DIV 6
+#endif
+#ifndef MIA_RMU_RATIO
+#define MIA_RMU_RATIO 2
+#endif
+#ifndef MIA_RMU_HSPLIT
+#define MIA_RMU_HSPLIT 1
+#endif
 
 inline size_t tiled_rmu_smem_bytes(bool unit_w) {
-	const size_t fixed = sizeof(Cand) * TW * STAGES * CH_RMU + sizeof(int) * TW * MAX_NEIGH + 256 + 768;
+	const size_t fixed = sizeof(Cand) * TW * STAGES * CH_RMU + sizeof(int) * TW * MAX_NEIGH_RMU + 256 + 768;
 	const size_t per_slot = (size_t)TP * (8 + 8 + 4 + (unit_w ? 0 : 8));
 	return fixed + per_slot * NS_RMU;
 }
@@ -54,6 +66,180 @@ inline bool rmu_supported(const mia_params *p, int &w_r) {
 		if (!(thr[b + 1] > thr[b]) || !std::isfinite(thr[b + 1])) return false;
 	w_r = (2 * n <= NS_RMU && p->n_r > 1) ? 2 : 1;
 	return true;
+}
+
+inline int env_int(const char *name, int dflt) {
+	const char *v = getenv(name);
+	return (v && *v) ? atoi(v) : dflt;
+}
+
+// Grid of the (r, mu_r) kernel: cubic candidate cells of about r_max / DIV, aligned with the jackknife sub-boxes (a cell
+// then carries one label) and with the coarser shape columns.
+inline bool plan_rmu_grid(const mia_params *p, int n_side, TiledConfig &cfg, int &nc, int &nz, int &k) {
+	const double L = p->boxsize, reach = p->r_search * (1.0 + 1e-6);
+	int div = env_int("MIA_RMU_DIV", MIA_RMU_DIV), ratio = env_int("MIA_RMU_RATIO", MIA_RMU_RATIO);
+	int hs = env_int("MIA_RMU_HSPLIT", MIA_RMU_HSPLIT);
+	if (div < 1) div = 1;
+	if (ratio < 1) ratio = 1;
+	if (hs != 1 && hs != 2 && hs != 4) hs = 1;
+	for (;; div--) {
+		nc = (int)floor(L / (reach / (double)div));
+		if (nc > 512) nc = 512;
+		if (nc < 1) nc = 1;
+		int rt = ratio;
+		while (rt > 1 && nc < 4 * rt) rt--;
+		int m = rt;  // nc a multiple of lcm(n_side, ratio) when the box is large enough
+		if (n_side > 1) {
+			int a = n_side, b = rt;
+			while (b) {
+				const int t_ = a % b;
+				a = b;
+				b = t_;
+			}
+			m = n_side / a * rt;
+		}
+		if (nc >= 2 * m) nc = nc / m * m;
+		else if (nc >= 2 * rt) nc = nc / rt * rt;
+		else rt = 1;
+		const double cs = L / nc;
+		k = (int)ceil(reach / cs);
+		if (k < 1) k = 1;
+		const bool all_mode = (2 * k + rt >= nc);
+		const long long n_off = all_mode ? (long long)nc * nc : (long long)(2 * k + rt) * (2 * k + rt);
+		const unsigned long long nkeys = (unsigned long long)nc * nc * nc * 4ull * (unsigned long long)(p->num_jk > 0 ? p->num_jk : 1);
+		if (n_off <= MAX_NEIGH_RMU && nkeys <= (1ull << 31)) {
+			cfg.ratio = rt;
+			break;
+		}
+		if (div == 1) return false;
+	}
+	nz = nc;
+	cfg.hsplit = hs;
+	cfg.n_lr = (n_side > 1 && nz % n_side == 0) ? n_side : 1;
+	return true;
+}
+
+// Neighbour enumeration shared by the task-cost kernel and the pair kernel.  Offsets (iu, iv) run over a
+// (2k + ratio)^2 window (or the whole grid when that wraps); returns the candidate column or -1.
+__device__ __forceinline__ int rmu_neighbour(int o, int su0, int sv0, int ratio, int ncu, int ncv, int k, int periodic,
+											 double cs, double reach) {
+	const bool all_u = 2 * k + ratio >= ncu, all_v = 2 * k + ratio >= ncv;
+	const int wu = all_u ? ncu : 2 * k + ratio, wv = all_v ? ncv : 2 * k + ratio;
+	if (o >= wu * wv) return -1;
+	const int iu = o / wv, iv = o - iu * wv;
+	const int ou = iu - k, ov = iv - k;  // offsets from the first candidate column of the shape column
+	int nu = all_u ? iu : ratio * su0 + ou, nv = all_v ? iv : ratio * sv0 + ov;
+	if (nu < 0) {
+		if (!periodic) return -1;
+		nu += ncu;
+	} else if (nu >= ncu) {
+		if (!periodic) return -1;
+		nu -= ncu;
+	}
+	if (nv < 0) {
+		if (!periodic) return -1;
+		nv += ncv;
+	} else if (nv >= ncv) {
+		if (!periodic) return -1;
+		nv -= ncv;
+	}
+	if (!all_u && !all_v) {
+		const double gu = ou < 0 ? (double)(-ou - 1) : (ou >= ratio ? (double)(ou - ratio) : 0.0);
+		const double gv = ov < 0 ? (double)(-ov - 1) : (ov >= ratio ? (double)(ov - ratio) : 0.0);
+		if (!((gu * gu + gv * gv) * cs * cs * (1.0 - 1e-6) < reach * reach)) return -1;
+	}
+	return nu * ncv + nv;
+}
+
+__device__ __forceinline__ int rmu_n_offsets(int ratio, int ncu, int ncv, int k) {
+	const int wu = (2 * k + ratio >= ncu) ? ncu : 2 * k + ratio, wv = (2 * k + ratio >= ncv) ? ncv : 2 * k + ratio;
+	return wu * wv;
+}
+
+// One warp task = up to spt consecutive shape galaxies of one shape column; cost = shapes x candidates in reach.
+__global__ void k_fill_tasks_rmu(const int64_t *__restrict__ prim_cell_start, const int64_t *__restrict__ cell_start,
+								 const int32_t *__restrict__ task_off, int ncu, int ncv, int nz, int ratio, int nzs, int spt,
+								 int k, int periodic, double cs, double reach, int32_t *__restrict__ task_col,
+								 int64_t *__restrict__ task_first, int32_t *__restrict__ task_n,
+								 int32_t *__restrict__ task_slab, unsigned long long *__restrict__ task_cost,
+								 int32_t *__restrict__ n_tasks) {
+	const int ncu_s = ncu / ratio, ncv_s = ncv / ratio;
+	const int64_t ncol = (int64_t)ncu_s * ncv_s;
+	const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+	if (c == 0) n_tasks[0] = task_off[ncol];
+	if (c >= ncol) return;
+	const int64_t p0 = prim_cell_start[c * nzs], p1 = prim_cell_start[(c + 1) * nzs];
+	if (p1 <= p0) return;
+	const int su0 = (int)(c / ncv_s), sv0 = (int)(c % ncv_s);
+	const int n_off = rmu_n_offsets(ratio, ncu, ncv, k);
+	unsigned long long W = 0;
+	for (int o = 0; o < n_off; o++) {
+		const int nc_ = rmu_neighbour(o, su0, sv0, ratio, ncu, ncv, k, periodic, cs, reach);
+		if (nc_ >= 0) W += (unsigned long long)(cell_start[(int64_t)(nc_ + 1) * nz] - cell_start[(int64_t)nc_ * nz]);
+	}
+	int t = task_off[c];
+	for (int64_t p = p0; p < p1; p += spt, t++) {
+		const int n = (int)((p1 - p < spt) ? (p1 - p) : spt);
+		task_col[t] = (int32_t)c;
+		task_first[t] = p;
+		task_n[t] = n;
+		task_slab[2 * t] = 0;
+		task_slab[2 * t + 1] = nz;
+		task_cost[t] = (unsigned long long)n * W + 1ull;
+	}
+}
+
+inline int rmu_fill_tasks(const TiledArgs &a, const int64_t *prim_cell_start, const int64_t *cell_start, const int32_t *task_off,
+						  int ncol_s, int nzs, int k, int32_t *task_col, int64_t *task_first, int32_t *task_n,
+						  int32_t *task_slab, unsigned long long *task_cost, int32_t *n_tasks, cudaStream_t st) {
+	const DevParams &P = a.P;
+	const double cs = P.L / P.ncu, reach = sqrt(P.r2_thr[P.n_r]) * (1.0 + 1e-6);
+	k_fill_tasks_rmu<<<(unsigned)((ncol_s + 127) / 128), 128, 0, st>>>(prim_cell_start, cell_start, task_off, P.ncu, P.ncv, P.ncl,
+																	   a.ratio, nzs, 32 / a.hsplit, k, P.periodic, cs, reach, task_col,
+																	   task_first, task_n, task_slab, task_cost, n_tasks);
+	return (int)cudaGetLastError();
+}
+
+// Neighbour candidate columns of a shape column, ordered by jackknife (u, v) region so that candidate labels change
+// rarely.  Writes the list to nlist (per-warp shared scratch) and returns its length.
+__device__ __noinline__ int build_neighbour_list_rmu(int *nlist, int2 *scratch, int scol, int ratio, int ncu, int ncv, int k,
+													 int periodic, int n_side, double cs, double reach) {
+	const int lane = threadIdx.x & 31;
+	const int ncv_s = ncv / ratio;
+	const int su0 = scol / ncv_s, sv0 = scol % ncv_s;
+	const int n_off = rmu_n_offsets(ratio, ncu, ncv, k), n_keys = n_side * n_side;
+	__syncwarp();
+	for (int o = lane; o < n_off; o += 32) {  // scratch = this warp's (idle) staging buffers
+		const int c_ = rmu_neighbour(o, su0, sv0, ratio, ncu, ncv, k, periodic, cs, reach);
+		int key = -1;
+		if (c_ >= 0) {
+			const int nu = c_ / ncv, nv = c_ - nu * ncv;
+			key = ((nu * n_side) / ncu) * n_side + (nv * n_side) / ncv;
+		}
+		scratch[o] = make_int2(c_, key);
+	}
+	__syncwarp();
+	int nn = 0;
+	for (int key = 0; key < n_keys; key++) {
+		for (int base = 0; base < n_off; base += 32) {
+			const int2 ck = (base + lane < n_off) ? scratch[base + lane] : make_int2(-1, -1);
+			const bool mine = ck.y == key;
+			const unsigned m = __ballot_sync(0xffffffffu, mine);
+			if (mine) nlist[nn + __popc(m & ((1u << lane) - 1u))] = ck.x;
+			nn += __popc(m);
+		}
+	}
+	__syncwarp();
+	return nn;
+}
+
+// order-preserving float <-> unsigned maps (warp min / max with one REDUX instruction)
+__device__ __forceinline__ unsigned f2ord(float f) {
+	const unsigned u = __float_as_uint(f);
+	return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned o) {
+	return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
 }
 
 // The approximate per-pair quantities of the fast loop, in ONE place: the slow path must reproduce the fast loop's
@@ -99,18 +285,21 @@ __device__ __forceinline__ RmuApprox rmu_approx(double du, double dv, double dz,
 	return r;
 }
 
-// Window of r bins [ra, ra + W_R): limits and interior threshold as bit patterns (s >= 0: integer order == double order)
+// Window of r bins [ra, ra + W_R): limits and the interior threshold on s = r^2, and the r_p^2 cut
 struct RmuWindow {
-	long long lo_b, hi_b, thr_b, cut_b;
+	double lo, hi, thr, cut;
 	int ra;
 };
 
-// One staged chunk against this thread's shape galaxy.  VAR 0: no periodic image; 1: lane-constant image shifts
-// (su, sv, sl); 2: every separation wrapped per pair (a chunk straddles +-L/2 for some lane: tiny boxes only).
+// One staged chunk against this thread's shape galaxy.  VAR 0: no periodic image; 1: warp-constant image shifts
+// (su, sv, sl); 2: every separation wrapped per pair (the chunk straddles +-L/2 for the warp: tiny boxes only).
+// A warp works on hsplit candidates at a time (one per group of 32 / hsplit lanes): cb = address of this lane's first
+// candidate, n = number of candidates of this lane, hstep = bytes between them.
 template <bool UNITW, bool LOS2, int VAR>
-__device__ __forceinline__ bool pair_loop_rmu(uint32_t cb, int n, double L, double halfL, double pu, double pv, double pl,
-											  double a0, double a1, double su, double sv, double sl, const RmuWindow &rw,
-											  long long hi_lane_b, double hn, double tbias, int n_mu, const PrivAcc &acc) {
+__device__ __forceinline__ bool pair_loop_rmu(uint32_t cb, int n, uint32_t hstep, double L, double halfL, double pu, double pv,
+											  double pl, double a0, double a1, double su, double sv, double sl, double w_lo,
+											  double w_hi, double w_thr, double w_cut, double hn, double tbias, int n_mu,
+											  const PrivAcc &acc) {
 	auto wrap = [&](double d) {
 		const double c = __hiloint2double(__double2hiint(L) | (__double2hiint(d) & 0x80000000), __double2loint(L));
 		return (fabs(d) > halfL) ? __dsub_rn(d, c) : d;  // c = copysign(L, d): measure_m_box_jk.py:419-421
@@ -120,13 +309,13 @@ __device__ __forceinline__ bool pair_loop_rmu(uint32_t cb, int n, double L, doub
 	lds_v2(cu, cv, cb);
 	lds_v2(cl, cw, cb + 16);
 	{
-		const uint32_t a1_ = cb + (uint32_t)((1 < n) ? 1 : 0) * (uint32_t)sizeof(Cand);
+		const uint32_t a1_ = cb + (uint32_t)((1 < n) ? 1 : 0) * hstep;
 		lds_v2(mu_, mv_, a1_);
 		lds_v2(ml_, mw_, a1_ + 16);
 	}
 	MIA_UNROLL_PRAGMA(MIA_UNROLL)
 	for (int j = 0; j < n; j++) {
-		const uint32_t na = cb + (uint32_t)((j + 2 < n) ? (j + 2) : (n - 1)) * (uint32_t)sizeof(Cand);
+		const uint32_t na = cb + (uint32_t)((j + 2 < n) ? (j + 2) : (n - 1)) * hstep;
 		double nu, nv, nl, nw;
 		lds_v2(nu, nv, na);
 		lds_v2(nl, nw, na + 16);
@@ -145,10 +334,9 @@ __device__ __forceinline__ bool pair_loop_rmu(uint32_t cb, int n, double L, doub
 		// r^2 summed over the ORIGINAL columns 0, 1, 2 (:428): (u, v, l) if the line of sight is column 2, else (u, l, v)
 		// or (l, u, v), which round identically
 		const double s = LOS2 ? __dadd_rn(rp2, ll) : __dadd_rn(__dadd_rn(uu, ll), vv);
-		const long long sb = __double_as_longlong(s);
-		bool ok = (sb >= rw.lo_b) && (sb < hi_lane_b) && (__double_as_longlong(rp2) > rw.cut_b);
+		bool ok = (s >= w_lo) && (s < w_hi) && (rp2 > w_cut);
 		const RmuApprox ap = rmu_approx(du, dv, dz, rp2, s, a0, a1, hn, tbias, n_mu);
-		const int slot = ap.idx + ((sb >= rw.thr_b) ? n_mu : 0);
+		const int slot = ap.idx + ((s >= w_thr) ? n_mu : 0);
 		const uint32_t so = (uint32_t)slot * (uint32_t)TP;
 		double s0, s1, sw = 0.0;
 		lds_v2(s0, s1, acc.a2 + so * 16u);
@@ -180,8 +368,8 @@ __device__ __forceinline__ bool pair_loop_rmu(uint32_t cb, int n, double L, doub
 template <bool UNITW, bool LOS2>
 __device__ __noinline__ void slow_pairs_rmu(bool lane_susp, uint32_t cb, int n, int periodic, double L, double halfL,
 											double pu, double pv, double pl, double a0, double a1, const RmuWindow rw,
-											long long hi_lane_b, double hn, double tbias, int n_mu, const double *thr2,
-											PrivAcc acc, unsigned long long &nan_pairs) {
+											double hi_lane, double hn, double tbias, int n_mu, const double *thr2,
+											PrivAcc acc, uint32_t hstep, unsigned long long &nan_pairs) {
 	if (!lane_susp) return;
 	auto sep = [&](double s_, double c_) {  // measure_m_box_jk.py:418-421
 		double d = __dsub_rn(s_, c_);
@@ -193,14 +381,13 @@ __device__ __noinline__ void slow_pairs_rmu(bool lane_susp, uint32_t cb, int n, 
 	};
 	for (int j = 0; j < n; j++) {
 		double cu, cv, cl, cw;
-		lds_v2(cu, cv, cb + (uint32_t)j * (uint32_t)sizeof(Cand));
-		lds_v2(cl, cw, cb + (uint32_t)j * (uint32_t)sizeof(Cand) + 16);
+		lds_v2(cu, cv, cb + (uint32_t)j * hstep);
+		lds_v2(cl, cw, cb + (uint32_t)j * hstep + 16);
 		const double du = sep(pu, cu), dv = sep(pv, cv), dz = sep(pl, cl);
 		const double uu = __dmul_rn(du, du), vv = __dmul_rn(dv, dv), ll = __dmul_rn(dz, dz);
 		const double rp2 = __dadd_rn(uu, vv);
 		const double s = LOS2 ? __dadd_rn(rp2, ll) : __dadd_rn(__dadd_rn(uu, ll), vv);
-		const long long sb = __double_as_longlong(s);
-		if (!((sb >= rw.lo_b) && (sb < hi_lane_b) && (__double_as_longlong(rp2) > rw.cut_b))) continue;
+		if (!((s >= rw.lo) && (s < hi_lane) && (rp2 > rw.cut))) continue;
 		const RmuApprox ap = rmu_approx(du, dv, dz, rp2, s, a0, a1, hn, tbias, n_mu);
 		if (!ap.susp) continue;  // the fast loop accumulated this pair
 		const double mu = __ddiv_rn(dz, __dsqrt_rn(s));  // :431
@@ -211,7 +398,7 @@ __device__ __noinline__ void slow_pairs_rmu(bool lane_susp, uint32_t cb, int n, 
 		double gp = 0.0, gc = 0.0;
 		if (fabs(c) <= 1.0) shape_projection(c, gp, gc);
 		else nan_pairs++;  // arccos -> NaN -> e+ = ex = 0, the pair still counts (:437-438)
-		const int slot = idx + ((sb >= rw.thr_b) ? n_mu : 0);
+		const int slot = idx + ((s >= rw.thr) ? n_mu : 0);
 		const uint32_t so = (uint32_t)slot * (uint32_t)TP;
 		double s0, s1;
 		lds_v2(s0, s1, acc.a2 + so * 16u);
@@ -303,12 +490,133 @@ __device__ __forceinline__ double warp_max_f64(double x) {
 	return x;
 }
 
-struct ChunkRmu {
-	long long start;
-	int n, label;
-	int xy;        // projected axes: 0 no image, 1 lane-constant image shifts, 2 some lane straddles +-L/2
-	int cl0, cl1;  // first / last non-empty slab of the chunk's run (bounds of its line-of-sight coordinates)
+// Everything the chunk consumer needs for one (task, window).  Lives in the kernel's local memory; process_round() --
+// a __noinline__ function with its own register allocation -- loads it once per ROUND of up to 32 column descriptors.
+struct RmuCtx {
+	// per lane
+	double pu, pv, pl, a0, a1, hi_lane, pe, pw;
+	int jk, dead;
+	// per (task, window)
+	double L, halfL, lo, hi, thr, cut, hn, tbias;
+	int n_mu, ns, ra, rb, periodic, hlog, half;
+	uint32_t a2, aw, ac, ring_u32, hstep;
+	const Cand *cand;
+	Cand *ring;
+	uint64_t *full;
+	const double *thr2;
+	FlushCtx fc;
+	// mutable: stream state, current candidate label, statistics
+	uint32_t phase0, phase1;
+	int st_issue, cur_label;
+	unsigned long long tested, binned, nan_pairs;
 };
+
+// Image codes of a chunk: per axis 0 = no image, 1 = every pair wraps down (d -= L), 2 = up (d += L), 3 = the chunk
+// straddles +-L/2 for the warp (wrap per pair).  codes = cu | cv << 2 | cl(piece A) << 4 | cl(piece B) << 6.
+__device__ __forceinline__ double code_shift(int code, double L) { return code == 1 ? -L : (code == 2 ? L : 0.0); }
+
+// Consume one round: lane e (bit e of mask) holds a column descriptor = up to two contiguous candidate ranges [sA, eA),
+// [sB, eB) with ONE jackknife label `lab` and warp-constant image codes.  Ranges are cut into chunks of <= CH_RMU,
+// streamed through the warp's double buffer (bulk copy of chunk k+1 in flight while chunk k is processed).
+template <bool UNITW, bool LOS2>
+__device__ __noinline__ void process_round(RmuCtx *cx, int sA, int eA, int sB, int eB, int lab, int codes, unsigned mask) {
+	const int lane = threadIdx.x & 31;
+	const double L = cx->L, halfL = cx->halfL, pu = cx->pu, pv = cx->pv, pl = cx->pl, a0 = cx->a0, a1 = cx->a1;
+	const double hi_lane = cx->hi_lane, hn = cx->hn, tbias = cx->tbias;
+	RmuWindow rw;
+	rw.lo = cx->lo;
+	rw.hi = cx->hi;
+	rw.thr = cx->thr;
+	rw.cut = cx->cut;
+	rw.ra = cx->ra;
+	const int n_mu = cx->n_mu, hlog = cx->hlog, half = cx->half;
+	const bool dead = cx->dead != 0;
+	PrivAcc acc;
+	acc.a2 = cx->a2;
+	acc.aw = cx->aw;
+	acc.ac = cx->ac;
+	const uint32_t ring_u32 = cx->ring_u32, hstep = cx->hstep;
+	const Cand *cand = cx->cand;
+	Cand *ring = cx->ring;
+	uint64_t *full = cx->full;
+	uint32_t phase0 = cx->phase0, phase1 = cx->phase1;
+	int st_issue = cx->st_issue, cur_label = cx->cur_label;
+	unsigned long long tested = 0, nan_pairs = 0;
+	unsigned binned = 0;
+
+	int pend_n = 0, pend_st = 0, pend_label = -1, pend_codes = 0;
+	auto consume = [&]() {
+		if (pend_label != cur_label) {  // candidates of another jackknife region: flush the private slots
+			if (cur_label >= 0)
+				binned += flush_slots_rmu<UNITW>(cx->fc, acc, cx->jk, dead, cx->pe, cx->pw, rw.ra, cx->rb, n_mu, cx->ns, cur_label);
+			cur_label = pend_label;
+		}
+		const int cu_ = pend_codes & 3, cv_ = (pend_codes >> 2) & 3, cl_ = (pend_codes >> 4) & 3;
+		if (pend_st == 0) {
+			mbar_wait(&full[0], phase0);
+			phase0 ^= 1u;
+		} else {
+			mbar_wait(&full[1], phase1);
+			phase1 ^= 1u;
+		}
+		const int n_mine = (pend_n - half + (1 << hlog) - 1) >> hlog;  // candidates half, half + hsplit, ... of the chunk
+		if (!dead) tested += (unsigned long long)n_mine;
+		const uint32_t cb = ring_u32 + (uint32_t)pend_st * (uint32_t)(CH_RMU * sizeof(Cand)) + (uint32_t)half * (uint32_t)sizeof(Cand);
+		bool susp;
+		if (cu_ == 3 || cv_ == 3 || cl_ == 3)
+			susp = pair_loop_rmu<UNITW, LOS2, 2>(cb, n_mine, hstep, L, halfL, pu, pv, pl, a0, a1, 0.0, 0.0, 0.0, rw.lo, hi_lane, rw.thr,
+												 rw.cut, hn, tbias, n_mu, acc);
+		else if (pend_codes & 63)
+			susp = pair_loop_rmu<UNITW, LOS2, 1>(cb, n_mine, hstep, L, halfL, pu, pv, pl, a0, a1, code_shift(cu_, L),
+												 code_shift(cv_, L), code_shift(cl_, L), rw.lo, hi_lane, rw.thr, rw.cut, hn, tbias,
+												 n_mu, acc);
+		else
+			susp = pair_loop_rmu<UNITW, LOS2, 0>(cb, n_mine, hstep, L, halfL, pu, pv, pl, a0, a1, 0.0, 0.0, 0.0, rw.lo, hi_lane, rw.thr,
+												 rw.cut, hn, tbias, n_mu, acc);
+		if (__any_sync(0xffffffffu, susp))
+			slow_pairs_rmu<UNITW, LOS2>(susp, cb, n_mine, cx->periodic, L, halfL, pu, pv, pl, a0, a1, rw, hi_lane, hn, tbias, n_mu,
+										cx->thr2, acc, hstep, nan_pairs);
+		__syncwarp();  // every lane is done with the stage before it is refilled
+	};
+
+	while (mask) {
+		const int e = __ffs(mask) - 1;
+		mask &= mask - 1u;
+		const int d_lab = __shfl_sync(0xffffffffu, lab, e), d_codes = __shfl_sync(0xffffffffu, codes, e);
+		const int d_sA = __shfl_sync(0xffffffffu, sA, e), d_eA = __shfl_sync(0xffffffffu, eA, e);
+		const int d_sB = __shfl_sync(0xffffffffu, sB, e), d_eB = __shfl_sync(0xffffffffu, eB, e);
+#pragma unroll 1
+		for (int piece = 0; piece < 2; piece++) {
+			int s = piece ? d_sB : d_sA;
+			const int en = piece ? d_eB : d_eA;
+			const int pc = (d_codes & 15) | (((d_codes >> (4 + 2 * piece)) & 3) << 4);
+			while (s < en) {
+				const int rest = en - s, nch = (rest + CH_RMU - 1) / CH_RMU;  // equal chunks (66 -> 33 + 33, not 64 + 2)
+				const int n = (rest + nch - 1) / nch;
+				if (lane == 0) {
+					const uint32_t bytes = (uint32_t)n * (uint32_t)sizeof(Cand);
+					mbar_expect_tx(&full[st_issue], bytes);
+					bulk_load(ring + (size_t)st_issue * CH_RMU, cand + s, bytes, &full[st_issue]);
+				}
+				if (pend_n > 0) consume();
+				pend_n = n;
+				pend_st = st_issue;
+				pend_label = d_lab;
+				pend_codes = pc;
+				st_issue ^= 1;
+				s += n;
+			}
+		}
+	}
+	if (pend_n > 0) consume();
+	cx->phase0 = phase0;
+	cx->phase1 = phase1;
+	cx->st_issue = st_issue;
+	cx->cur_label = cur_label;
+	cx->tested += tested;
+	cx->binned += binned;
+	cx->nan_pairs += nan_pairs;
+}
 
 template <bool UNITW, bool LOS2>
 __global__ void __launch_bounds__(TP, MIA_MIN_CTAS) k_tiled_rmu(const TiledArgs a) {
@@ -321,23 +629,44 @@ __global__ void __launch_bounds__(TP, MIA_MIN_CTAS) k_tiled_rmu(const TiledArgs 
 	const double L = P.L, halfL = P.halfL;
 	const int n_mu = P.n_2, w_r = a.w_r, ns = w_r * n_mu;
 	const int nz = a.nz;
-	const double hn = 0.5 * (double)n_mu, tbias = hn + 6145.0;
+	// a warp works on spt = 32 / hsplit shape galaxies; lane group `half` takes every hsplit-th candidate of a chunk
+	const int hsplit = a.hsplit, spt = 32 / hsplit;
+	const int sidx = lane & (spt - 1);
 
 	// ---- shared memory carve-up ------------------------------------------------------------------------------------
 	Cand *ring = reinterpret_cast<Cand *>(smem);  // [warp][stage][CH_RMU]
 	int *nlist_all = reinterpret_cast<int *>(smem + sizeof(Cand) * TW * STAGES * CH_RMU);
-	uint64_t *full = reinterpret_cast<uint64_t *>(nlist_all + TW * MAX_NEIGH);  // [warp][stage]
+	uint64_t *full = reinterpret_cast<uint64_t *>(nlist_all + TW * MAX_NEIGH_RMU);  // [warp][stage]
 	double *thr2_s = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(full) + 256);
 	unsigned char *accbase = reinterpret_cast<unsigned char *>(thr2_s) + 768;
 	const uint32_t acc_u32 = smem_u32(accbase);
 	Cand *my_ring = ring + (size_t)warp * STAGES * CH_RMU;
-	uint64_t *my_full = full + warp * STAGES;
-	int *nlist = nlist_all + warp * MAX_NEIGH;
-	const uint32_t my_ring_u32 = smem_u32(my_ring);
-	PrivAcc acc;
-	acc.a2 = acc_u32 + (uint32_t)tid * 16u;
-	acc.aw = acc_u32 + (uint32_t)NS_RMU * TP * 16u + (uint32_t)tid * 8u;
-	acc.ac = acc_u32 + (uint32_t)NS_RMU * TP * (UNITW ? 16u : 24u) + (uint32_t)tid * 4u;
+	int *nlist = nlist_all + warp * MAX_NEIGH_RMU;
+
+	RmuCtx cx;
+	cx.a2 = acc_u32 + (uint32_t)tid * 16u;
+	cx.aw = acc_u32 + (uint32_t)NS_RMU * TP * 16u + (uint32_t)tid * 8u;
+	cx.ac = acc_u32 + (uint32_t)NS_RMU * TP * (UNITW ? 16u : 24u) + (uint32_t)tid * 4u;
+	cx.ring_u32 = smem_u32(my_ring);
+	cx.ring = my_ring;
+	cx.full = full + warp * STAGES;
+	cx.cand = a.cand;
+	cx.thr2 = thr2_s;
+	cx.hstep = (uint32_t)hsplit * (uint32_t)sizeof(Cand);
+	cx.hlog = hsplit == 4 ? 2 : (hsplit == 2 ? 1 : 0);
+	cx.half = lane / spt;
+	cx.L = L;
+	cx.halfL = halfL;
+	cx.periodic = periodic;
+	cx.n_mu = n_mu;
+	cx.ns = ns;
+	cx.hn = 0.5 * (double)n_mu;
+	cx.tbias = cx.hn + 6145.0;
+	cx.cut = P.rp2_cut;
+	cx.phase0 = cx.phase1 = 0u;
+	cx.st_issue = 0;
+	cx.cur_label = -1;
+	cx.tested = cx.binned = cx.nan_pairs = 0ull;
 
 	if (tid == 0) {
 		for (int s = 0; s < TW * STAGES; s++) mbar_init(&full[s], 1);
@@ -347,9 +676,9 @@ __global__ void __launch_bounds__(TP, MIA_MIN_CTAS) k_tiled_rmu(const TiledArgs 
 	for (int e = tid; e <= P.n_2; e += blockDim.x) thr2_s[e] = P.thr2[e];
 #pragma unroll 1
 	for (int s = 0; s < NS_RMU; s++) {
-		sts_v2(acc.a2 + (uint32_t)s * TP * 16u, 0.0, 0.0);
-		if (!UNITW) sts_f64(acc.aw + (uint32_t)s * TP * 8u, 0.0);
-		sts_u32(acc.ac + (uint32_t)s * TP * 4u, 0u);
+		sts_v2(cx.a2 + (uint32_t)s * TP * 16u, 0.0, 0.0);
+		if (!UNITW) sts_f64(cx.aw + (uint32_t)s * TP * 8u, 0.0);
+		sts_u32(cx.ac + (uint32_t)s * TP * 4u, 0u);
 	}
 	__syncthreads();  // the only CTA-wide synchronisation
 
@@ -381,36 +710,53 @@ __global__ void __launch_bounds__(TP, MIA_MIN_CTAS) k_tiled_rmu(const TiledArgs 
 	}
 
 	const size_t part = (size_t)(blockIdx.x * TW + warp) * (size_t)a.A.rows * nb;
-	FlushCtx fc;
-	fc.pcnt = a.A.cnt + part;
-	fc.pddw = a.A.ddw + part;
-	fc.psp = a.A.sp + part;
-	fc.psc = a.A.sc + part;
-	fc.flags = a.flags;
-	fc.n_2 = P.n_2;
-	fc.nb = nb;
-	fc.J = J;
-	fc.num_jk = P.num_jk;
+	cx.fc.pcnt = a.A.cnt + part;
+	cx.fc.pddw = a.A.ddw + part;
+	cx.fc.psp = a.A.sp + part;
+	cx.fc.psc = a.A.sc + part;
+	cx.fc.flags = a.flags;
+	cx.fc.n_2 = P.n_2;
+	cx.fc.nb = nb;
+	cx.fc.J = J;
+	cx.fc.num_jk = P.num_jk;
 
-	uint32_t phase0 = 0u, phase1 = 0u;
-	int st_issue = 0;
-	unsigned long long tested = 0, binned = 0, nan_pairs = 0;
 	const double TN = P.r2_thr[P.n_r];
 	const double cs = L / P.ncu, reach = sqrt(TN) * (1.0 + 1e-6);
 	const int n_win = (P.n_r + w_r - 1) / w_r;
 	// line-of-sight regions: when the slabs are aligned with the jackknife sub-boxes, candidates are visited region by
 	// region so that the label of consecutive chunks changes as rarely as possible
-	const int n_lr = (a.n_side > 1 && nz % a.n_side == 0) ? a.n_side : 1;
+	const int n_lr = a.n_lr;
 	const int lr_cells = nz / n_lr;
 	const double eps_l = 1e-9 * L;
+
+	// image code of an axis for the whole warp: shapes in [b0, b1], candidates in [cmin, cmax]; fl(shape - candidate) is
+	// monotone in both, so the two extreme differences bracket every pair's
+	auto axis_code = [&](double b0, double b1, double cmin, double cmax) -> int {
+		if (!periodic) return 0;
+		const double lo = __dsub_rn(b0, cmax), hi = __dsub_rn(b1, cmin);
+		if (lo >= -halfL && hi <= halfL) return 0;
+		if (lo > halfL) return 1;   // every pair wraps down: sep -= L (measure_m_box_jk.py:420)
+		if (hi < -halfL) return 2;  // every pair wraps up (:421)
+		return 3;
+	};
+	// distance of the point x from the interval [cmin, cmax] under the image of `code` (3: nearest of the three images)
+	auto gap = [&](double x, double cmin, double cmax, int code) -> double {
+		if (code == 3) {
+			double g = fmax(0.0, fmax(cmin - x, x - cmax));
+			g = fmin(g, fmax(0.0, fmax((cmin + L) - x, x - (cmax + L))));
+			return fmin(g, fmax(0.0, fmax((cmin - L) - x, x - (cmax - L))));
+		}
+		const double sh = code == 1 ? L : (code == 2 ? -L : 0.0);  // candidates seen at c + sh
+		return fmax(0.0, fmax((cmin + sh) - x, x - (cmax + sh)));
+	};
 
 	for (int task = task0; task < task1; task++) {
 		const int col = a.task_col[task];
 		const int np = a.task_n[task];
-		const bool dead = lane >= np;
+		const bool dead = sidx >= np;
 		Prim p;
 		if (!dead) {
-			p = a.prim[a.task_first[task] + lane];
+			p = a.prim[a.task_first[task] + sidx];
 		} else {
 			p.u = p.v = p.l = 0.0;
 			p.w = 0.0;
@@ -420,31 +766,66 @@ __global__ void __launch_bounds__(TP, MIA_MIN_CTAS) k_tiled_rmu(const TiledArgs 
 			p.jk = 0;
 			p.orig = -1;
 		}
-		const double pe = p.w * p.e;
-		const int nn = build_neighbour_list(nlist, col, P.ncu, P.ncv, P.ku, P.kv, periodic, a.n_side, cs, reach);
+		cx.pu = p.u;
+		cx.pv = p.v;
+		cx.pl = p.l;
+		cx.a0 = p.a0;
+		cx.a1 = p.a1;
+		cx.pe = p.w * p.e;
+		cx.pw = p.w;
+		cx.jk = p.jk;
+		cx.dead = dead ? 1 : 0;
+		int nn = build_neighbour_list_rmu(nlist, reinterpret_cast<int2 *>(my_ring), col, a.ratio, P.ncu, P.ncv, P.ku, periodic,
+										  a.n_side, cs, reach);
+		// bounding box of the warp's shape galaxies
+		const double bu0 = warp_min_f64(dead ? INFINITY : p.u), bu1 = warp_max_f64(dead ? -INFINITY : p.u);
+		const double bv0 = warp_min_f64(dead ? INFINITY : p.v), bv1 = warp_max_f64(dead ? -INFINITY : p.v);
+		const double sl0 = warp_min_f64(dead ? INFINITY : p.l), sl1 = warp_max_f64(dead ? -INFINITY : p.l);
 
 		for (int q = 0; q < n_win; q++) {
 			// ---- accumulation window q: r bins [ra, rb] counted from the top -----------------------------------------------
 			const int rb = P.n_r - 1 - q * w_r, ra = (rb - w_r + 1 > 0) ? rb - w_r + 1 : 0;
-			RmuWindow rw;
-			rw.ra = ra;
-			rw.lo_b = __double_as_longlong(P.r2_thr[ra]);
-			rw.hi_b = __double_as_longlong(P.r2_thr[rb + 1]);
-			rw.thr_b = (ra + 1 <= rb) ? __double_as_longlong(P.r2_thr[ra + 1]) : 0x7ff0000000000000ll;
-			rw.cut_b = __double_as_longlong(P.rp2_cut);
 			const double win_hi = P.r2_thr[rb + 1];
-			const long long hi_lane_b = dead ? 0ll : rw.hi_b;  // dead lanes never pass the range test
+			cx.ra = ra;
+			cx.rb = rb;
+			cx.lo = P.r2_thr[ra];
+			cx.hi = win_hi;
+			cx.thr = (ra + 1 <= rb) ? P.r2_thr[ra + 1] : INFINITY;
+			cx.hi_lane = dead ? -1.0 : win_hi;  // dead lanes never pass the range test
 			const double reach_q = sqrt(win_hi) * (1.0 + 1e-9);
 
-			auto flush = [&](int jkD) {
-				binned += flush_slots_rmu<UNITW>(fc, acc, p.jk, dead, pe, p.w, ra, rb, n_mu, ns, jkD);
-			};
+			// ---- keep only the neighbour columns the warp's bounding box can reach in this window (windows shrink, so the
+			// list is compacted in place) ------------------------------------------------------------------------------------
+			{
+				int kept = 0;
+				for (int base = 0; base < nn; base += 32) {
+					const int c_ = (base + lane < nn) ? nlist[base + lane] : -1;
+					bool keep = false;
+					if (c_ >= 0) {
+						const ColInfo ci = a.colinfo[c_];
+						const int cu_ = axis_code(bu0, bu1, ci.umin, ci.umax), cv_ = axis_code(bv0, bv1, ci.vmin, ci.vmax);
+						// box to box under the warp's image of the column (straddling: always keep)
+						auto box_gap = [&](double b0, double b1, double cmin, double cmax, int code) -> double {
+							if (code == 3) return 0.0;
+							const double sh = code == 1 ? L : (code == 2 ? -L : 0.0);
+							return fmax(0.0, fmax((cmin + sh) - b1, b0 - (cmax + sh)));
+						};
+						const double gu_ = box_gap(bu0, bu1, ci.umin, ci.umax, cu_), gv_ = box_gap(bv0, bv1, ci.vmin, ci.vmax, cv_);
+						keep = (gu_ * gu_ + gv_ * gv_) * (1.0 - 1e-9) < win_hi;
+					}
+					const unsigned m = __ballot_sync(0xffffffffu, keep);
+					__syncwarp();
+					if (keep) nlist[kept + __popc(m & ((1u << lane) - 1u))] = c_;
+					kept += __popc(m);
+				}
+				__syncwarp();
+				nn = kept;
+			}
 
 			// line-of-sight regions the warp can reach at all in this window
 			int lr_first = 0, lr_count = n_lr;
 			if (n_lr > 1) {
-				const double wl0 = warp_min_f64(dead ? INFINITY : p.l) - reach_q - eps_l;
-				const double wl1 = warp_max_f64(dead ? -INFINITY : p.l) + reach_q + eps_l;
+				const double wl0 = sl0 - reach_q - 2.0 * eps_l, wl1 = sl1 + reach_q + 2.0 * eps_l;
 				if (wl1 - wl0 < L) {
 					const int c0 = (int)floor(wl0 * P.inv_cl), c1 = (int)floor(wl1 * P.inv_cl);  // may lie outside [0, nz)
 					const int r0 = (int)floor((double)c0 / (double)lr_cells), r1 = (int)floor((double)c1 / (double)lr_cells);
@@ -455,288 +836,149 @@ __global__ void __launch_bounds__(TP, MIA_MIN_CTAS) k_tiled_rmu(const TiledArgs 
 				}
 			}
 
-			// ---- chunk generator: region -> neighbour column -> segment of slabs -> batch of 32 cells -> label run -> chunk
-			int g_lri = 0;                        // regions done
-			int g_R0 = 0, g_R1 = -1;              // slab range of the current region
-			int g_ci = nn;                        // next neighbour column (nn: open the next region first)
-			int g_xy = 0;
-			double g_su = 0.0, g_sv = 0.0;
-			long long g_colbase = 0;
-			int g_seg_next = 0, g_seg_last = -1;  // current segment of slabs (inclusive)
-			int g_seg2_lo = 0, g_seg2_hi = -1;    // pending second segment
-			long long d_start = 0, d_end = 0;     // per lane: candidate range of one cell of the batch
-			int d_label = -1, d_nlab = 0;
-			unsigned g_runs = 0u, g_ne = 0u;
-			int g_batch_c0 = 0;
-			long long g_pos = 0, g_run_end = 0, g_cell_end = 0;
-			int g_label = -1, g_cl0 = 0, g_cl1 = 0;
-
-			auto next_chunk = [&](ChunkRmu &c) -> bool {
-				for (;;) {
-					if (g_pos < g_run_end) {
-						const int rest = (int)((g_run_end - g_pos < 1000000) ? (g_run_end - g_pos) : 1000000);
-						const int nch = (rest + CH_RMU - 1) / CH_RMU;
-						c.start = g_pos;
-						c.n = (rest + nch - 1) / nch;
-						c.label = g_label;
-						c.xy = g_xy;
-						c.cl0 = g_cl0;
-						c.cl1 = g_cl1;
-						g_pos += c.n;
-						return true;
-					}
-					if (g_pos < g_cell_end) {  // next label run of a cell that holds several labels
-						g_label = a.cand_jk[g_pos];
-						long long qq = g_pos + 1;
-						while (qq < g_cell_end && a.cand_jk[qq] == g_label) qq++;
-						g_run_end = qq;
-						continue;
-					}
-					if (g_runs) {  // next run of the batch
-						const int e = __ffs(g_runs) - 1;
-						g_runs &= g_runs - 1u;
-						const int nx = g_runs ? __ffs(g_runs) - 1 : 32;
-						const unsigned below = g_ne & (nx >= 32 ? 0xffffffffu : ((1u << nx) - 1u));
-						const int last = 31 - __clz(below);  // e itself is non-empty and below nx
-						g_pos = __shfl_sync(0xffffffffu, d_start, e);
-						g_cell_end = __shfl_sync(0xffffffffu, d_end, last);
-						g_label = __shfl_sync(0xffffffffu, d_label, e);
-						const int nlab = __shfl_sync(0xffffffffu, d_nlab, e);
-						g_cl0 = g_batch_c0 + e;
-						g_cl1 = g_batch_c0 + last;
-						g_run_end = g_cell_end;
-						if (nlab > 1) g_run_end = g_pos;  // a cell with several labels: split it into its label runs (above)
-						continue;
-					}
-					if (g_seg_next <= g_seg_last) {  // next batch of up to 32 cells of the segment
-						const int nbatch = (g_seg_last - g_seg_next + 1 < 32) ? (g_seg_last - g_seg_next + 1) : 32;
-						d_start = d_end = 0;
-						d_label = -1;
-						d_nlab = 0;
-						if (lane < nbatch) {
-							const long long cc = g_colbase + g_seg_next + lane;
-							d_start = a.cell_start[cc];
-							d_end = a.cell_start[cc + 1];
-							const CellInfo *ci = a.cinfo + cc;
-							d_label = ci->label;
-							d_nlab = ci->nlab;
-						}
-						const unsigned ne = __ballot_sync(0xffffffffu, d_end > d_start);
-						const unsigned below = ne & ((1u << lane) - 1u);
-						const int prev = below ? 31 - __clz(below) : 0;
-						const int prev_label = __shfl_sync(0xffffffffu, d_label, prev);
-						const int prev_nlab = __shfl_sync(0xffffffffu, d_nlab, prev);
-						const bool boundary = (d_end > d_start) &&
-											  (!below || d_label != prev_label || d_nlab > 1 || prev_nlab > 1);
-						g_runs = __ballot_sync(0xffffffffu, boundary);
-						g_ne = ne;
-						g_batch_c0 = g_seg_next;
-						g_seg_next += nbatch;
-						continue;
-					}
-					if (g_seg2_lo <= g_seg2_hi) {
-						g_seg_next = g_seg2_lo;
-						g_seg_last = g_seg2_hi;
-						g_seg2_hi = -1;
-						g_seg2_lo = 0;
-						continue;
-					}
-					if (g_ci >= nn) {  // next line-of-sight region
-						if (g_lri >= lr_count) return false;
-						int r = lr_first + g_lri;
-						if (r >= n_lr) r -= n_lr;
-						g_lri++;
-						g_R0 = r * lr_cells;
-						g_R1 = (n_lr > 1) ? g_R0 + lr_cells - 1 : nz - 1;
-						g_ci = 0;
-						continue;
-					}
-					// ---- open the next neighbour column: per-lane image shifts, culling, range of slabs ---------------------
-					const int ncol_ = nlist[g_ci++];
-					const ColInfo ci = a.colinfo[ncol_];
-					double ulo = __dsub_rn(p.u, ci.umax), uhi = __dsub_rn(p.u, ci.umin);
-					double vlo = __dsub_rn(p.v, ci.vmax), vhi = __dsub_rn(p.v, ci.vmin);
-					bool strad = false;
-					double su = 0.0, sv = 0.0;
-					if (periodic) {
-						if (!(ulo >= -halfL && uhi <= halfL)) {
-							if (ulo > halfL) {  // every pair of this lane with the column wraps down
-								ulo = __dsub_rn(ulo, L);
-								uhi = __dsub_rn(uhi, L);
-								su = -L;
-							} else if (uhi < -halfL) {
-								ulo = __dadd_rn(ulo, L);
-								uhi = __dadd_rn(uhi, L);
-								su = L;
-							} else {
-								strad = true;
-							}
-						}
-						if (!(vlo >= -halfL && vhi <= halfL)) {
-							if (vlo > halfL) {
-								vlo = __dsub_rn(vlo, L);
-								vhi = __dsub_rn(vhi, L);
-								sv = -L;
-							} else if (vhi < -halfL) {
-								vlo = __dadd_rn(vlo, L);
-								vhi = __dadd_rn(vhi, L);
-								sv = L;
-							} else {
-								strad = true;
-							}
+			for (int lri = 0; lri < lr_count; lri++) {
+				int g_r = lr_first + lri;
+				if (g_r >= n_lr) g_r -= n_lr;
+				const int R0 = g_r * lr_cells, R1 = (n_lr > 1) ? R0 + lr_cells - 1 : nz - 1;
+				for (int base = 0; base < nn; base += 32) {
+					// ---- ROUND: 32 neighbour columns, one per lane --------------------------------------------------------
+					const int r_c = (base + lane < nn) ? nlist[base + lane] : -1;
+					ColInfo ci;
+					ci.umin = ci.vmin = INFINITY;
+					ci.umax = ci.vmax = -INFINITY;
+					if (r_c >= 0) ci = a.colinfo[r_c];
+					const int cu_ = axis_code(bu0, bu1, ci.umin, ci.umax), cv_ = axis_code(bv0, bv1, ci.vmin, ci.vmax);
+					// slabs within sqrt(r_hi^2 - d_uv^2) of some shape of the warp: every shape (broadcast by shuffles)
+					// against this lane's column, in single precision rounded outwards (a superset is all that is needed)
+					float lmin_f = INFINITY, lmax_f = -INFINITY;
+					for (int i = 0; i < np; i++) {
+						const double xu = __shfl_sync(0xffffffffu, p.u, i), xv = __shfl_sync(0xffffffffu, p.v, i);
+						const double xl = __shfl_sync(0xffffffffu, p.l, i);
+						const double gu = gap(xu, ci.umin, ci.umax, cu_), gv = gap(xv, ci.vmin, ci.vmax, cv_);
+						const double g2 = (gu * gu + gv * gv) * (1.0 - 1e-9);
+						if (g2 < win_hi) {
+							const double dl = (double)(__fsqrt_ru(__double2float_ru(win_hi - g2)) * 1.000001f) + eps_l;
+							lmin_f = fminf(lmin_f, __double2float_rd(xl - dl));
+							lmax_f = fmaxf(lmax_f, __double2float_ru(xl + dl));
 						}
 					}
-					const double mu = ulo > 0.0 ? ulo : (uhi < 0.0 ? -uhi : 0.0);
-					const double mv = vlo > 0.0 ? vlo : (vhi < 0.0 ? -vhi : 0.0);
-					const double d2 = strad ? 0.0 : __dadd_rn(__dmul_rn(mu, mu), __dmul_rn(mv, mv));
-					const bool need = !dead && (d2 < win_hi);
-					if (!__any_sync(0xffffffffu, need)) continue;
-					// slabs within sqrt(r_hi^2 - d_uv^2) of some shape of the warp
-					double lmin = INFINITY, lmax = -INFINITY;
-					if (need) {
-						const double dl = sqrt(win_hi - d2) * (1.0 + 1e-9) + eps_l;
-						lmin = p.l - dl;
-						lmax = p.l + dl;
-					}
-					lmin = warp_min_f64(lmin);
-					lmax = warp_max_f64(lmax);
-					int sa0, sa1, sb0 = 0, sb1 = -1;
-					if (!periodic) {
-						sa0 = cell_index(lmin, P.inv_cl, nz);
-						sa1 = cell_index(lmax, P.inv_cl, nz);
-						if (lmax < 0.0 || lmin >= L) continue;
-					} else if (!(lmax - lmin < L)) {
-						sa0 = 0;
-						sa1 = nz - 1;
-					} else {
-						bool wrapped = false;
-						double x0 = lmin, x1 = lmax;
-						if (x0 < 0.0) {
-							x0 += L;
-							wrapped = true;
-						}
-						if (x1 >= L) {
-							x1 -= L;
-							wrapped = true;
-						}
-						const int ca = cell_index(x0, P.inv_cl, nz), cb_ = cell_index(x1, P.inv_cl, nz);
-						if (!wrapped) {
-							sa0 = ca;
-							sa1 = cb_;
-						} else if (cb_ >= ca - 1) {
+					int r_sA = 0, r_eA = 0, r_sB = 0, r_eB = 0, r_lab = -2, r_codes = 0, r_slA = 0, r_slB = 0;
+					if (r_c >= 0 && lmin_f <= lmax_f) {
+						const double lmin = (double)lmin_f, lmax = (double)lmax_f;
+						int sa0, sa1, sb0 = 0, sb1 = -1;
+						bool none = false;
+						if (!periodic) {
+							sa0 = cell_index(lmin, P.inv_cl, nz);
+							sa1 = cell_index(lmax, P.inv_cl, nz);
+							none = (lmax < 0.0 || lmin >= L);
+						} else if (!(lmax - lmin < L)) {
 							sa0 = 0;
 							sa1 = nz - 1;
 						} else {
-							sa0 = ca;
-							sa1 = nz - 1;
-							sb0 = 0;
-							sb1 = cb_;
+							bool wrapped = false;
+							double x0 = lmin, x1 = lmax;
+							if (x0 < 0.0) {
+								x0 += L;
+								wrapped = true;
+							}
+							if (x1 >= L) {
+								x1 -= L;
+								wrapped = true;
+							}
+							const int ca = cell_index(x0, P.inv_cl, nz), cb_ = cell_index(x1, P.inv_cl, nz);
+							if (!wrapped) {
+								sa0 = ca;
+								sa1 = cb_;
+							} else if (cb_ >= ca - 1) {
+								sa0 = 0;
+								sa1 = nz - 1;
+							} else {
+								sa0 = ca;
+								sa1 = nz - 1;
+								sb0 = 0;
+								sb1 = cb_;
+							}
+						}
+						// intersect with the current line-of-sight region
+						sa0 = sa0 > R0 ? sa0 : R0;
+						sa1 = sa1 < R1 ? sa1 : R1;
+						sb0 = sb0 > R0 ? sb0 : R0;
+						sb1 = sb1 < R1 ? sb1 : R1;
+						const long long cb0 = (long long)r_c * nz;
+						int clA = 0, clB = 0;
+						if (!none && sa0 <= sa1) {
+							r_sA = (int)a.cell_start[cb0 + sa0];
+							r_eA = (int)a.cell_start[cb0 + sa1 + 1];
+							r_slA = sa0 | (sa1 << 16);
+							clA = axis_code(sl0, sl1, a.slab_lo[sa0], a.slab_hi[sa1]);
+						}
+						if (!none && sb0 <= sb1) {
+							r_sB = (int)a.cell_start[cb0 + sb0];
+							r_eB = (int)a.cell_start[cb0 + sb1 + 1];
+							r_slB = sb0 | (sb1 << 16);
+							clB = axis_code(sl0, sl1, a.slab_lo[sb0], a.slab_hi[sb1]);
+						}
+						r_codes = cu_ | (cv_ << 2) | (clA << 4) | (clB << 6);
+						if (r_eA > r_sA || r_eB > r_sB) r_lab = a.colreg[(long long)r_c * n_lr + g_r];
+					}
+					const unsigned m_simple = __ballot_sync(0xffffffffu, r_lab >= 0);
+					if (m_simple) process_round<UNITW, LOS2>(&cx, r_sA, r_eA, r_sB, r_eB, r_lab, r_codes, m_simple);
+					// ---- column-regions holding several labels (cells cut by a jackknife face: unaligned grids only) ------------
+					unsigned m_cplx = __ballot_sync(0xffffffffu, r_lab == -1);
+					while (m_cplx) {
+						const int e = __ffs(m_cplx) - 1;
+						m_cplx &= m_cplx - 1u;
+						const long long cb0 = (long long)__shfl_sync(0xffffffffu, r_c, e) * nz;
+						const int codes_e = __shfl_sync(0xffffffffu, r_codes, e);
+						const int slA = __shfl_sync(0xffffffffu, r_slA, e), slB = __shfl_sync(0xffffffffu, r_slB, e);
+						const int okA = __shfl_sync(0xffffffffu, (int)(r_eA > r_sA), e), okB = __shfl_sync(0xffffffffu, (int)(r_eB > r_sB), e);
+						for (int piece = 0; piece < 2; piece++) {
+							if (!(piece ? okB : okA)) continue;
+							const int s0_ = (piece ? slB : slA) & 0xffff, s1_ = (piece ? slB : slA) >> 16;
+							const int pc = (codes_e & 15) | (((codes_e >> (4 + 2 * piece)) & 3) << 4);
+							for (int sb = s0_; sb <= s1_; sb += 32) {  // 32 cells at a time, one per lane
+								int c_s = 0, c_e = 0, c_lab = -2, c_nlab = 0;
+								if (sb + lane <= s1_) {
+									c_s = (int)a.cell_start[cb0 + sb + lane];
+									c_e = (int)a.cell_start[cb0 + sb + lane + 1];
+									const CellInfo *cinf = a.cinfo + cb0 + sb + lane;
+									c_nlab = (c_e > c_s) ? cinf->nlab : 0;
+									c_lab = (c_nlab == 1) ? cinf->label : -2;
+								}
+								const unsigned m1 = __ballot_sync(0xffffffffu, c_nlab == 1);
+								if (m1) process_round<UNITW, LOS2>(&cx, c_s, c_e, 0, 0, c_lab, pc, m1);
+								unsigned mm = __ballot_sync(0xffffffffu, c_nlab > 1);
+								while (mm) {  // a cell with several labels: one label run at a time
+									const int f = __ffs(mm) - 1;
+									mm &= mm - 1u;
+									int pos = __shfl_sync(0xffffffffu, c_s, f);
+									const int end = __shfl_sync(0xffffffffu, c_e, f);
+									while (pos < end) {
+										const int lb = a.cand_jk[pos];
+										int qq = pos + 1;
+										while (qq < end && a.cand_jk[qq] == lb) qq++;
+										process_round<UNITW, LOS2>(&cx, pos, qq, 0, 0, lb, pc, 1u);  // lane 0 carries the run
+										pos = qq;
+									}
+								}
+							}
 						}
 					}
-					// intersect with the current line-of-sight region
-					sa0 = sa0 > g_R0 ? sa0 : g_R0;
-					sa1 = sa1 < g_R1 ? sa1 : g_R1;
-					sb0 = sb0 > g_R0 ? sb0 : g_R0;
-					sb1 = sb1 < g_R1 ? sb1 : g_R1;
-					if (sa0 > sa1 && sb0 > sb1) continue;
-					g_xy = __any_sync(0xffffffffu, !dead && strad) ? 2
-						   : (__any_sync(0xffffffffu, !dead && (su != 0.0 || sv != 0.0)) ? 1 : 0);
-					g_su = su;
-					g_sv = sv;
-					g_colbase = (long long)ncol_ * nz;
-					if (sa0 <= sa1) {
-						g_seg_next = sa0;
-						g_seg_last = sa1;
-						g_seg2_lo = sb0;
-						g_seg2_hi = sb1;
-					} else {
-						g_seg_next = sb0;
-						g_seg_last = sb1;
-						g_seg2_lo = 0;
-						g_seg2_hi = -1;
-					}
-				}
-			};
-
-			// ---- software pipeline: issue the bulk copy of chunk k+1, then work on chunk k ----------------------------------
-			ChunkRmu pend, nxt;
-			double pend_su = 0.0, pend_sv = 0.0, nxt_su = 0.0, nxt_sv = 0.0;
-			pend.n = 0;
-			pend.label = -1;
-			int pend_st = 0, cur_label = -1;
-			bool more = true;
-			while (more || pend.n > 0) {
-				bool got = false;
-				if (more) {
-					got = next_chunk(nxt);
-					more = got;
-					nxt_su = g_su;
-					nxt_sv = g_sv;
-				}
-				if (got && lane == 0) {
-					const uint32_t bytes = (uint32_t)nxt.n * (uint32_t)sizeof(Cand);
-					mbar_expect_tx(&my_full[st_issue], bytes);
-					bulk_load(my_ring + (size_t)st_issue * CH_RMU, a.cand + nxt.start, bytes, &my_full[st_issue]);
-				}
-				const int lab = (pend.n > 0) ? pend.label : -2;
-				if (lab != cur_label) {
-					if (cur_label >= 0) flush(cur_label);
-					cur_label = lab;
-				}
-				if (pend.n > 0) {
-					// line-of-sight image of this lane for the chunk (its candidates lie in [zlo, zhi])
-					const double zlo = a.slab_lo[pend.cl0], zhi = a.slab_hi[pend.cl1];
-					double sl = 0.0;
-					bool zst = false;
-					if (periodic) {
-						const double lo = __dsub_rn(p.l, zhi), hi = __dsub_rn(p.l, zlo);
-						if (!(lo >= -halfL && hi <= halfL)) {
-							if (lo > halfL) sl = -L;
-							else if (hi < -halfL) sl = L;
-							else zst = true;
-						}
-					}
-					const bool gen = (pend.xy == 2) || __any_sync(0xffffffffu, !dead && zst);
-					const bool shifted =
-						(pend.xy == 1) || __any_sync(0xffffffffu, !dead && sl != 0.0);
-					if (pend_st == 0) {
-						mbar_wait(&my_full[0], phase0);
-						phase0 ^= 1u;
-					} else {
-						mbar_wait(&my_full[1], phase1);
-						phase1 ^= 1u;
-					}
-					if (!dead) tested += (unsigned long long)pend.n;
-					const uint32_t cb = my_ring_u32 + (uint32_t)pend_st * (uint32_t)(CH_RMU * sizeof(Cand));
-					bool susp;
-					if (gen)
-						susp = pair_loop_rmu<UNITW, LOS2, 2>(cb, pend.n, L, halfL, p.u, p.v, p.l, p.a0, p.a1, 0.0, 0.0, 0.0, rw,
-															 hi_lane_b, hn, tbias, n_mu, acc);
-					else if (shifted)
-						susp = pair_loop_rmu<UNITW, LOS2, 1>(cb, pend.n, L, halfL, p.u, p.v, p.l, p.a0, p.a1, pend_su, pend_sv, sl,
-															 rw, hi_lane_b, hn, tbias, n_mu, acc);
-					else
-						susp = pair_loop_rmu<UNITW, LOS2, 0>(cb, pend.n, L, halfL, p.u, p.v, p.l, p.a0, p.a1, 0.0, 0.0, 0.0, rw,
-															 hi_lane_b, hn, tbias, n_mu, acc);
-					if (__any_sync(0xffffffffu, susp))
-						slow_pairs_rmu<UNITW, LOS2>(susp, cb, pend.n, periodic, L, halfL, p.u, p.v, p.l, p.a0, p.a1, rw, hi_lane_b,
-													hn, tbias, n_mu, thr2_s, acc, nan_pairs);
-					__syncwarp();
-				}
-				if (got) {
-					pend = nxt;
-					pend_su = nxt_su;
-					pend_sv = nxt_sv;
-					pend_st = st_issue;
-					st_issue ^= 1;
-				} else {
-					pend.n = 0;
 				}
 			}
-			if (cur_label >= 0) flush(cur_label);
+			// ---- end of the window: flush what is left in the private slots --------------------------------------------------
+			if (cx.cur_label >= 0) {
+				PrivAcc acc;
+				acc.a2 = cx.a2;
+				acc.aw = cx.aw;
+				acc.ac = cx.ac;
+				cx.binned += flush_slots_rmu<UNITW>(cx.fc, acc, p.jk, dead, cx.pe, p.w, ra, rb, n_mu, ns, cx.cur_label);
+				cx.cur_label = -1;
+			}
 		}
 	}
 
+	unsigned long long tested = cx.tested, binned = cx.binned, nan_pairs = cx.nan_pairs;
 	for (int o = 16; o > 0; o >>= 1) {
 		tested += __shfl_down_sync(0xffffffffu, tested, o);
 		binned += __shfl_down_sync(0xffffffffu, binned, o);
