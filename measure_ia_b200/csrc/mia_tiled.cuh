@@ -49,6 +49,9 @@ constexpr int TW = TP / 32;      // warps per CTA (independent workers)
 #ifndef MIA_MIN_CTAS
 #define MIA_MIN_CTAS 3
 #endif
+#ifndef MIA_RPPI_ALIGN
+#define MIA_RPPI_ALIGN 1
+#endif
 constexpr int CH = MIA_CH;       // candidates per staged chunk
 constexpr int STAGES = 2;        // per-warp double buffering
 constexpr int MAX_NEIGH = 128;   // neighbour columns per task
@@ -207,6 +210,17 @@ inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g,
 		if (!(nz_d >= 1.0) || nz_d > 512.0) return false;
 		nz = (int)nz_d;
 		if (!build_lut(p, cfg)) return false;
+		// align columns and slabs with the jackknife sub-boxes: a cell then carries one label (no label runs to scan, fewer
+		// and larger chunks, fewer flushes)
+		{
+			const char *ev = getenv("MIA_RPPI_ALIGN");
+			const int mode = ev ? atoi(ev) : MIA_RPPI_ALIGN;
+			if (mode > 0 && n_side > 1 && nc >= 4 * n_side) {
+				nc = (mode == 1) ? nc / n_side * n_side : (nc + n_side - 1) / n_side * n_side;
+				const int nz2 = (nz + n_side - 1) / n_side * n_side;
+				if (nz2 <= 512) nz = nz2;
+			}
+		}
 	} else {
 		// (r, mu_r): 3-D search with cubic cells aligned with the jackknife sub-boxes (a cell then carries one label)
 		if (!rmu_supported(p, cfg.w_r)) return false;

@@ -43,6 +43,9 @@ constexpr int MAX_NEIGH_RMU = 384;  // neighbour (candidate) columns per task
 #ifndef MIA_RMU_HSPLIT
 #define MIA_RMU_HSPLIT 1
 #endif
+#ifndef MIA_UNROLL_RMU
+#define MIA_UNROLL_RMU 4
+#endif
 
 inline size_t tiled_rmu_smem_bytes(bool unit_w) {
 	const size_t fixed = sizeof(Cand) * TW * STAGES * CH_RMU + sizeof(int) * TW * MAX_NEIGH_RMU + 256 + 768;
@@ -263,9 +266,8 @@ __device__ __forceinline__ RmuApprox rmu_approx(double du, double dv, double dz,
 	const double mu = dz * y;
 	const double t = fma(mu, hn, tbias);  // (mu + 1) n_mu / 2 + 6145, rounded to 40 fractional bits
 	const unsigned thi = (unsigned)__double2hiint(t), tlo = (unsigned)__double2loint(t);
-	int idx = (int)((thi & 0xFFFFFu) >> 8) - 2049;
-	idx = idx < 0 ? 0 : idx;
-	r.idx = idx > n_mu - 1 ? n_mu - 1 : idx;
+	const unsigned raw = (thi & 0xFFFFFu) >> 8;  // 2049 + bin
+	r.idx = (int)min(max(raw, 2049u), 2048u + (unsigned)n_mu) - 2049;
 	const unsigned lo2 = tlo + MU_BAND;
 	const unsigned h8 = (thi + (lo2 < MU_BAND ? 1u : 0u)) & 0xFFu;
 	const bool susp_mu = (h8 == 0u) && (lo2 < 2u * MU_BAND);
@@ -305,20 +307,20 @@ __device__ __forceinline__ bool pair_loop_rmu(uint32_t cb, int n, uint32_t hstep
 		return (fabs(d) > halfL) ? __dsub_rn(d, c) : d;  // c = copysign(L, d): measure_m_box_jk.py:419-421
 	};
 	bool lane_susp = false;
+	// current candidate, the next one and the one after it (prefetch distance 2).  The prefetch may run up to two
+	// candidates past the end of the chunk: that is still inside this CTA's shared memory and the values are never used.
 	double cu, cv, cl, cw, mu_, mv_, ml_, mw_;
 	lds_v2(cu, cv, cb);
 	lds_v2(cl, cw, cb + 16);
-	{
-		const uint32_t a1_ = cb + (uint32_t)((1 < n) ? 1 : 0) * hstep;
-		lds_v2(mu_, mv_, a1_);
-		lds_v2(ml_, mw_, a1_ + 16);
-	}
-	MIA_UNROLL_PRAGMA(MIA_UNROLL)
+	lds_v2(mu_, mv_, cb + hstep);
+	lds_v2(ml_, mw_, cb + hstep + 16);
+	uint32_t na = cb + 2u * hstep;
+	MIA_UNROLL_PRAGMA(MIA_UNROLL_RMU)
 	for (int j = 0; j < n; j++) {
-		const uint32_t na = cb + (uint32_t)((j + 2 < n) ? (j + 2) : (n - 1)) * hstep;
 		double nu, nv, nl, nw;
 		lds_v2(nu, nv, na);
 		lds_v2(nl, nw, na + 16);
+		na += hstep;
 		double du = __dsub_rn(pu, cu), dv = __dsub_rn(pv, cv), dz = __dsub_rn(pl, cl);  // shape minus position, :418
 		if (VAR == 2) {
 			du = wrap(du);

@@ -68,8 +68,8 @@ def test_reference_fixture(torch_cuda, tmp_path, name, kernel):
 	box = run_box(meta, data, masks, kw, out, kernel)
 	got = read_all(out)
 	pu.assert_datasets_match(got, want, exact_counts=not meta["catalogue"].get("weights"), label=f"{name}[{kernel}]: ")
-	if kernel == "auto" and meta["measurement"]["kind"] == "w":
-		assert box.last_stats["kernel"] == 2, "the tiled kernel should cover every (r_p, Pi) fixture"
+	if kernel == "auto":
+		assert box.last_stats["kernel"] == 2, "the tiled kernels should cover every (r_p, Pi) and (r, mu_r) fixture"
 	dd_key = [k for k in want if k.endswith("xi_gg/All_DD")][0]
 	if not meta["catalogue"].get("weights"):
 		assert box.last_stats["binned"] == int(want[dd_key].sum())
@@ -93,6 +93,8 @@ def test_against_oracle_100k(torch_cuda, oracle, tmp_path, geom, kind, kernel):
 	want.pop("__meta__/n_tested")
 	assert np.array_equal(box.last_result["count"], count)
 	pu.assert_datasets_match(read_all(out), want, exact_counts=(geom == "rppi"), label=f"{geom}[{kernel}]: ")
+	if kernel == "auto":
+		assert box.last_stats["kernel"] == 2
 
 
 def _host_call(torch, oracle, data, geom, num_jk, boxsize, n_r, n_2, kernel=0, shard=(0, 1)):
