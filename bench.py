@@ -28,6 +28,8 @@ WORKLOADS = {
 	"cfg2": (1_000_000, 205.0, "w", 27, 10, 8),
 	"cfg2_default_bins": (1_000_000, 205.0, "w", 27, 8, 20),
 	"cfg3": (1_000_000, 205.0, "multipoles", 27, 10, 8),
+	"cfg3_default_bins": (1_000_000, 205.0, "multipoles", 27, 8, 20),
+	"cfg4_multipoles": (10_000_000, 300.0, "multipoles", 64, 10, 8),
 	"cfg4": (10_000_000, 300.0, "w", 64, 10, 8),
 	"small": (100_000, 205.0, "w", 27, 10, 8),
 }

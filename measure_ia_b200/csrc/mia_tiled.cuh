@@ -712,20 +712,20 @@ __device__ __forceinline__ bool pair_loop(uint32_t cb, int n, int periodic, doub
 		return (fabs(d) > halfL) ? __dsub_rn(d, sl) : d;  // sl = copysign(L, d)
 	};
 	bool lane_susp = false;
-	double cu, cv, cl, cw, mu_, mv_, ml_, mw_;  // current candidate and the one after it (prefetch distance 2)
+	// current candidate, the next one and the one after it (prefetch distance 2).  The prefetch may run up to two
+	// candidates past the end of the chunk: that is still inside this CTA's shared memory and the values are never used.
+	double cu, cv, cl, cw, mu_, mv_, ml_, mw_;
 	lds_v2(cu, cv, cb);
 	lds_v2(cl, cw, cb + 16);
-	{
-		const uint32_t a1_ = cb + (uint32_t)((1 < n) ? 1 : 0) * (uint32_t)sizeof(Cand);
-		lds_v2(mu_, mv_, a1_);
-		lds_v2(ml_, mw_, a1_ + 16);
-	}
+	lds_v2(mu_, mv_, cb + (uint32_t)sizeof(Cand));
+	lds_v2(ml_, mw_, cb + (uint32_t)sizeof(Cand) + 16);
+	uint32_t na = cb + 2u * (uint32_t)sizeof(Cand);
 	MIA_UNROLL_PRAGMA(MIA_UNROLL)
 	for (int j = 0; j < n; j++) {
-		const uint32_t na = cb + (uint32_t)((j + 2 < n) ? (j + 2) : (n - 1)) * (uint32_t)sizeof(Cand);
 		double nu, nv, nl, nw;
 		lds_v2(nu, nv, na);
 		lds_v2(nl, nw, na + 16);
+		na += (uint32_t)sizeof(Cand);
 		double du = __dsub_rn(pu, cu), dv = __dsub_rn(pv, cv), dz = __dsub_rn(pl, cl);  // shape minus position, :401
 		if (GEN) {
 			if (periodic) {
