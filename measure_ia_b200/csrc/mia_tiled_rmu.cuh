@@ -621,7 +621,7 @@ __device__ __noinline__ void process_round(RmuCtx *cx, int sA, int eA, int sB, i
 }
 
 template <bool UNITW, bool LOS2>
-__global__ void __launch_bounds__(TP, MIA_MIN_CTAS) k_tiled_rmu(const TiledArgs a) {
+__global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	const DevParams &P = a.P;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
