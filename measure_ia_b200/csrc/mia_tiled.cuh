@@ -49,6 +49,9 @@ constexpr int TW = TP / 32;      // warps per CTA (independent workers)
 #ifndef MIA_MIN_CTAS
 #define MIA_MIN_CTAS 3
 #endif
+#ifndef MIA_TASKS_PER_WARP
+#define MIA_TASKS_PER_WARP 32.0
+#endif
 #ifndef MIA_RPPI_ALIGN
 #define MIA_RPPI_ALIGN 1
 #endif
@@ -124,7 +127,7 @@ inline size_t tiled_rmu_smem_bytes(bool unit_w);
 inline int launch_rmu(const TiledArgs &a, bool unit_w, bool los2, int n_ctas, size_t smem, cudaStream_t st);
 inline bool plan_rmu_grid(const mia_params *p, int n_side, TiledConfig &cfg, int &nc, int &nz, int &k);
 inline int rmu_fill_tasks(const TiledArgs &a, const int64_t *prim_cell_start, const int64_t *cell_start, const int32_t *task_off,
-						  int ncol_s, int nzs, int k, int32_t *task_col, int64_t *task_first, int32_t *task_n,
+						  int ncol_s, int nzs, int k, int split, int32_t *task_col, int64_t *task_first, int32_t *task_n,
 						  int32_t *task_slab, unsigned long long *task_cost, int32_t *n_tasks, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1364,11 +1367,13 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &gc, const GridDi
 	// when there are few tasks per worker warp (small catalogues, many GPUs) cut each task along the line of sight
 	const int spt = 32 / cfg.hsplit;  // shape galaxies per warp task
 	const double tasks_est = (double)nS / (double)spt + 0.5 * (double)ncol;
-	const double want = 8.0 * (double)cfg.n_ctas * TW * (double)shard.count;
+	// (measured, profiles/r01_tuning.md: finer tasks help the (r_p, Pi) kernel's tail, the (r, mu_r) kernel pays more per task)
+	const char *tpw_env = getenv("MIA_TASKS_PER_WARP");
+	const double tasks_per_warp = tpw_env ? atof(tpw_env) : (cfg.geom == MIA_GEOM_RMU ? 8.0 : MIA_TASKS_PER_WARP);
+	const double want = tasks_per_warp * (double)cfg.n_ctas * TW * (double)shard.count;
 	int split = (int)ceil(want / (tasks_est > 1.0 ? tasks_est : 1.0));
 	split = split < 1 ? 1 : (split > MAX_SPLIT ? MAX_SPLIT : split);
-	if (split > cfg.nz) split = cfg.nz;
-	if (cfg.geom == MIA_GEOM_RMU) split = 1;  // a warp's shapes are local along the line of sight: nothing to cut
+	if (cfg.geom != MIA_GEOM_RMU && split > cfg.nz) split = cfg.nz;  // (r_p, Pi): parts = ranges of slabs; (r, mu_r): of columns
 	k_col_chunks<<<(unsigned)((ncol + 1 + 255) / 256), 256, 0, st>>>(prim_cell_start, ncol, nzs, split, w.col_chunks, spt);
 	MIA_CUDA_CHECK(cudaGetLastError());
 	size_t cb = w.cub_bytes;
@@ -1378,7 +1383,7 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &gc, const GridDi
 	a.ratio = cfg.ratio;
 	a.hsplit = cfg.hsplit;
 	if (cfg.geom == MIA_GEOM_RMU) {
-		const int rc = rmu_fill_tasks(a, prim_cell_start, G.cell_start, w.task_off, (int)ncol, nzs, P.ku, w.task_col, w.task_first,
+		const int rc = rmu_fill_tasks(a, prim_cell_start, G.cell_start, w.task_off, (int)ncol, nzs, P.ku, split, w.task_col, w.task_first,
 									  w.task_n, w.task_slab, w.task_cost, w.n_tasks, st);
 		if (rc) return rc;
 	} else {

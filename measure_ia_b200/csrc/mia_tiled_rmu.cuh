@@ -44,7 +44,7 @@ constexpr int MAX_NEIGH_RMU = 384;  // neighbour (candidate) columns per task
 #define MIA_RMU_HSPLIT 1
 #endif
 #ifndef MIA_UNROLL_RMU
-#define MIA_UNROLL_RMU 4
+#define MIA_UNROLL_RMU 2
 #endif
 
 inline size_t tiled_rmu_smem_bytes(bool unit_w) {
@@ -162,7 +162,7 @@ __device__ __forceinline__ int rmu_n_offsets(int ratio, int ncu, int ncv, int k)
 // One warp task = up to spt consecutive shape galaxies of one shape column; cost = shapes x candidates in reach.
 __global__ void k_fill_tasks_rmu(const int64_t *__restrict__ prim_cell_start, const int64_t *__restrict__ cell_start,
 								 const int32_t *__restrict__ task_off, int ncu, int ncv, int nz, int ratio, int nzs, int spt,
-								 int k, int periodic, double cs, double reach, int32_t *__restrict__ task_col,
+								 int split, int k, int periodic, double cs, double reach, int32_t *__restrict__ task_col,
 								 int64_t *__restrict__ task_first, int32_t *__restrict__ task_n,
 								 int32_t *__restrict__ task_slab, unsigned long long *__restrict__ task_cost,
 								 int32_t *__restrict__ n_tasks) {
@@ -181,24 +181,26 @@ __global__ void k_fill_tasks_rmu(const int64_t *__restrict__ prim_cell_start, co
 		if (nc_ >= 0) W += (unsigned long long)(cell_start[(int64_t)(nc_ + 1) * nz] - cell_start[(int64_t)nc_ * nz]);
 	}
 	int t = task_off[c];
-	for (int64_t p = p0; p < p1; p += spt, t++) {
+	for (int64_t p = p0; p < p1; p += spt) {
 		const int n = (int)((p1 - p < spt) ? (p1 - p) : spt);
-		task_col[t] = (int32_t)c;
-		task_first[t] = p;
-		task_n[t] = n;
-		task_slab[2 * t] = 0;
-		task_slab[2 * t + 1] = nz;
-		task_cost[t] = (unsigned long long)n * W + 1ull;
+		for (int part = 0; part < split; part++, t++) {  // the same shapes against consecutive parts of the neighbour list
+			task_col[t] = (int32_t)c;
+			task_first[t] = p;
+			task_n[t] = n;
+			task_slab[2 * t] = part;
+			task_slab[2 * t + 1] = split;
+			task_cost[t] = (unsigned long long)n * W / (unsigned long long)split + 1ull;
+		}
 	}
 }
 
 inline int rmu_fill_tasks(const TiledArgs &a, const int64_t *prim_cell_start, const int64_t *cell_start, const int32_t *task_off,
-						  int ncol_s, int nzs, int k, int32_t *task_col, int64_t *task_first, int32_t *task_n,
+						  int ncol_s, int nzs, int k, int split, int32_t *task_col, int64_t *task_first, int32_t *task_n,
 						  int32_t *task_slab, unsigned long long *task_cost, int32_t *n_tasks, cudaStream_t st) {
 	const DevParams &P = a.P;
 	const double cs = P.L / P.ncu, reach = sqrt(P.r2_thr[P.n_r]) * (1.0 + 1e-6);
 	k_fill_tasks_rmu<<<(unsigned)((ncol_s + 127) / 128), 128, 0, st>>>(prim_cell_start, cell_start, task_off, P.ncu, P.ncv, P.ncl,
-																	   a.ratio, nzs, 32 / a.hsplit, k, P.periodic, cs, reach, task_col,
+																	   a.ratio, nzs, 32 / a.hsplit, split, k, P.periodic, cs, reach, task_col,
 																	   task_first, task_n, task_slab, task_cost, n_tasks);
 	return (int)cudaGetLastError();
 }
@@ -779,6 +781,15 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 		cx.dead = dead ? 1 : 0;
 		int nn = build_neighbour_list_rmu(nlist, reinterpret_cast<int2 *>(my_ring), col, a.ratio, P.ncu, P.ncv, P.ku, periodic,
 										  a.n_side, cs, reach);
+		// when tasks are scarce (small catalogues, many GPUs) a task covers one of `nparts` consecutive parts of the list
+		int noff = 0;
+		{
+			const int part = a.task_slab[2 * task], nparts = a.task_slab[2 * task + 1];
+			if (nparts > 1) {
+				noff = (int)((long long)nn * part / nparts);
+				nn = (int)((long long)nn * (part + 1) / nparts) - noff;
+			}
+		}
 		// bounding box of the warp's shape galaxies
 		const double bu0 = warp_min_f64(dead ? INFINITY : p.u), bu1 = warp_max_f64(dead ? -INFINITY : p.u);
 		const double bv0 = warp_min_f64(dead ? INFINITY : p.v), bv1 = warp_max_f64(dead ? -INFINITY : p.v);
@@ -801,7 +812,7 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 			{
 				int kept = 0;
 				for (int base = 0; base < nn; base += 32) {
-					const int c_ = (base + lane < nn) ? nlist[base + lane] : -1;
+					const int c_ = (base + lane < nn) ? nlist[noff + base + lane] : -1;
 					bool keep = false;
 					if (c_ >= 0) {
 						const ColInfo ci = a.colinfo[c_];
@@ -822,6 +833,7 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 				}
 				__syncwarp();
 				nn = kept;
+				noff = 0;  // the compacted list starts at the front
 			}
 
 			// line-of-sight regions the warp can reach at all in this window
