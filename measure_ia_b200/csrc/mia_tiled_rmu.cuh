@@ -43,6 +43,9 @@ constexpr int MAX_NEIGH_RMU = 384;  // neighbour (candidate) columns per task
 #ifndef MIA_RMU_HSPLIT
 #define MIA_RMU_HSPLIT 1
 #endif
+#ifndef MIA_RMU_LMUL
+#define MIA_RMU_LMUL 3
+#endif
 #ifndef MIA_UNROLL_RMU
 #define MIA_UNROLL_RMU 2
 #endif
@@ -116,7 +119,14 @@ inline bool plan_rmu_grid(const mia_params *p, int n_side, TiledConfig &cfg, int
 		}
 		if (div == 1) return false;
 	}
-	nz = nc;
+	// slabs thinner than the columns are wide: the streamed range of a column is trimmed to whole slabs, so thin slabs
+	// cost nothing (ranges are contiguous) and tighten the culling along the line of sight
+	int lmul = env_int("MIA_RMU_LMUL", MIA_RMU_LMUL);
+	if (lmul < 1) lmul = 1;
+	while (lmul > 1 && ((long long)nc * lmul > 512 ||
+						(unsigned long long)nc * nc * nc * lmul * 4ull * (unsigned long long)(p->num_jk > 0 ? p->num_jk : 1) > (1ull << 31)))
+		lmul--;
+	nz = nc * lmul;
 	cfg.hsplit = hs;
 	cfg.n_lr = (n_side > 1 && nz % n_side == 0) ? n_side : 1;
 	return true;
