@@ -9,6 +9,7 @@
 #include "mia_grid.cuh"
 #include "mia_tiled.cuh"
 #include "mia_tiled_rmu.cuh"
+#include "mia_tiled_rppi2.cuh"
 
 using namespace mia;
 
@@ -84,8 +85,11 @@ int make_plan(const mia_params *p, int64_t nD, int64_t nS, Plan &pl) {
 	if (pl.kernel == MIA_KERNEL_GENERAL) {
 		plan_general_grid(p, pl);
 		pl.n_partials = 1;
+		pl.tiled.v2 = 0;
+		pl.tiled.ratio = 1;
 	} else {
 		pl.n_partials = pl.tiled.n_partials;
+		pl.g.order = pl.tiled.v2 ? 1 : 0;  // row-streaming (r_p, Pi) kernel: candidates sorted by (u row, slab, v cell)
 	}
 	const uint64_t nkeys = (uint64_t)pl.g.ncell() * 4ull * (uint64_t)J;  // x4: the shape sample's sub-cell ordering
 	if (nkeys > (1ull << 31)) return MIA_ERR_UNSUPPORTED;
@@ -347,6 +351,7 @@ int mia_paircount(const mia_params *params, const mia_sample *D, const mia_sampl
 	// ---- shape sample -> sorted primaries ---------------------------------------------------------------------------
 	GridDims g_prim = pl.g;
 	g_prim.sub = (pl.kernel == MIA_KERNEL_TILED) ? 2 : 1;
+	g_prim.order = 0;
 	if (pl.kernel == MIA_KERNEL_TILED && pl.tiled.ratio > 1) {  // (r, mu_r): the shape sample is sorted on coarser columns
 		g_prim.ncu /= pl.tiled.ratio;
 		g_prim.ncv /= pl.tiled.ratio;

@@ -19,6 +19,8 @@ struct GridDims {
 	double inv_cu, inv_cv, inv_cl;
 	int jk_rows;  // max(num_jk, 1)
 	int sub;      // shape sample only: each cell's galaxies are ordered by sub x sub projected sub-cell (compact warps)
+	int order;    // 0: cell = (cu, cv, cl) -- the slabs of a column are contiguous; 1: cell = (cu, cl, cv) -- the cells of a
+	              // (u row, slab) are contiguous along v (row-streaming (r_p, Pi) kernel)
 	int64_t ncell() const { return (int64_t)ncu * ncv * ncl; }
 	int64_t nsorted_cells() const { return ncell() * (sub > 1 ? sub * sub : 1); }
 };
@@ -32,7 +34,7 @@ __global__ void k_make_keys(const double *__restrict__ pos, const int32_t *__res
 	// the reference's periodic KDTree requires 0 <= x < L (scipy raises otherwise); NaNs fail here as well
 	if (!(u >= 0.0 && u < L && v >= 0.0 && v < L && l >= 0.0 && l < L)) atomicExch(range_err, 1);
 	int cu = cell_index(u, g.inv_cu, g.ncu), cv = cell_index(v, g.inv_cv, g.ncv), cl = cell_index(l, g.inv_cl, g.ncl);
-	uint32_t cell = (uint32_t)((cu * g.ncv + cv) * g.ncl + cl);
+	uint32_t cell = g.order ? (uint32_t)((cu * g.ncl + cl) * g.ncv + cv) : (uint32_t)((cu * g.ncv + cv) * g.ncl + cl);
 	if (g.sub > 1) {
 		int su = (int)((u * g.inv_cu - cu) * g.sub), sv = (int)((v * g.inv_cv - cv) * g.sub);
 		su = su < 0 ? 0 : (su >= g.sub ? g.sub - 1 : su);

@@ -52,6 +52,12 @@ constexpr int TW = TP / 32;      // warps per CTA (independent workers)
 #ifndef MIA_TASKS_PER_WARP
 #define MIA_TASKS_PER_WARP 32.0
 #endif
+#ifndef MIA_SWP
+#define MIA_SWP 0
+#endif
+#ifndef MIA_RPPI_V2
+#define MIA_RPPI_V2 1
+#endif
 #ifndef MIA_RPPI_ALIGN
 #define MIA_RPPI_ALIGN 1
 #endif
@@ -87,6 +93,7 @@ struct TiledConfig {
 	int ratio;       // (r, mu_r): a shape column is ratio x ratio candidate columns wide
 	int hsplit;      // (r, mu_r): a warp works on 32 / hsplit shape galaxies, hsplit candidates at a time
 	int n_lr;        // (r, mu_r): line-of-sight regions (= jackknife sub-boxes per side when the slabs are aligned with them)
+	int v2;          // (r_p, Pi): row-streaming kernel (mia_tiled_rppi2.cuh); n_lr then counts the regions along v
 	int n_partials;  // accumulator copies = worker warps
 	int n_ctas;
 	int num_sms;
@@ -117,7 +124,8 @@ struct TiledArgs {
 	int lut_hi0, lut_shift, lut_n;
 	Accum A;
 	int nz, n_side, n_workers, shard_index, shard_count, max_tasks;
-	int w_r, ratio, hsplit, n_lr;  // (r, mu_r) kernel only
+	int w_r, ratio, hsplit, n_lr;  // (r, mu_r) kernel (ratio, n_lr: also the row-streaming (r_p, Pi) kernel)
+	const double *vlo, *vhi;       // row-streaming (r_p, Pi) kernel: envelopes of the v coordinates per column index cv
 	int *flags;
 };
 
@@ -126,6 +134,15 @@ inline bool rmu_supported(const mia_params *p, int &w_r);
 inline size_t tiled_rmu_smem_bytes(bool unit_w);
 inline int launch_rmu(const TiledArgs &a, bool unit_w, bool los2, int n_ctas, size_t smem, cudaStream_t st);
 inline bool plan_rmu_grid(const mia_params *p, int n_side, TiledConfig &cfg, int &nc, int &nz, int &k);
+// defined in mia_tiled_rppi2.cuh
+struct TiledWorkspace;
+inline bool plan_rppi2_grid(const mia_params *p, int n_side, TiledConfig &cfg, int &nc, int nz, int &k);
+inline size_t tiled_rppi2_smem_bytes(bool unit_w);
+inline int rppi2_prepare(const TiledConfig &cfg, const GridDims &g, const TiledWorkspace &w, cudaStream_t st);
+inline int rppi2_fill_tasks(const TiledArgs &a, const int64_t *prim_cell_start, const int64_t *cell_start, const int32_t *task_off,
+							int ncol_s, int nzs, int k, int split, int32_t *task_col, int64_t *task_first, int32_t *task_n,
+							int32_t *task_slab, unsigned long long *task_cost, int32_t *n_tasks, cudaStream_t st);
+inline int launch_rppi2(const TiledArgs &a, bool unit_w, int n_ctas, size_t smem, cudaStream_t st);
 inline int rmu_fill_tasks(const TiledArgs &a, const int64_t *prim_cell_start, const int64_t *cell_start, const int32_t *task_off,
 						  int ncol_s, int nzs, int k, int split, int32_t *task_col, int64_t *task_first, int32_t *task_n,
 						  int32_t *task_slab, unsigned long long *task_cost, int32_t *n_tasks, cudaStream_t st);
@@ -196,6 +213,7 @@ inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g,
 	cfg.ratio = 1;
 	cfg.hsplit = 1;
 	cfg.n_lr = 1;
+	cfg.v2 = 0;
 	// columns: about a quarter of the search radius wide
 	int nc = (int)floor(L / (reach / 4.0));
 	if (nc > 2048) nc = 2048;
@@ -232,11 +250,30 @@ inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g,
 	if (p->geometry == MIA_GEOM_RMU) {
 		if (!plan_rmu_grid(p, n_side, cfg, nc, nz, k)) return false;
 	} else {
-		const double cs = L / nc;
-		k = (int)ceil(reach / cs);
-		if (k < 1) k = 1;
-		const bool all_mode = (2 * k + 1 >= nc);
-		if (all_mode ? ((long long)nc * nc > MAX_NEIGH) : ((2 * k + 1) * (2 * k + 1) > MAX_NEIGH)) return false;
+		// Row-streaming kernel (mia_tiled_rppi2.cuh) or cell-by-cell kernel?  Measured (profiles/r01_tuning.md): rows win when
+		// a (row, slab) range holds many candidates -- dense catalogues, slabs not too thin; 1 = decide by that estimate,
+		// 0 = never, 2 = always.
+		const char *ev = getenv("MIA_RPPI_V2");
+		int v2 = ev ? atoi(ev) : MIA_RPPI_V2;
+		int div2 = 0;
+		if (v2 == 1) {
+			const double rho = (double)nD / (L * L * L);
+			auto piece = [&](int d) { return rho * (reach / d) * (1.6 * reach) * (L / nz); };  // candidates per streamed range
+			if (nz > 16) v2 = 0;
+			else if (piece(10) >= 100.0) div2 = 10;
+			else if (piece(6) >= 15.0) div2 = 6;
+			else v2 = 0;
+		}
+		if (v2) {  // row-streaming kernel: finer columns, coarser shape columns
+			cfg.w_r = div2;  // (r_p, Pi): carries the chosen cells per r_max to plan_rppi2_grid (0 = default)
+			if (!plan_rppi2_grid(p, n_side, cfg, nc, nz, k)) return false;
+		} else {
+			const double cs = L / nc;
+			k = (int)ceil(reach / cs);
+			if (k < 1) k = 1;
+			const bool all_mode = (2 * k + 1 >= nc);
+			if (all_mode ? ((long long)nc * nc > MAX_NEIGH) : ((2 * k + 1) * (2 * k + 1) > MAX_NEIGH)) return false;
+		}
 	}
 	g.ncu = g.ncv = nc;
 	g.ncl = nz;
@@ -264,6 +301,7 @@ struct TiledWorkspace {
 	CellInfo *cinfo;
 	ColInfo *colinfo;
 	int32_t *colreg;
+	double *vlo, *vhi;
 	double *slab_lo, *slab_hi;
 	int32_t *col_chunks, *task_off, *task_col, *task_n, *task_slab, *n_tasks;
 	int64_t *task_first;
@@ -293,8 +331,11 @@ inline TiledWorkspace carve_tiled(const TiledConfig &cfg, const GridDims &g, voi
 	};
 	const int64_t ncell = g.ncell(), ncol = (int64_t)g.ncu * g.ncv;
 	w.cinfo = (CellInfo *)take(sizeof(CellInfo) * ncell);
-	w.colinfo = (ColInfo *)take(cfg.geom == MIA_GEOM_RMU ? sizeof(ColInfo) * ncol : 0);
-	w.colreg = (int32_t *)take(cfg.geom == MIA_GEOM_RMU ? sizeof(int32_t) * ncol * cfg.n_lr : 0);
+	const int64_t n_info = cfg.geom == MIA_GEOM_RMU ? ncol : (cfg.v2 ? (int64_t)g.ncu * cfg.nz : 0);  // columns / (u row, slab)
+	w.colinfo = (ColInfo *)take(sizeof(ColInfo) * n_info);
+	w.colreg = (int32_t *)take(sizeof(int32_t) * n_info * cfg.n_lr);
+	w.vlo = (double *)take(cfg.v2 ? sizeof(double) * g.ncv : 0);
+	w.vhi = (double *)take(cfg.v2 ? sizeof(double) * g.ncv : 0);
 	w.slab_lo = (double *)take(sizeof(double) * cfg.nz);
 	w.slab_hi = (double *)take(sizeof(double) * cfg.nz);
 	w.col_chunks = (int32_t *)take(sizeof(int32_t) * (ncol + 1));
@@ -322,7 +363,8 @@ inline size_t tiled_workspace_bytes(const TiledConfig &cfg, const GridDims &g, i
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void k_cell_info(const Cand *__restrict__ cand, const int32_t *__restrict__ cand_jk,
 							const int64_t *__restrict__ cell_start, int64_t ncell, int nz, CellInfo *__restrict__ info,
-							unsigned long long *__restrict__ slab_lo, unsigned long long *__restrict__ slab_hi) {
+							unsigned long long *__restrict__ slab_lo, unsigned long long *__restrict__ slab_hi, int order = 0,
+							int ncv = 1) {
 	const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
 	if (c >= ncell) return;
 	const int64_t j0 = cell_start[c], j1 = cell_start[c + 1];
@@ -347,7 +389,7 @@ __global__ void k_cell_info(const Cand *__restrict__ cand, const int32_t *__rest
 			if (lab != prev) ci.nlab++;
 			prev = lab;
 		}
-		const int s = (int)(c % nz);
+		const int s = order ? (int)((c / ncv) % nz) : (int)(c % nz);
 		// l >= 0, so the bit pattern of (l + 0.0) is monotone in l
 		atomicMin(&slab_lo[s], (unsigned long long)__double_as_longlong(lmin + 0.0));
 		atomicMax(&slab_hi[s], (unsigned long long)__double_as_longlong(lmax + 0.0));
@@ -723,6 +765,12 @@ __device__ __forceinline__ bool pair_loop(uint32_t cb, int n, int periodic, doub
 	lds_v2(mu_, mv_, cb + (uint32_t)sizeof(Cand));
 	lds_v2(ml_, mw_, cb + (uint32_t)sizeof(Cand) + 16);
 	uint32_t na = cb + 2u * (uint32_t)sizeof(Cand);
+#if MIA_SWP
+	bool p_ok = false;  // the candidate whose accumulation is still pending
+	uint32_t p_so = 0u;
+	unsigned p_c0 = 0u;
+	double p_s0 = 0.0, p_s1 = 0.0, p_gp = 0.0, p_gc = 0.0, p_sw = 0.0, p_cw = 0.0;
+#endif
 	MIA_UNROLL_PRAGMA(MIA_UNROLL)
 	for (int j = 0; j < n; j++) {
 		double nu, nv, nl, nw;
@@ -751,11 +799,13 @@ __device__ __forceinline__ bool pair_loop(uint32_t cb, int n, int periodic, doub
 #pragma unroll
 		for (int k = 0; k < W_R - 1; k++) slot += (r2 >= rw.thr[k]) ? 2 : 0;
 		const uint32_t so = (uint32_t)slot * (uint32_t)TP;
+#if !MIA_SWP
 		// private slots: loads first, the arithmetic below hides their latency
 		double s0, s1, sw = 0.0;
 		lds_v2(s0, s1, acc.a2 + so * 16u);
 		const unsigned c0 = lds_u32(acc.ac + so * 4u);
 		if (!UNITW) sw = lds_f64(acc.aw + so * 8u);
+#endif
 		const double cr = fma(du, a0, __dmul_rn(dv, a1));   // r_p cos(phi)
 		const double sr = fma(du, a1, -__dmul_rn(dv, a0));  // r_p sin(phi) (sign irrelevant)
 		// 2 / r2: 20-bit hardware seed, one cubically convergent step y(1 + e + e^2) (relative error ~1e-17; a plain
@@ -773,6 +823,26 @@ __device__ __forceinline__ bool pair_loop(uint32_t cb, int n, int periodic, doub
 		const bool susp = ok && (gp >= 1.0 - 1e-11);  // |cos| ~ 1: the reference's NaN rule may apply -> exact path
 		lane_susp = lane_susp || susp;
 		ok = ok && !susp;
+#if MIA_SWP
+		// software pipeline of the accumulation: retire the PREVIOUS candidate (its slot was loaded one iteration ago, so
+		// the load latency is covered by a whole iteration of arithmetic), then load this candidate's slot.  Stores and
+		// loads are volatile and stay in this order, so two consecutive candidates in the same slot are handled correctly.
+		if (!UNITW) {
+			gp *= cw;
+			gc *= cw;
+			sts_f64_if(p_ok, acc.aw + p_so * 8u, p_sw + p_cw);
+		}
+		sts_v2_if(p_ok, acc.a2 + p_so * 16u, p_s0 + p_gp, p_s1 + p_gc);
+		sts_u32_if(p_ok, acc.ac + p_so * 4u, p_c0 + 1u);
+		lds_v2(p_s0, p_s1, acc.a2 + so * 16u);
+		p_c0 = lds_u32(acc.ac + so * 4u);
+		if (!UNITW) p_sw = lds_f64(acc.aw + so * 8u);
+		p_ok = ok;
+		p_so = so;
+		p_gp = gp;
+		p_gc = gc;
+		p_cw = cw;
+#else
 		if (!UNITW) {
 			gp *= cw;
 			gc *= cw;
@@ -780,6 +850,7 @@ __device__ __forceinline__ bool pair_loop(uint32_t cb, int n, int periodic, doub
 		}
 		sts_v2_if(ok, acc.a2 + so * 16u, s0 + gp, s1 + gc);
 		sts_u32_if(ok, acc.ac + so * 4u, c0 + 1u);
+#endif
 		cu = mu_;
 		cv = mv_;
 		cl = ml_;
@@ -789,6 +860,11 @@ __device__ __forceinline__ bool pair_loop(uint32_t cb, int n, int periodic, doub
 		ml_ = nl;
 		mw_ = nw;
 	}
+#if MIA_SWP
+	if (!UNITW) sts_f64_if(p_ok, acc.aw + p_so * 8u, p_sw + p_cw);
+	sts_v2_if(p_ok, acc.a2 + p_so * 16u, p_s0 + p_gp, p_s1 + p_gc);
+	sts_u32_if(p_ok, acc.ac + p_so * 4u, p_c0 + 1u);
+#endif
 	return lane_susp;
 }
 
@@ -1337,9 +1413,12 @@ inline int tiled_prepare_candidates(const TiledConfig &cfg, const GridDims &g, c
 	const int64_t ncell = g.ncell();
 	k_cell_info<<<(unsigned)((ncell + 127) / 128), 128, 0, st>>>(cand, cand_jk, cell_start, ncell, cfg.nz, w.cinfo,
 																 (unsigned long long *)w.slab_lo,
-																 (unsigned long long *)w.slab_hi);
+																 (unsigned long long *)w.slab_hi, g.order, g.ncv);
 	MIA_CUDA_CHECK(cudaGetLastError());
-	if (cfg.geom == MIA_GEOM_RMU) {
+	if (cfg.v2) {
+		const int rc = rppi2_prepare(cfg, g, w, st);
+		if (rc) return rc;
+	} else if (cfg.geom == MIA_GEOM_RMU) {
 		const int64_t ncol = (int64_t)g.ncu * g.ncv;
 		k_col_info<<<(unsigned)((ncol + 127) / 128), 128, 0, st>>>(w.cinfo, ncol, cfg.nz, cfg.n_lr, w.colinfo, w.colreg,
 																   w.slab_lo, w.slab_hi);
@@ -1382,7 +1461,11 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &gc, const GridDi
 	a.P = P;
 	a.ratio = cfg.ratio;
 	a.hsplit = cfg.hsplit;
-	if (cfg.geom == MIA_GEOM_RMU) {
+	if (cfg.v2) {
+		const int rc = rppi2_fill_tasks(a, prim_cell_start, G.cell_start, w.task_off, (int)ncol, nzs, P.ku, split, w.task_col,
+										w.task_first, w.task_n, w.task_slab, w.task_cost, w.n_tasks, st);
+		if (rc) return rc;
+	} else if (cfg.geom == MIA_GEOM_RMU) {
 		const int rc = rmu_fill_tasks(a, prim_cell_start, G.cell_start, w.task_off, (int)ncol, nzs, P.ku, split, w.task_col, w.task_first,
 									  w.task_n, w.task_slab, w.task_cost, w.n_tasks, st);
 		if (rc) return rc;
@@ -1400,8 +1483,8 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &gc, const GridDi
 	// grouping of the fp64 sums, hence every output bit, is the same for the weighted and the unit-weight kernel variants,
 	// which is what lets w = 0.5 scale the results by exactly 1/4 (reference tests/test_weights.py:34-35). ---------------
 	const bool rmu = cfg.geom == MIA_GEOM_RMU;
-	const size_t smem = rmu ? tiled_rmu_smem_bytes(unit_w) : tiled_smem_bytes(unit_w);
-	if (rmu) {
+	const size_t smem = rmu ? tiled_rmu_smem_bytes(unit_w) : (cfg.v2 ? tiled_rppi2_smem_bytes(unit_w) : tiled_smem_bytes(unit_w));
+	if (rmu || cfg.v2) {
 	} else if (unit_w) {
 		MIA_CUDA_CHECK(cudaFuncSetAttribute(k_tiled_rppi<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	} else {
@@ -1409,6 +1492,8 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &gc, const GridDi
 	}
 	a.colinfo = w.colinfo;
 	a.colreg = w.colreg;
+	a.vlo = w.vlo;
+	a.vhi = w.vhi;
 	a.n_lr = cfg.n_lr;
 	a.w_r = cfg.w_r;
 	a.cand = G.cand;
@@ -1440,6 +1525,9 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &gc, const GridDi
 	if (ev_before) MIA_CUDA_CHECK(cudaEventRecord(ev_before, st));
 	if (rmu) {
 		const int rc = launch_rmu(a, unit_w, P.los == 2, cfg.n_ctas, smem, st);
+		if (rc) return rc;
+	} else if (cfg.v2) {
+		const int rc = launch_rppi2(a, unit_w, cfg.n_ctas, smem, st);
 		if (rc) return rc;
 	} else if (unit_w) {
 		k_tiled_rppi<true><<<cfg.n_ctas, TP, smem, st>>>(a);

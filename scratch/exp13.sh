@@ -1,0 +1,14 @@
+#!/bin/bash
+run() { label=$1; shift
+  out=$(env "$@" timeout 400 python bench.py --workload $WL --steps ${ST:-3} --warmup ${WU:-2} --no-e2e --no-cpu-baseline 2>gpurun_out/exp13.err | tail -1)
+  echo "$out" | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$label', '$WL', 'ms', round(d['ms_per_step'],2), 'pairs/s', round(d['value']/1e9,1),'e9 tested', d['config']['candidates_tested_per_step'], d['config']['kernel'], 'frac', round(d['roofline']['frac'],3))" || { echo "$label FAILED"; tail -3 gpurun_out/exp13.err; }
+}
+WL=cfg2_default_bins
+run v2 X=1
+run old MIA_RPPI_V2=0
+WL=small
+run v2 X=1
+run old MIA_RPPI_V2=0
+ST=1 WU=1 WL=cfg4
+run v2 X=1
+run old MIA_RPPI_V2=0
