@@ -274,3 +274,64 @@ def test_tiled_kernel_is_bit_reproducible(torch_cuda):
 	box.measure_xi_w("a", "both", 27, temp_file_path=False)
 	for k, v in first.items():
 		assert np.array_equal(v, box.last_result[k]), k
+
+
+# ---- tiled kernels against the general kernel over awkward configurations -------------------------------------------------
+_CROSS_CASES = [
+	# n, boxsize, seed, num_jk, n_r, n_2, generator / constructor options
+	(3000, 205.0, 1, 27, 10, 8, {}),
+	(20000, 150.0, 4, 8, 6, 12, dict(los=1, weights=True)),
+	(5000, 50.0, 5, 8, 4, 4, {}),                 # tiny box: every column is a neighbour, chunks straddle +-L/2
+	(2000, 30.0, 6, 27, 5, 5, {}),                # r_max > L/2
+	(33, 50.0, 8, 8, 4, 4, {}),
+	(60000, 300.0, 10, 64, 8, 20, dict(n_shape=30000, weights=True, clustered=0.5)),
+	(30000, 205.0, 14, 27, 10, 8, dict(periodicity=False)),
+	(30000, 205.0, 13, 125, 10, 10, dict(los=0)),
+	(50000, 205.0, 15, 27, 10, 8, dict(pi_max=30.0)),
+]
+
+
+def _run_cross(kind, case, kernel):
+	from measure_ia_b200 import MeasureIABox
+	from measure_ia_b200.synthetic import uniform_box
+	n, L, seed, jk, n_r, n_2, kw = case
+	kw = dict(kw)
+	per = kw.pop("periodicity", True)
+	pi_max = kw.pop("pi_max", None)
+	data = uniform_box(n, L, seed=seed, **kw)
+	box = MeasureIABox(data, None, boxsize=L, num_bins_r=n_r, num_bins_pi=n_2, periodicity=per, pi_max=pi_max)
+	box.kernel = kernel
+	(box.measure_xi_w if kind == "w" else box.measure_xi_multipoles)("a", "both", jk, temp_file_path=False)
+	return box.last_result, box.last_stats
+
+
+def _assert_same_sums(got, want, label):
+	assert np.array_equal(got["count"], want["count"]), f"{label}: pair counts differ"
+	assert np.array_equal(got["count_jk"], want["count_jk"]), f"{label}: jackknife pair counts differ"
+	for k in ("DD", "SpD_raw", "ScD_raw", "DD_jk", "SpD_jk"):
+		a, b = np.asarray(want[k]), np.asarray(got[k])
+		if a.size:
+			tol = pu.RTOL * np.abs(a) + pu.ATOL_SCALE * np.abs(a).max()
+			assert (np.abs(a - b) <= tol).all(), f"{label}: {k} differs by {np.abs(a - b).max():.3e}"
+
+
+@pytest.mark.parametrize("mode", ["default", "rows", "cells", "split"])
+@pytest.mark.parametrize("case", _CROSS_CASES, ids=[f"n{c[0]}_L{int(c[1])}_jk{c[3]}" for c in _CROSS_CASES])
+@pytest.mark.parametrize("kind", ["w", "multipoles"])
+def test_tiled_kernels_match_general(torch_cuda, monkeypatch, kind, case, mode):
+	"""Every tiled code path (row-streaming / cell-by-cell (r_p, Pi), column-streaming (r, mu_r), tasks cut into parts as on
+	many GPUs) against the reference-exact general kernel: pair counts bit-identical, sums to 1e-10."""
+	if kind == "multipoles" and (mode in ("rows", "cells") or case[6].get("pi_max")):
+		pytest.skip("(r_p, Pi)-only variation")
+	want, st_g = _run_cross(kind, case, "general")
+	assert st_g["kernel"] == 1
+	if mode == "rows":
+		monkeypatch.setenv("MIA_RPPI_V2", "2")
+	elif mode == "cells":
+		monkeypatch.setenv("MIA_RPPI_V2", "0")
+	elif mode == "split":
+		monkeypatch.setenv("MIA_TASKS_PER_WARP", "1000")
+	got, st_t = _run_cross(kind, case, "tiled")
+	assert st_t["kernel"] == 2
+	assert st_t["binned"] == int(want["count"].sum())
+	_assert_same_sums(got, want, f"{kind}/{mode}")

@@ -212,3 +212,33 @@ def test_operator_refuses_cpu_tensors():
 	with pytest.raises(RuntimeError, match="CUDA|cuda|No CUDA|device"):
 		torch.ops.measure_ia_b200.paircount(z, None, None, z, None, None, z[:, :2].contiguous(), z[:, 0].contiguous(), thr,
 											thr, 0, 2, True, 0, 10.0, 2.0, 0.0, 0, 0, 1)
+
+
+def test_workspace_planning_runs_without_a_gpu(monkeypatch):
+	"""mia_workspace_bytes plans the grid and the kernel choice on the host only (no compute call): every configuration the
+	tiled kernels take or decline must yield a workspace size, forced-tiled requests on declined configurations must not,
+	and the size must grow with the catalogue."""
+	import torch
+	from measure_ia_b200 import MeasureIABox, ops
+	from measure_ia_b200.synthetic import uniform_box
+	lib = ops.load_library()
+	box = MeasureIABox(uniform_box(10, 205.0, seed=1), None, boxsize=205.0, num_bins_r=10, num_bins_pi=8)
+
+	def ws(geom, n, num_jk=27, kernel="auto", n_2=8):
+		b = box if n_2 == 8 else MeasureIABox(uniform_box(10, 205.0, seed=1), None, boxsize=205.0, num_bins_r=10, num_bins_pi=n_2)
+		r2_thr, thr2, rp2_cut, _ = b._thresholds_for(geom, None)
+		p = ops.make_params(ops.GEOM_RPPI if geom == "rppi" else ops.GEOM_RMU, 10, n_2, 2, True, num_jk, ops.KERNEL_NAMES[kernel],
+							205.0, float(b.r_bins[-1]), float(rp2_cut), torch.from_numpy(r2_thr), torch.from_numpy(thr2))
+		return lib.mia_workspace_bytes(ctypes.byref(p), n, n)
+
+	import ctypes
+	for geom in ("rppi", "rmu"):
+		sizes = [ws(geom, n) for n in (1000, 100000, 1000000)]
+		assert all(s > 0 for s in sizes) and sizes[0] < sizes[1] < sizes[2], (geom, sizes)
+		assert ws(geom, 100000, num_jk=0) > 0 and ws(geom, 100000, kernel="general") > 0
+	# both (r_p, Pi) kernels plan; 40 mu bins exceed the tiled (r, mu_r) kernel's private slots: auto falls back, forced fails
+	for mode in ("0", "2"):
+		monkeypatch.setenv("MIA_RPPI_V2", mode)
+		assert ws("rppi", 1000000, kernel="tiled") > 0
+	assert ws("rmu", 100000, n_2=40) > 0
+	assert ws("rmu", 100000, n_2=40, kernel="tiled") == 0
