@@ -42,7 +42,7 @@ constexpr int TW = TP / 32;      // warps per CTA (independent workers)
 #define MIA_W_R 5
 #endif
 #ifndef MIA_UNROLL
-#define MIA_UNROLL 4
+#define MIA_UNROLL 2
 #endif
 #define MIA_PRAGMA(x) _Pragma(#x)
 #define MIA_UNROLL_PRAGMA(n) MIA_PRAGMA(unroll n)
