@@ -1,4 +1,6 @@
-// mia_tiled.cuh -- the TILED (r_p, Pi) pair kernel for sm_100a: the fast, bit-reproducible path.
+// mia_tiled.cuh -- the TILED (r_p, Pi) pair kernel for sm_100a (cell-by-cell variant) and everything the tiled kernels
+// share: planning, workspace, task table, mbarrier / bulk-copy helpers, the pair loop, the flush.  The row-streaming
+// (r_p, Pi) variant lives in mia_tiled_rppi2.cuh, the (r, mu_r) kernel in mia_tiled_rmu.cuh; plan_tiled() picks.
 //
 // Replaces the hot loop of the reference, src/measureia/measure_w_box_jk.py:387-461 (and measure_w_box.py:313-365).
 //
