@@ -242,3 +242,43 @@ def test_workspace_planning_runs_without_a_gpu(monkeypatch):
 		assert ws("rppi", 1000000, kernel="tiled") > 0
 	assert ws("rmu", 100000, n_2=40) > 0
 	assert ws("rmu", 100000, n_2=40, kernel="tiled") == 0
+
+
+def test_h5lite_reuses_the_tree_it_wrote_last(tmp_path):
+	"""Re-opening a file this process wrote and nobody touched since skips the parse; changes made through the new handle
+	are written, and a file replaced on disk is parsed again."""
+	import os
+	import time
+	from measure_ia_b200 import h5lite
+	p = os.path.join(str(tmp_path), "a.hdf5")
+	f = h5lite.File(p, "a")
+	f.create_group("w/xi").create_dataset("A", data=np.arange(6.).reshape(2, 3))
+	f.close()
+	f = h5lite.File(p, "a")  # cache hit: modify a nested and a top-level member, then read back with a FRESH parse
+	assert "w/xi/A" in f
+	del f["w/xi/A"]
+	f["w/xi"].create_dataset("A", data=np.ones(4))
+	f.create_dataset("top", data=np.arange(3))
+	f.close()
+	h5lite._RECENT.clear()
+	f = h5lite.File(p, "r")
+	assert np.array_equal(f["w/xi/A"][:], np.ones(4)) and np.array_equal(f["top"][:], np.arange(3))
+	f.close()
+	f = h5lite.File(p, "a")
+	f.create_dataset("x", data=np.zeros(2))
+	f.close()
+	time.sleep(0.01)  # another writer replaces the file: the cached tree must not be used
+	q = os.path.join(str(tmp_path), "b.hdf5")
+	f2 = h5lite.File(q, "w")
+	f2.create_dataset("other", data=np.arange(5))
+	f2.close()
+	os.replace(q, p)
+	f = h5lite.File(p, "r")
+	assert list(f.keys()) == ["other"]
+	f.close()
+	f = h5lite.File(p, "a")
+	f.create_dataset("y", data=np.arange(2))
+	f.close()
+	f = h5lite.File(p, "r")  # read-only reopen right after a write: served from the cache
+	assert sorted(f.keys()) == ["other", "y"]
+	f.close()
