@@ -196,7 +196,8 @@ class Group:
 		if data is None:
 			arr = np.zeros(shape if shape is not None else (), dtype=dtype or np.float64)
 		else:
-			arr = np.asarray(data, dtype=dtype) if dtype is not None else np.asarray(data)
+			arr = np.array(data, dtype=dtype, copy=True)  # own the payload (h5py copies too): later in-place changes of the
+			# caller's array must not leak into the tree, which may be reused by the next handle on this file
 			if shape is not None:
 				arr = arr.reshape(shape)
 		if arr.dtype == np.bool_:
