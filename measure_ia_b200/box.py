@@ -320,7 +320,7 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 			w_s = d["weight_shape_sample"][masks["weight_shape_sample"]]
 			same = False
 		axis_len = np.sqrt(np.sum(axis_v ** 2, axis=1))
-		axis = (axis_v.transpose() / axis_len).transpose()
+		axis = (axis_v.transpose() / axis_len).transpose()[:, :2]
 		if ellipticity == "distortion":
 			e = (1 - q ** 2) / (1 + q ** 2)
 		elif ellipticity == "ellipticity":
@@ -391,8 +391,15 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 			pos, pos_s = pos[mk("Position")], pos_s[mk("Position_shape_sample")]
 			axis_v, q = axis_v[mk("Axis_Direction")], q[mk("q")]
 			w, w_s = w[mk("weight")], w_s[mk("weight_shape_sample")]
-		axis_len = torch.sqrt(axis_v[:, 0] * axis_v[:, 0] + axis_v[:, 1] * axis_v[:, 1])
-		axis = (axis_v / axis_len[:, None]).contiguous()
+		if axis_v.dim() != 2 or axis_v.shape[1] < 2 or pos.dim() != 2 or pos.shape[1] != 3 or pos_s.shape[1:] != pos.shape[1:]:
+			raise ValueError("Position / Position_shape_sample must be (N, 3) and Axis_Direction (N_s, >= 2) arrays")
+		# row norm over ALL columns, summed left to right like np.sum(axis_v ** 2, axis=1) (measure_w_box_jk.py:326); the
+		# pair loop reads the first two normalised components (calculate_dot_product_arrays iterates over the columns of
+		# the 2-D projected separation, measure_IA_base.py:186-205)
+		sq = axis_v[:, 0] * axis_v[:, 0]
+		for c in range(1, axis_v.shape[1]):
+			sq = sq + axis_v[:, c] * axis_v[:, c]
+		axis = (axis_v / torch.sqrt(sq)[:, None])[:, :2].contiguous()
 		if ellipticity == "distortion":
 			e = (1 - q * q) / (1 + q * q)
 		elif ellipticity == "ellipticity":

@@ -80,6 +80,15 @@ int make_plan(const mia_params *p, int64_t nD, int64_t nS, Plan &pl) {
 		} else {
 			if (pl.kernel == MIA_KERNEL_TILED) return MIA_ERR_UNSUPPORTED;
 			pl.kernel = MIA_KERNEL_GENERAL;
+			// not silent: the general kernel is ~30x slower (one thread per shape galaxy, atomics)
+			static bool warned = false;
+			if (!warned && nD * nS > 0) {
+				warned = true;
+				fprintf(stderr,
+						"libmia_b200: warning: this configuration (%s, %d x %d bins, %d jackknife regions) is outside what the "
+						"tiled kernels cover; falling back to the general kernel (about 30x slower)\n",
+						p->geometry == MIA_GEOM_RPPI ? "(r_p, Pi)" : "(r, mu_r)", p->n_r, p->n_2, p->num_jk);
+			}
 		}
 	}
 	if (pl.kernel == MIA_KERNEL_GENERAL) {
@@ -321,8 +330,15 @@ int mia_paircount(const mia_params *params, const mia_sample *D, const mia_sampl
 	A.rows = pl.rows;
 	int *flags = (int *)(ws + pl.off_flags);
 
-	// optional phase timing with CUDA events on the caller's stream
-	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+	// optional phase timing with CUDA events on the caller's stream (destroyed on every exit path)
+	struct Events {
+		cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+		~Events() {
+			for (int i = 0; i < 4; i++)
+				if (e[i]) cudaEventDestroy(e[i]);
+		}
+	} evs;
+	cudaEvent_t *ev = evs.e;
 	const bool timed = params->timings_host != nullptr;
 	if (timed) {
 		for (int i = 0; i < 4; i++) MIA_CUDA_CHECK(cudaEventCreate(&ev[i]));
@@ -439,7 +455,6 @@ int mia_paircount(const mia_params *params, const mia_sample *D, const mia_sampl
 		cudaEventElapsedTime(&t[1], ev[1], ev[2]);
 		cudaEventElapsedTime(&t[2], ev[2], ev[3]);
 		cudaEventElapsedTime(&t[3], ev[0], ev[3]);
-		for (int i = 0; i < 4; i++) cudaEventDestroy(ev[i]);
 	}
 	if (h_flags[0]) return MIA_ERR_RANGE;
 	if (h_flags[1]) return MIA_ERR_WINDOW;

@@ -103,7 +103,15 @@ def _dev_ptr(t: Optional[torch.Tensor], dtype, shape_tail=None):
 		raise RuntimeError("measure_ia_b200::paircount needs CUDA tensors (no CPU fallback)")
 	if t.dtype != dtype or not t.is_contiguous():
 		raise RuntimeError(f"expected a contiguous {dtype} tensor, got {t.dtype} (contiguous={t.is_contiguous()})")
+	if shape_tail is not None and tuple(t.shape[1:]) != tuple(shape_tail):
+		raise RuntimeError(f"expected shape (N, {', '.join(map(str, shape_tail))}), got {tuple(t.shape)}" if shape_tail
+						   else f"expected a 1-D tensor, got shape {tuple(t.shape)}")
 	return t.data_ptr()
+
+
+def _check_rows(name, t, n):
+	if t is not None and t.shape[0] != n:
+		raise RuntimeError(f"{name}: {t.shape[0]} rows, expected {n}")
 
 
 @torch.library.custom_op("measure_ia_b200::paircount", mutates_args=())
@@ -123,9 +131,13 @@ def paircount(pos_d: torch.Tensor, weight_d: Optional[torch.Tensor], jk_d: Optio
 	params = make_params(geometry, n_r, n_2, los, periodic, num_jk, kernel, boxsize, r_search, rp2_cut, r2_thr, thr2,
 						 _timing_buf)
 	f64, i32, i64 = torch.float64, torch.int32, torch.int64
-	D = MiaSample(pos_d.shape[0], _dev_ptr(pos_d, f64), _dev_ptr(weight_d, f64), _dev_ptr(jk_d, i32), None, None)
-	S = MiaSample(pos_s.shape[0], _dev_ptr(pos_s, f64), _dev_ptr(weight_s, f64), _dev_ptr(jk_s, i32),
-				  _dev_ptr(axis, f64), _dev_ptr(e, f64))
+	# shapes are validated here, at the operator boundary: the library indexes pos as [n][3] and axis as [n][2]
+	D = MiaSample(pos_d.shape[0], _dev_ptr(pos_d, f64, (3,)), _dev_ptr(weight_d, f64, ()), _dev_ptr(jk_d, i32, ()), None, None)
+	S = MiaSample(pos_s.shape[0], _dev_ptr(pos_s, f64, (3,)), _dev_ptr(weight_s, f64, ()), _dev_ptr(jk_s, i32, ()),
+				  _dev_ptr(axis, f64, (2,)), _dev_ptr(e, f64, ()))
+	for nm, t, n in (("weight_d", weight_d, D.n), ("jk_d", jk_d, D.n), ("weight_s", weight_s, S.n), ("jk_s", jk_s, S.n),
+					 ("axis", axis, S.n), ("e", e, S.n)):
+		_check_rows(nm, t, n)
 	with torch.cuda.device(dev):
 		dd_count = torch.empty((n_r, n_2), dtype=i64, device=dev)
 		dd_w, spd, scd = (torch.empty((n_r, n_2), dtype=f64, device=dev) for _ in range(3))

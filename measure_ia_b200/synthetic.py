@@ -62,3 +62,48 @@ def expected_pairs_rppi(n_pos, n_shape, boxsize, r_min, r_max, pi_lo, pi_hi):
 def expected_pairs_rmu(n_pos, n_shape, boxsize, r_min, r_max):
 	"""Expected number of binned ordered pairs for uniform randoms, (r, mu_r) geometry."""
 	return n_pos * n_shape * 4.0 / 3.0 * np.pi * (r_max ** 3 - r_min ** 3) / boxsize ** 3
+
+
+def aligned_pairs_box(n, boxsize, seed=1, los=2):
+	"""Catalogue that makes the reference's NaN rule fire (SURVEY.md section 8(a) hazard 3,
+	``measure_w_box_jk.py:411-417``): galaxy 2k+1 sits a few Mpc from galaxy 2k, and the axis of galaxy 2k is its
+	projected minimum-image separation from 2k+1 (times a random sign and length), i.e. exactly (anti)parallel.  The
+	normalised dot product then exceeds 1 by an ulp for ~10 % of those pairs; the reference zeroes e+ / ex for them and
+	still counts them in DD.  Auto-correlation (one array object for both samples)."""
+	rng = np.random.default_rng(seed)
+	n -= n % 2
+	pos = rng.random((n, 3)) * boxsize
+	off = rng.normal(size=(n // 2, 3))
+	off *= (rng.uniform(0.3, 12.0, n // 2) / np.sqrt((off ** 2).sum(axis=1)))[:, None]
+	pos[1::2] = np.mod(pos[0::2] + off, boxsize)
+	pos[pos >= boxsize] = np.nextafter(boxsize, 0.0)
+	not_los = [c for c in range(3) if c != los]
+	theta = np.pi * rng.random(n)
+	axis = np.stack([np.cos(theta), np.sin(theta)], axis=1) * rng.uniform(0.5, 2.0, n)[:, None]
+	sep = pos[0::2][:, not_los] - pos[1::2][:, not_los]  # shape minus position, then the reference's two shifts
+	sep[sep > boxsize / 2.0] -= boxsize
+	sep[sep < -boxsize / 2.0] += boxsize
+	axis[0::2] = sep * (rng.uniform(0.5, 2.0, n // 2) * rng.choice([-1.0, 1.0], n // 2))[:, None]
+	return {"Position": pos, "Position_shape_sample": pos, "Axis_Direction": axis, "LOS": int(los),
+			"q": rng.uniform(0.2, 1.0, n)}
+
+
+def lattice_box(per_side, boxsize, seed=1, los=2, n_random=0):
+	"""Every coordinate a multiple of boxsize / per_side (plus ``n_random`` uniform points): separations land EXACTLY
+	on Pi bin edges, on +-L/2 (the periodic wrap's strict inequalities), on dz = 0 (mu_r = 0, an edge for an even
+	number of mu_r bins), on r_p = r_min when separation_limits[0] is a lattice distance, and on jackknife faces
+	(label-0 rule).  Auto-correlation."""
+	rng = np.random.default_rng(seed)
+	g = np.arange(per_side) * (boxsize / per_side)
+	pos = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(-1, 3)
+	pos = pos[rng.permutation(len(pos))]
+	if n_random:
+		pos = np.concatenate([pos, rng.random((n_random, 3)) * boxsize])
+	n = len(pos)
+	theta = np.pi * rng.random(n)
+	axis = np.stack([np.cos(theta), np.sin(theta)], axis=1) * rng.uniform(0.5, 2.0, n)[:, None]
+	return {"Position": pos, "Position_shape_sample": pos, "Axis_Direction": axis, "LOS": int(los),
+			"q": rng.uniform(0.2, 1.0, n)}
+
+
+GENERATORS = {"uniform": uniform_box, "aligned_pairs": aligned_pairs_box, "lattice": lattice_box}

@@ -22,7 +22,7 @@ _REPO = os.path.dirname(_HERE)
 sys.path.insert(0, _REPO)
 sys.path.insert(0, _HERE)
 
-from measure_ia_b200.synthetic import uniform_box  # noqa: E402
+from measure_ia_b200.synthetic import GENERATORS, uniform_box  # noqa: E402
 import run_reference  # noqa: E402
 
 GOLDEN = os.path.join(_REPO, "tests", "golden")
@@ -54,6 +54,24 @@ CONFIGS = {
 															 separation_limits=(0.5, 12.0), variant="brute")),
 	"w_auto_jk27_30k": (dict(n=30000, boxsize=205.0, seed=1), dict(kind="w", num_jk=27, num_bins_r=10, num_bins_pi=8)),
 	"m_auto_jk27_30k": (dict(n=30000, boxsize=205.0, seed=1), dict(kind="multipoles", num_jk=27, num_bins_r=10, num_bins_pi=8)),
+	# the reference's NaN rule (|c| > 1 by rounding -> e+ = ex = 0, pair still counted; measure_w_box_jk.py:411-417,
+	# measure_m_box_jk.py:431-438): ~1500 exactly (anti)parallel pairs, of which > 100 trip it
+	"w_nan_rule": (dict(gen="aligned_pairs", n=3000, boxsize=100.0, seed=12),
+				   dict(kind="w", num_jk=8, num_bins_r=10, num_bins_pi=8)),
+	"m_nan_rule": (dict(gen="aligned_pairs", n=3000, boxsize=100.0, seed=12),
+				   dict(kind="multipoles", num_jk=8, num_bins_r=10, num_bins_pi=8)),
+	"w_nan_rule_los0": (dict(gen="aligned_pairs", n=2000, boxsize=60.0, seed=13, los=0),
+						dict(kind="w", num_jk=27, num_bins_r=6, num_bins_pi=6)),
+	# exact edges: lattice coordinates put Pi on bin edges and on +-L/2, dz = 0 (mu_r on the central edge), r_p = r_min,
+	# points on jackknife faces; the brute variant keeps r_p == r_min (the tree variant drops it, SURVEY.md 8(a) hazard 7)
+	"w_lattice": (dict(gen="lattice", per_side=16, boxsize=40.0, seed=14, n_random=300),
+				  dict(kind="w", num_jk=8, num_bins_r=5, num_bins_pi=8, separation_limits=(2.5, 15.0), variant="brute")),
+	"m_lattice": (dict(gen="lattice", per_side=16, boxsize=40.0, seed=14, n_random=300),
+				  dict(kind="multipoles", num_jk=8, num_bins_r=5, num_bins_pi=8, separation_limits=(2.5, 15.0),
+					   variant="brute")),
+	"w_lattice_los1_pimax": (dict(gen="lattice", per_side=12, boxsize=30.0, seed=15, los=1, n_random=150),
+							 dict(kind="w", num_jk=27, num_bins_r=4, num_bins_pi=6, separation_limits=(2.5, 12.5), pi_max=7.5,
+								  variant="brute")),
 }
 
 
@@ -70,7 +88,9 @@ def make_masks(data, mask_seed):
 
 def build_inputs(cat_kw, meas_kw):
 	cat_kw = dict(cat_kw)
-	data = uniform_box(cat_kw.pop("n"), cat_kw.pop("boxsize"), **cat_kw)
+	gen = GENERATORS[cat_kw.pop("gen", "uniform")]
+	first = cat_kw.pop("n") if "n" in cat_kw else cat_kw.pop("per_side")
+	data = gen(first, cat_kw.pop("boxsize"), **cat_kw)
 	meas_kw = dict(meas_kw)
 	masks = None
 	if "mask_seed" in meas_kw:

@@ -52,7 +52,14 @@ def _lib():
 
 
 def max_threads():
-	return int(_lib().oracle_max_threads())
+	"""Host threads this process may use: the scheduler affinity mask, NOT OpenMP's default (torchrun exports
+	OMP_NUM_THREADS=1 to its workers, which would make the CPU arm single-threaded).  oracle.c passes the count in an
+	explicit ``num_threads`` clause, so the environment variable does not cap it."""
+	try:
+		n = len(os.sched_getaffinity(0))
+	except AttributeError:
+		n = os.cpu_count() or 1
+	return max(1, int(n))
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -236,7 +243,8 @@ def paircount(geom, pos, w, jk_p, pos_s, axis, e, w_s, jk_s, r_bins, sep_limits,
 			  two_R, num_box=0, rp_cut=0.0, s_range=None, use_grid=True, n_threads=1, r_thr=None, thr2=None):
 	"""Five-tuple of the reference worker (measure_w_box_jk.py:646) + integer counts.
 
-	Returns dict(DD, SpD, ScD, DD_jk, SpD_jk, count, n_tested); SpD / ScD carry 1/(2R), SpD_jk does not.
+	Returns dict(DD, SpD, ScD, DD_jk, SpD_jk, count, n_tested, var, n_nan); SpD / ScD carry 1/(2R), SpD_jk does not;
+	var = sum (w_D w_S e+ / 2R)^2, the brute variants' variance (measure_w_box_jk.py:196); n_nan = NaN-rule pairs.
 	"""
 	lib = _lib()
 	n_r, n_2 = len(r_bins) - 1, len(bins2) - 1
@@ -248,7 +256,8 @@ def paircount(geom, pos, w, jk_p, pos_s, axis, e, w_s, jk_s, r_bins, sep_limits,
 	DD, SpD, ScD = (np.zeros(nb) for _ in range(3))
 	DD_jk, SpD_jk = np.zeros(max(njk, 1) * nb), np.zeros(max(njk, 1) * nb)
 	count = np.zeros(nb, dtype=np.int64)
-	tested = ctypes.c_int64(0)
+	var = np.zeros(nb)
+	tested, n_nan = ctypes.c_int64(0), ctypes.c_int64(0)
 	pos = np.ascontiguousarray(pos, dtype=np.float64)
 	pos_s = np.ascontiguousarray(pos_s, dtype=np.float64)
 	axis = np.ascontiguousarray(axis, dtype=np.float64)
@@ -266,13 +275,14 @@ def paircount(geom, pos, w, jk_p, pos_s, axis, e, w_s, jk_s, r_bins, sep_limits,
 							  _ptr(e, D), _ptr(w_s, D), _ptr(js, ctypes.c_int32), ctypes.c_int64(s0),
 							  ctypes.c_int64(s1), _ptr(rt, D), _ptr(t2, D), ctypes.c_int(1 if use_grid else 0),
 							  ctypes.c_int(int(n_threads)), _ptr(DD, D), _ptr(SpD, D), _ptr(ScD, D), _ptr(DD_jk, D),
-							  _ptr(SpD_jk, D), _ptr(count, ctypes.c_int64), ctypes.byref(tested))
+							  _ptr(SpD_jk, D), _ptr(count, ctypes.c_int64), ctypes.byref(tested), _ptr(var, D),
+							  ctypes.byref(n_nan))
 	if rc != 0:
 		raise RuntimeError(f"oracle_paircount failed: {rc}")
 	shp = (n_r, n_2)
 	return dict(DD=DD.reshape(shp), SpD=SpD.reshape(shp), ScD=ScD.reshape(shp),
 				DD_jk=DD_jk.reshape((max(njk, 1),) + shp)[:njk], SpD_jk=SpD_jk.reshape((max(njk, 1),) + shp)[:njk],
-				count=count.reshape(shp), n_tested=int(tested.value))
+				count=count.reshape(shp), n_tested=int(tested.value), var=var.reshape(shp), n_nan=int(n_nan.value))
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -344,7 +354,8 @@ def measure(data, kind, dataset_name="All", corr_type="both", num_jk=0, boxsize=
 		put(f"{top}/xi_gg", X + n2, mid2)
 		if num_jk > 0:
 			for grp in (f"{top}/xi_g_plus", f"{top}/xi_g_cross/{jkg}", f"{top}/xi_gg"):
-				put(grp, X + "_sigmasq", zeros)  # tree variant: variance never accumulated (measure_w_box_jk.py:374,492)
+				# tree variant: variance never accumulated (measure_w_box_jk.py:374,492); brute: sum term^2 / RR^2 (:196,:242)
+				put(grp, X + "_sigmasq", res["var"] / RR ** 2 if variant == "brute" else zeros)
 			R_jk = responsivity_jk(w_s, e, jk_s, num_jk)
 			vol_jk = L3 * (num_jk - 1) / num_jk
 			for i in range(num_jk):

@@ -10,11 +10,9 @@ def test_oracle_matches_reference_fixture(oracle, name):
 	meta, want = pu.load_fixture(name)
 	data, masks, kw = pu.rebuild_inputs(meta)
 	kind = kw.pop("kind")
-	variant = kw.pop("variant", "tree")
-	if variant == "brute":  # the brute variants also accumulate a variance the tree variants leave at zero
-		want = {k: v for k, v in want.items() if not k.endswith("_sigmasq")}
+	variant = kw.pop("variant", "tree")  # brute: `_sigmasq` = sum term^2 / RR^2 (measure_w_box_jk.py:196,242); tree: zeros
 	unit_weights = "weight" not in data
-	got = oracle.measure(data, kind, boxsize=meta["catalogue"]["boxsize"], masks=masks, n_threads=4, **kw)
+	got = oracle.measure(data, kind, boxsize=meta["catalogue"]["boxsize"], masks=masks, n_threads=4, variant=variant, **kw)
 	pu.assert_datasets_match(got, want, exact_counts=unit_weights, label=f"{name}: ")
 
 
