@@ -30,11 +30,14 @@
 extern "C" {
 #endif
 
-#define MIA_ABI_VERSION 2
+#define MIA_ABI_VERSION 3
 #define MIA_MAX_BINS 64 /* per axis */
 
 enum { MIA_GEOM_RPPI = 0, MIA_GEOM_RMU = 1 };
-enum { MIA_KERNEL_AUTO = 0, MIA_KERNEL_GENERAL = 1, MIA_KERNEL_TILED = 2 };
+/* kernel selection.  AUTO / TILED pick, for an auto-correlation (position and shape sample alias: same pos / weight / jk
+ * pointers), the symmetric kernel that visits every unordered pair once; TILED_ORDERED never does.  TILED_SYM is only
+ * REPORTED (stats[4]), not requested. */
+enum { MIA_KERNEL_AUTO = 0, MIA_KERNEL_GENERAL = 1, MIA_KERNEL_TILED = 2, MIA_KERNEL_TILED_ORDERED = 3, MIA_KERNEL_TILED_SYM = 4 };
 enum {
 	MIA_OK = 0,
 	MIA_ERR_ARG = -1,       /* NULL pointer, negative size, bins out of range ... */
@@ -92,7 +95,8 @@ typedef struct mia_hist {
 	int64_t *dd_jk_count;
 	double *dd_jk_w;      /* -> DD_jk      */
 	double *spd_jk;       /* -> Splus_D_jk */
-	uint64_t *stats;      /* [8]: 0 candidate pairs tested, 1 pairs binned, 2 |c|>1 pairs (NaN rule), 3 window errors,
+	uint64_t *stats;      /* [8]: 0 separations computed (the symmetric kernel computes one per UNORDERED pair), 1 ordered pairs
+	                                binned, 2 |c|>1 pairs (NaN rule), 3 window errors,
 	                                4 kernel used (MIA_KERNEL_*), 5 cells, 6 warp tasks, 7 kernels launched by the library
 	                                (its own kernels; the CUB radix-sort / scan launches are not counted) */
 } mia_hist;

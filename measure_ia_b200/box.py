@@ -370,12 +370,13 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 		def up(a, dtype=f64):
 			return torch.from_numpy(np.ascontiguousarray(a)).to(dev).to(dtype)
 
-		same = masks is None and d["Position"] is d["Position_shape_sample"] and d["weight"] is d["weight_shape_sample"]
+		same_pos = d["Position"] is d["Position_shape_sample"]
+		same_w = d["weight"] is d["weight_shape_sample"]
 		pos = up(d["Position"])
-		pos_s = pos if same else up(d["Position_shape_sample"])
+		pos_s = pos if same_pos else up(d["Position_shape_sample"])
 		axis_v, q = up(d["Axis_Direction"]), up(d["q"])
 		w = up(d["weight"])
-		w_s = w if same else up(d["weight_shape_sample"])
+		w_s = w if same_w else up(d["weight_shape_sample"])
 		if masks is not None:
 			# quirk kept from the reference (measure_w_box_jk.py:338-347): without explicit weight masks the FIRST
 			# sum(mask) weights are used, and the fabricated masks are stored in the caller's dict
@@ -391,6 +392,13 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 			pos, pos_s = pos[mk("Position")], pos_s[mk("Position_shape_sample")]
 			axis_v, q = axis_v[mk("Axis_Direction")], q[mk("q")]
 			w, w_s = w[mk("weight")], w_s[mk("weight_shape_sample")]
+		# auto-correlation?  Decided by VALUE on the device (the constructor injects two separate unit-weight arrays, and a
+		# user may pass equal copies): the operator then receives the same tensors on both sides, which lets the library
+		# visit every unordered pair once (include/mia_b200.h, MIA_KERNEL_TILED_SYM)
+		same = bool(pos.shape == pos_s.shape and w.shape == w_s.shape and pos.shape[0] == w.shape[0]
+					and (pos is pos_s or torch.equal(pos, pos_s)) and (w is w_s or torch.equal(w, w_s)))
+		if same:
+			pos_s, w_s = pos, w
 		if axis_v.dim() != 2 or axis_v.shape[1] < 2 or pos.dim() != 2 or pos.shape[1] != 3 or pos_s.shape[1:] != pos.shape[1:]:
 			raise ValueError("Position / Position_shape_sample must be (N, 3) and Axis_Direction (N_s, >= 2) arrays")
 		# row norm over ALL columns, summed left to right like np.sum(axis_v ** 2, axis=1) (measure_w_box_jk.py:326); the

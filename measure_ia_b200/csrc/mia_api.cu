@@ -10,6 +10,7 @@
 #include "mia_tiled.cuh"
 #include "mia_tiled_rmu.cuh"
 #include "mia_tiled_rppi2.cuh"
+#include "mia_tiled_rppi2s.cuh"
 
 using namespace mia;
 
@@ -26,6 +27,7 @@ struct Plan {
 	int kernel;       // resolved MIA_KERNEL_*
 	int key_bits;
 	int n_partials;   // accumulator copies (1 for the general kernel, one per CTA for the tiled kernel)
+	int cand_bytes;   // bytes per sorted candidate record (Cand, or CandS when the symmetric kernel may run)
 	int rows;         // 2 * max(num_jk, 1)
 	int nb;
 	TiledConfig tiled;
@@ -72,6 +74,8 @@ int make_plan(const mia_params *p, int64_t nD, int64_t nS, Plan &pl) {
 	pl.rows = 2 * J;
 	pl.g.jk_rows = J;
 	pl.kernel = p->kernel;
+	const bool ordered_only = (pl.kernel == MIA_KERNEL_TILED_ORDERED);
+	if (ordered_only) pl.kernel = MIA_KERNEL_TILED;
 	if (pl.kernel == MIA_KERNEL_AUTO || pl.kernel == MIA_KERNEL_TILED) {
 		// the tiled grids are fine (cells ~ r_max / 4): their sort keys must fit 31 bits
 		if (plan_tiled(p, nD, nS, pl.g, pl.ku, pl.kv, pl.kl, pl.tiled) &&
@@ -99,7 +103,11 @@ int make_plan(const mia_params *p, int64_t nD, int64_t nS, Plan &pl) {
 	} else {
 		pl.n_partials = pl.tiled.n_partials;
 		pl.g.order = pl.tiled.v2 ? 1 : 0;  // row-streaming (r_p, Pi) kernel: candidates sorted by (u row, slab, v cell)
+		if (ordered_only || env_int("MIA_SYM", 1) == 0) pl.tiled.sym_ok = 0;
 	}
+	// the symmetric auto-correlation kernel needs 64-byte candidate records; whether the two samples really are the same
+	// catalogue is only known at call time, so the workspace is sized for it whenever the sizes agree
+	pl.cand_bytes = (pl.kernel == MIA_KERNEL_TILED && pl.tiled.sym_ok && nD == nS) ? (int)sizeof(CandSW) : (int)sizeof(Cand);
 	const uint64_t nkeys = (uint64_t)pl.g.ncell() * 4ull * (uint64_t)J;  // x4: the shape sample's sub-cell ordering
 	if (nkeys > (1ull << 31)) return MIA_ERR_UNSUPPORTED;
 	pl.key_bits = ilog2_ceil(nkeys > 1 ? nkeys : 2);
@@ -112,7 +120,7 @@ int make_plan(const mia_params *p, int64_t nD, int64_t nS, Plan &pl) {
 		o = align_up(o + bytes);
 		return at;
 	};
-	pl.off_cand = take(sizeof(Cand) * (size_t)nD);
+	pl.off_cand = take((size_t)pl.cand_bytes * (size_t)nD);
 	pl.off_cand_jk = take(sizeof(int32_t) * (size_t)nD);
 	pl.off_prim = take(sizeof(Prim) * (size_t)nS);
 	pl.off_cell_start = take(sizeof(int64_t) * (size_t)(pl.g.ncell() + 1));
@@ -305,6 +313,10 @@ int mia_paircount(const mia_params *params, const mia_sample *D, const mia_sampl
 	unsigned char *ws = (unsigned char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
 	if (ws + pl.total > (unsigned char *)workspace + workspace_bytes) return MIA_ERR_WORKSPACE;
 
+	// same catalogue on both sides (auto-correlation): every unordered pair is visited once (mia_tiled_rppi2s.cuh)
+	const bool alias = (D->pos == S->pos && D->weight == S->weight && D->jk == S->jk && nD == nS);
+	pl.tiled.sym = (pl.kernel == MIA_KERNEL_TILED && pl.tiled.sym_ok && alias && pl.cand_bytes == (int)sizeof(CandSW)) ? 1 : 0;
+	if (pl.tiled.sym) pl.tiled.sym = rppi2s_cand_bytes(D->weight == nullptr);  // bytes per candidate record (48 / 64)
 	DevParams P;
 	fill_dev_params(params, pl, P);
 	const int nl0 = (params->los == 0) ? 1 : 0, nl1 = (params->los == 2) ? 1 : 2, los = params->los;
@@ -354,7 +366,10 @@ int mia_paircount(const mia_params *params, const mia_sample *D, const mia_sampl
 	// ---- position sample -> sorted candidates + cell offsets ------------------------------------------------------
 	rc = sort_by_cell(D->pos, D->jk, nD, nl0, nl1, los, pl.g, params->boxsize, sc, pl.key_bits, flags, st);
 	if (rc) return rc;
-	if (nD > 0) {
+	if (nD > 0 && pl.tiled.sym) {
+		k_gather_cands<<<(unsigned)((nD + T - 1) / T), T, 0, st>>>(D->pos, D->weight, D->jk, S->axis, S->e, sc.idx_out, nD, nl0,
+																	nl1, los, (void *)cand, cand_jk);
+	} else if (nD > 0) {
 		k_gather_cand<<<(unsigned)((nD + T - 1) / T), T, 0, st>>>(D->pos, D->weight, D->jk, sc.idx_out, nD, nl0, nl1, los,
 																   cand, cand_jk);
 	}
@@ -440,7 +455,8 @@ int mia_paircount(const mia_params *params, const mia_sample *D, const mia_sampl
 	MIA_CUDA_CHECK(cudaGetLastError());
 	if (out->stats) {
 		n_launches += 2;  // finalize + copy_stats
-		k_copy_stats<<<1, 32, 0, st>>>(A.stats, out->stats, (unsigned long long)pl.kernel, (unsigned long long)ncell,
+		k_copy_stats<<<1, 32, 0, st>>>(A.stats, out->stats,
+									   (unsigned long long)(pl.tiled.sym ? MIA_KERNEL_TILED_SYM : pl.kernel), (unsigned long long)ncell,
 									   n_tasks, n_launches);
 		MIA_CUDA_CHECK(cudaGetLastError());
 	}

@@ -96,6 +96,8 @@ struct TiledConfig {
 	int hsplit;      // (r, mu_r): a warp works on 32 / hsplit shape galaxies, hsplit candidates at a time
 	int n_lr;        // (r, mu_r): line-of-sight regions (= jackknife sub-boxes per side when the slabs are aligned with them)
 	int v2;          // (r_p, Pi): row-streaming kernel (mia_tiled_rppi2.cuh); n_lr then counts the regions along v
+	int sym_ok;      // (r_p, Pi), row-streaming: the grid admits the symmetric auto-correlation kernel (mia_tiled_rppi2s.cuh)
+	int sym;         // ... and this call uses it (position sample == shape sample): bytes per candidate record (CandSU / CandSW), else 0
 	int n_partials;  // accumulator copies = worker warps
 	int n_ctas;
 	int num_sms;
@@ -142,9 +144,13 @@ inline bool plan_rppi2_grid(const mia_params *p, int n_side, TiledConfig &cfg, i
 inline size_t tiled_rppi2_smem_bytes(bool unit_w);
 inline int rppi2_prepare(const TiledConfig &cfg, const GridDims &g, const TiledWorkspace &w, cudaStream_t st);
 inline int rppi2_fill_tasks(const TiledArgs &a, const int64_t *prim_cell_start, const int64_t *cell_start, const int32_t *task_off,
-							int ncol_s, int nzs, int k, int split, int32_t *task_col, int64_t *task_first, int32_t *task_n,
+							int ncol_s, int nzs, int k, int split, int sym, int32_t *task_col, int64_t *task_first, int32_t *task_n,
 							int32_t *task_slab, unsigned long long *task_cost, int32_t *n_tasks, cudaStream_t st);
 inline int launch_rppi2(const TiledArgs &a, bool unit_w, int n_ctas, size_t smem, cudaStream_t st);
+// defined in mia_tiled_rppi2s.cuh
+inline bool rppi2s_supported(int ncu, int k, int ratio);
+inline size_t tiled_rppi2s_smem_bytes(bool unit_w);
+inline int launch_rppi2s(const TiledArgs &a, bool unit_w, int n_ctas, size_t smem, cudaStream_t st);
 inline int rmu_fill_tasks(const TiledArgs &a, const int64_t *prim_cell_start, const int64_t *cell_start, const int32_t *task_off,
 						  int ncol_s, int nzs, int k, int split, int32_t *task_col, int64_t *task_first, int32_t *task_n,
 						  int32_t *task_slab, unsigned long long *task_cost, int32_t *n_tasks, cudaStream_t st);
@@ -216,6 +222,8 @@ inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g,
 	cfg.hsplit = 1;
 	cfg.n_lr = 1;
 	cfg.v2 = 0;
+	cfg.sym_ok = 0;
+	cfg.sym = 0;
 	// columns: about a quarter of the search radius wide
 	int nc = (int)floor(L / (reach / 4.0));
 	if (nc > 2048) nc = 2048;
@@ -269,6 +277,7 @@ inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g,
 		if (v2) {  // row-streaming kernel: finer columns, coarser shape columns
 			cfg.w_r = div2;  // (r_p, Pi): carries the chosen cells per r_max to plan_rppi2_grid (0 = default)
 			if (!plan_rppi2_grid(p, n_side, cfg, nc, nz, k)) return false;
+			cfg.sym_ok = rppi2s_supported(nc, k, cfg.ratio) ? 1 : 0;
 		} else {
 			const double cs = L / nc;
 			k = (int)ceil(reach / cs);
@@ -363,7 +372,7 @@ inline size_t tiled_workspace_bytes(const TiledConfig &cfg, const GridDims &g, i
 // ------------------------------------------------------------------------------------------------------------------
 // preparation kernels
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void k_cell_info(const Cand *__restrict__ cand, const int32_t *__restrict__ cand_jk,
+__global__ void k_cell_info(const unsigned char *__restrict__ cand, int stride, const int32_t *__restrict__ cand_jk,
 							const int64_t *__restrict__ cell_start, int64_t ncell, int nz, CellInfo *__restrict__ info,
 							unsigned long long *__restrict__ slab_lo, unsigned long long *__restrict__ slab_hi, int order = 0,
 							int ncv = 1) {
@@ -379,7 +388,9 @@ __global__ void k_cell_info(const Cand *__restrict__ cand, const int32_t *__rest
 		double lmin = INFINITY, lmax = -INFINITY;
 		int prev = -1;
 		for (int64_t j = j0; j < j1; j++) {
-			const Cand q = cand[j];
+			// u, v, l lead every candidate record (Cand, CandSU, CandSW)
+			const double2 uv = *reinterpret_cast<const double2 *>(cand + (size_t)j * stride);
+			struct { double u, v, l; } q = {uv.x, uv.y, *reinterpret_cast<const double *>(cand + (size_t)j * stride + 16)};
 			ci.umin = fmin(ci.umin, q.u);
 			ci.umax = fmax(ci.umax, q.u);
 			ci.vmin = fmin(ci.vmin, q.v);
@@ -582,8 +593,9 @@ struct ZWindow {
 	bool gen, dead, err;
 };
 
-// Which (at most two) Pi bins can pairs of this shape galaxy with candidates of a slab [zlo, zhi] fall in?
-__device__ __noinline__ ZWindow z_window(double pl, double zlo, double zhi, const ZParams P) {
+// Which (at most two) Pi bins can a pair fall in whose raw line-of-sight separation (before the periodic shift) lies in
+// [lo, hi]?  (hi - lo is smaller than the narrowest Pi bin.)
+__device__ __noinline__ ZWindow z_window_sep(double lo, double hi, const ZParams P) {
 	ZWindow w;
 	w.t_split = INFINITY;
 	w.t_lo = -INFINITY;
@@ -597,7 +609,6 @@ __device__ __noinline__ ZWindow z_window(double pl, double zlo, double zhi, cons
 	w.dead = false;
 	w.err = false;
 	const int n2 = P.n_2;
-	double lo = __dsub_rn(pl, zhi), hi = __dsub_rn(pl, zlo);  // fl(s - c) is monotone in c
 	bool straddle = false;
 	if (P.periodic && !(lo >= -P.halfL && hi <= P.halfL)) {
 		if (lo > P.halfL) {  // every pair wraps down: sep -= L (measure_w_box_jk.py:403)
@@ -671,6 +682,11 @@ __device__ __noinline__ ZWindow z_window(double pl, double zlo, double zhi, cons
 	}
 	w.dead = (w.b0 < 0 && w.b1 < 0);
 	return w;
+}
+
+// The same for one shape galaxy at line-of-sight coordinate pl against the candidates of a slab [zlo, zhi].
+__device__ __forceinline__ ZWindow z_window(double pl, double zlo, double zhi, const ZParams P) {
+	return z_window_sep(__dsub_rn(pl, zhi), __dsub_rn(pl, zlo), P);  // fl(s - c) is monotone in c
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1413,8 +1429,8 @@ inline int tiled_prepare_candidates(const TiledConfig &cfg, const GridDims &g, c
 	MIA_CUDA_CHECK(cudaMemsetAsync(w.slab_lo, 0xFF, sizeof(double) * cfg.nz, st));
 	MIA_CUDA_CHECK(cudaMemsetAsync(w.slab_hi, 0x00, sizeof(double) * cfg.nz, st));
 	const int64_t ncell = g.ncell();
-	k_cell_info<<<(unsigned)((ncell + 127) / 128), 128, 0, st>>>(cand, cand_jk, cell_start, ncell, cfg.nz, w.cinfo,
-																 (unsigned long long *)w.slab_lo,
+	k_cell_info<<<(unsigned)((ncell + 127) / 128), 128, 0, st>>>((const unsigned char *)cand, cfg.sym ? cfg.sym : (int)sizeof(Cand), cand_jk,
+																 cell_start, ncell, cfg.nz, w.cinfo, (unsigned long long *)w.slab_lo,
 																 (unsigned long long *)w.slab_hi, g.order, g.ncv);
 	MIA_CUDA_CHECK(cudaGetLastError());
 	if (cfg.v2) {
@@ -1464,7 +1480,7 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &gc, const GridDi
 	a.ratio = cfg.ratio;
 	a.hsplit = cfg.hsplit;
 	if (cfg.v2) {
-		const int rc = rppi2_fill_tasks(a, prim_cell_start, G.cell_start, w.task_off, (int)ncol, nzs, P.ku, split, w.task_col,
+		const int rc = rppi2_fill_tasks(a, prim_cell_start, G.cell_start, w.task_off, (int)ncol, nzs, P.ku, split, cfg.sym, w.task_col,
 										w.task_first, w.task_n, w.task_slab, w.task_cost, w.n_tasks, st);
 		if (rc) return rc;
 	} else if (cfg.geom == MIA_GEOM_RMU) {
@@ -1485,7 +1501,8 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &gc, const GridDi
 	// grouping of the fp64 sums, hence every output bit, is the same for the weighted and the unit-weight kernel variants,
 	// which is what lets w = 0.5 scale the results by exactly 1/4 (reference tests/test_weights.py:34-35). ---------------
 	const bool rmu = cfg.geom == MIA_GEOM_RMU;
-	const size_t smem = rmu ? tiled_rmu_smem_bytes(unit_w) : (cfg.v2 ? tiled_rppi2_smem_bytes(unit_w) : tiled_smem_bytes(unit_w));
+	const size_t smem = rmu ? tiled_rmu_smem_bytes(unit_w)
+							: (cfg.sym ? tiled_rppi2s_smem_bytes(unit_w) : (cfg.v2 ? tiled_rppi2_smem_bytes(unit_w) : tiled_smem_bytes(unit_w)));
 	if (rmu || cfg.v2) {
 	} else if (unit_w) {
 		MIA_CUDA_CHECK(cudaFuncSetAttribute(k_tiled_rppi<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1527,6 +1544,9 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &gc, const GridDi
 	if (ev_before) MIA_CUDA_CHECK(cudaEventRecord(ev_before, st));
 	if (rmu) {
 		const int rc = launch_rmu(a, unit_w, P.los == 2, cfg.n_ctas, smem, st);
+		if (rc) return rc;
+	} else if (cfg.sym) {
+		const int rc = launch_rppi2s(a, unit_w, cfg.n_ctas, smem, st);
 		if (rc) return rc;
 	} else if (cfg.v2) {
 		const int rc = launch_rppi2(a, unit_w, cfg.n_ctas, smem, st);

@@ -125,7 +125,7 @@ __global__ void k_v_envelope(double *__restrict__ vlo, double *__restrict__ vhi,
 // cost = shapes x candidates in the u rows within reach.
 __global__ void k_fill_tasks_rppi2(const int64_t *__restrict__ prim_cell_start, const int64_t *__restrict__ cell_start,
 								   const int32_t *__restrict__ task_off, int ncu, int ncv, int nz, int ratio, int nzs, int split,
-								   int k, int periodic, int32_t *__restrict__ task_col, int64_t *__restrict__ task_first,
+								   int k, int periodic, int sym, int32_t *__restrict__ task_col, int64_t *__restrict__ task_first,
 								   int32_t *__restrict__ task_n, int32_t *__restrict__ task_slab,
 								   unsigned long long *__restrict__ task_cost, int32_t *__restrict__ n_tasks) {
 	const int ncu_s = ncu / ratio, ncv_s = ncv / ratio;
@@ -139,7 +139,7 @@ __global__ void k_fill_tasks_rppi2(const int64_t *__restrict__ prim_cell_start, 
 	const bool all_u = 2 * k + ratio >= ncu;
 	const int nrows = all_u ? ncu : 2 * k + ratio;
 	unsigned long long W = 0;
-	for (int o = 0; o < nrows; o++) {
+	for (int o = sym ? k : 0; o < nrows; o++) {  // symmetric kernel: own rows and the rows ahead only
 		int cu = all_u ? o : ratio * su0 - k + o;
 		if (cu < 0 || cu >= ncu) {
 			if (!periodic) continue;
@@ -650,11 +650,11 @@ inline int rppi2_prepare(const TiledConfig &cfg, const GridDims &g, const TiledW
 }
 
 inline int rppi2_fill_tasks(const TiledArgs &a, const int64_t *prim_cell_start, const int64_t *cell_start, const int32_t *task_off,
-							int ncol_s, int nzs, int k, int split, int32_t *task_col, int64_t *task_first, int32_t *task_n,
+							int ncol_s, int nzs, int k, int split, int sym, int32_t *task_col, int64_t *task_first, int32_t *task_n,
 							int32_t *task_slab, unsigned long long *task_cost, int32_t *n_tasks, cudaStream_t st) {
 	const DevParams &P = a.P;
 	k_fill_tasks_rppi2<<<(unsigned)((ncol_s + 127) / 128), 128, 0, st>>>(prim_cell_start, cell_start, task_off, P.ncu, P.ncv, P.ncl,
-																		 a.ratio, nzs, split, k, P.periodic, task_col, task_first, task_n,
+																		 a.ratio, nzs, split, k, P.periodic, sym, task_col, task_first, task_n,
 																		 task_slab, task_cost, n_tasks);
 	return (int)cudaGetLastError();
 }

@@ -14,10 +14,12 @@ import torch
 
 from .build import LIB_PATH
 
-MIA_ABI_VERSION = 2
+MIA_ABI_VERSION = 3
 GEOM_RPPI, GEOM_RMU = 0, 1
-KERNEL_AUTO, KERNEL_GENERAL, KERNEL_TILED = 0, 1, 2
-KERNEL_NAMES = {"auto": KERNEL_AUTO, "general": KERNEL_GENERAL, "tiled": KERNEL_TILED}
+KERNEL_AUTO, KERNEL_GENERAL, KERNEL_TILED, KERNEL_TILED_ORDERED, KERNEL_TILED_SYM = 0, 1, 2, 3, 4
+# "tiled_ordered": the tiled kernels without the symmetric auto-correlation path (every ordered pair evaluated on its own)
+KERNEL_NAMES = {"auto": KERNEL_AUTO, "general": KERNEL_GENERAL, "tiled": KERNEL_TILED, "tiled_ordered": KERNEL_TILED_ORDERED}
+KERNEL_REPORTED = {KERNEL_GENERAL: "general", KERNEL_TILED: "tiled", KERNEL_TILED_SYM: "tiled_sym"}
 
 
 class MiaParams(ctypes.Structure):

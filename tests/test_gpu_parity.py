@@ -11,7 +11,8 @@ import parity_util as pu
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = ["general", "auto"]
+KERNELS = ["general", "auto", "tiled_ordered"]
+TILED = (2, 4)  # reported kernel ids: tiled, tiled with the symmetric auto-correlation path (mia_b200.h)
 
 
 @pytest.fixture(scope="module")
@@ -69,8 +70,9 @@ def test_reference_fixture(torch_cuda, tmp_path, name, kernel):
 	box = run_box(meta, data, masks, kw, out, kernel)
 	got = read_all(out)
 	pu.assert_datasets_match(got, want, exact_counts=not meta["catalogue"].get("weights"), label=f"{name}[{kernel}]: ")
-	if kernel == "auto":
-		assert box.last_stats["kernel"] == 2, "the tiled kernels should cover every (r_p, Pi) and (r, mu_r) fixture"
+	if kernel != "general":
+		assert box.last_stats["kernel"] in TILED, "the tiled kernels should cover every (r_p, Pi) and (r, mu_r) fixture"
+		assert kernel == "auto" or box.last_stats["kernel"] == 2
 	if "nan_rule" in name:
 		# the reference's NaN rule (measure_w_box_jk.py:411-417, measure_m_box_jk.py:431-438) must actually fire, in both
 		# kernels, on exactly the pairs the oracle zeroes
@@ -107,8 +109,8 @@ def test_against_oracle_100k(torch_cuda, oracle, tmp_path, geom, kind, kernel):
 	want.pop("__meta__/n_tested")
 	assert np.array_equal(box.last_result["count"], count)
 	pu.assert_datasets_match(read_all(out), want, exact_counts=(geom == "rppi"), label=f"{geom}[{kernel}]: ")
-	if kernel == "auto":
-		assert box.last_stats["kernel"] == 2
+	if kernel != "general":
+		assert box.last_stats["kernel"] in TILED
 
 
 def _host_call(torch, oracle, data, geom, num_jk, boxsize, n_r, n_2, kernel=0, shard=(0, 1)):
@@ -175,7 +177,7 @@ def test_exact_quarter_scaling_with_half_weights(torch_cuda, tmp_path):
 	box.measure_xi_w("B", "both", 8, temp_file_path=False)
 	g = read_all(out)
 	assert np.array_equal(g["w/xi_gg/A_DD"], 4 * g["w/xi_gg/B_DD"])
-	if box.last_stats["kernel"] == 2:  # the tiled kernel accumulates in a fixed order
+	if box.last_stats["kernel"] in TILED:  # the tiled kernels accumulate in a fixed order
 		assert np.array_equal(g["w_g_plus/A"], 4 * g["w_g_plus/B"])
 	np.testing.assert_allclose(g["w_g_plus/A"], 4 * g["w_g_plus/B"], rtol=1e-12)
 	np.testing.assert_allclose(g["w_g_plus/A_jackknife_cov_8"], 16 * g["w_g_plus/B_jackknife_cov_8"], rtol=1e-9)
@@ -272,8 +274,8 @@ def test_clustered_weighted_default_bins_vs_oracle(torch_cuda, oracle, tmp_path,
 	want.pop("__meta__/n_tested")
 	assert np.array_equal(box.last_result["count"], count)
 	pu.assert_datasets_match(read_all(out), want, exact_counts=False, label=f"clustered[{kernel}]: ")
-	if kernel == "auto":
-		assert box.last_stats["kernel"] == 2
+	if kernel != "general":
+		assert box.last_stats["kernel"] in TILED
 
 
 def test_tiled_kernel_is_bit_reproducible(torch_cuda):
@@ -339,24 +341,30 @@ def _assert_same_sums(got, want, label):
 			assert (np.abs(a - b) <= tol).all(), f"{label}: {k} differs by {np.abs(a - b).max():.3e}"
 
 
-@pytest.mark.parametrize("mode", ["default", "rows", "cells", "split"])
+@pytest.mark.parametrize("mode", ["default", "rows", "rows_ordered", "cells", "split"])
 @pytest.mark.parametrize("case", _CROSS_CASES, ids=[f"n{c[0]}_L{int(c[1])}_jk{c[3]}" for c in _CROSS_CASES])
 @pytest.mark.parametrize("kind", ["w", "multipoles"])
 def test_tiled_kernels_match_general(torch_cuda, monkeypatch, kind, case, mode):
 	"""Every tiled code path (row-streaming / cell-by-cell (r_p, Pi), column-streaming (r, mu_r), tasks cut into parts as on
 	many GPUs) against the reference-exact general kernel: pair counts bit-identical, sums to 1e-10."""
-	if kind == "multipoles" and (mode in ("rows", "cells") or case[6].get("pi_max")):
+	if kind == "multipoles" and (mode in ("rows", "rows_ordered", "cells") or case[6].get("pi_max")):
 		pytest.skip("(r_p, Pi)-only variation")
 	want, st_g = _run_cross(kind, case, "general")
 	assert st_g["kernel"] == 1
-	if mode == "rows":
+	if mode in ("rows", "rows_ordered"):
 		monkeypatch.setenv("MIA_RPPI_V2", "2")
 	elif mode == "cells":
 		monkeypatch.setenv("MIA_RPPI_V2", "0")
 	elif mode == "split":
 		monkeypatch.setenv("MIA_TASKS_PER_WARP", "1000")
-	got, st_t = _run_cross(kind, case, "tiled")
-	assert st_t["kernel"] == 2
+	got, st_t = _run_cross(kind, case, "tiled_ordered" if mode == "rows_ordered" else "tiled")
+	assert st_t["kernel"] in TILED
+	if mode == "rows_ordered":
+		assert st_t["kernel"] == 2
+	if mode == "rows" and kind == "w" and "n_shape" not in case[6] and case[0] in (3000, 20000, 30000, 50000):
+		# auto-correlations on grids wide enough for the half-space rule take the symmetric kernel (every unordered pair
+		# visited once, both orderings accumulated: mia_tiled_rppi2s.cuh)
+		assert st_t["kernel"] == 4, case
 	assert st_t["binned"] == int(want["count"].sum())
 	assert st_t["nan_rule"] == st_g["nan_rule"]
 	if case[6].get("gen") == "aligned_pairs":
@@ -374,7 +382,7 @@ def test_full_size_tiled_matches_general(torch_cuda, workload):
 	kind = "w" if workload == "cfg2" else "multipoles"
 	want, st_g = _run_cross(kind, case, "general")
 	got, st_t = _run_cross(kind, case, "auto")
-	assert st_g["kernel"] == 1 and st_t["kernel"] == 2
+	assert st_g["kernel"] == 1 and st_t["kernel"] == (4 if kind == "w" else 2)
 	assert st_t["binned"] == st_g["binned"] == int(want["count"].sum())
 	assert st_t["nan_rule"] == st_g["nan_rule"]
 	print(f"{workload}: {st_t['binned']} pairs, nan_rule {st_t['nan_rule']}, tested {st_t['tested']}")
