@@ -466,17 +466,21 @@ __device__ __noinline__ unsigned flush_slots_rmu(const FlushCtx &fc, PrivAcc acc
 			if (rbin > rb) {
 				atomicExch(&fc.flags[1], 1);
 			} else {
+				// all loads before the first store: one memory latency per flush group instead of seven
 				const size_t bin = (size_t)rbin * fc.n_2 + b2;
 				const size_t ia = (size_t)k * fc.nb + bin;
-				fc.pcnt[ia] += tot_cnt;
-				fc.pddw[ia] += tot_dw;
-				fc.psp[ia] += tot_sp;
-				fc.psc[ia] += tot_sc;
-				if (fc.num_jk > 0 && jkD != k) {
-					const size_t ib = (size_t)(fc.J + jkD) * fc.nb + bin;
-					fc.pcnt[ib] += tot_cnt;
-					fc.pddw[ib] += tot_dw;
-					fc.psp[ib] += tot_sp;
+				const bool has_b = fc.num_jk > 0 && jkD != k;
+				const size_t ib = has_b ? (size_t)(fc.J + jkD) * fc.nb + bin : ia;
+				const unsigned long long c_a = fc.pcnt[ia], c_b = fc.pcnt[ib];
+				const double d_a = fc.pddw[ia], p_a = fc.psp[ia], x_a = fc.psc[ia], d_b = fc.pddw[ib], p_b = fc.psp[ib];
+				fc.pcnt[ia] = c_a + tot_cnt;
+				fc.pddw[ia] = d_a + tot_dw;
+				fc.psp[ia] = p_a + tot_sp;
+				fc.psc[ia] = x_a + tot_sc;
+				if (has_b) {
+					fc.pcnt[ib] = c_b + tot_cnt;
+					fc.pddw[ib] = d_b + tot_dw;
+					fc.psp[ib] = p_b + tot_sp;
 				}
 				binned += tot_cnt;
 			}

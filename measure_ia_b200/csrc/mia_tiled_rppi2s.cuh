@@ -22,11 +22,13 @@
 
 namespace mia {
 
+// Tuning (B200, cfg2, profiles/r02_tuning.md): 2 resident CTAs per SM with 255 registers and no spills in the chunk consumer
+// beat 3 CTAs at the 168-register cap (113 vs 120 ms); chunks of 128 (unit weights, 48-byte records) / 96 (64-byte records).
 #ifndef MIA_S_CH_U
-#define MIA_S_CH_U 72
+#define MIA_S_CH_U 128
 #endif
 #ifndef MIA_S_CH_W
-#define MIA_S_CH_W 36
+#define MIA_S_CH_W 96
 #endif
 #ifndef MIA_S_WR
 #define MIA_S_WR 5
@@ -35,7 +37,7 @@ namespace mia {
 #define MIA_S_UNROLL 2
 #endif
 #ifndef MIA_S_MIN_CTAS
-#define MIA_S_MIN_CTAS 3
+#define MIA_S_MIN_CTAS 2
 #endif
 constexpr int WRS = MIA_S_WR;    // r bins per accumulation window (the same for both variants: it fixes the grouping of the sums)
 constexpr int NSLOT_S = 2 * WRS; // private slots per thread: (r bin of the window) x (Pi slot of the forward pair)
