@@ -69,6 +69,9 @@ typedef struct mia_params {
 	 * [0] the cell-list build (keys, radix sort, gather, offsets, task table), [1] the pair kernel, [2] the fixed-order
 	 * reductions, [3] the whole call.  NULL = do not time. */
 	float *timings_host;
+	/* 1: also accumulate mia_hist.var = sum (w_D w_S e_+)^2 per bin, the `variance` of the reference's brute variants
+	 * (measure_w_box_jk.py:196,242; measure_m_box_jk.py:207,255).  Such calls use the ordered kernels. */
+	int32_t variance;
 } mia_params;
 
 /* One catalogue.  pos is row-major [n][3] in the caller's column order.  axis / e are only read for the shape sample:
@@ -99,6 +102,7 @@ typedef struct mia_hist {
 	                                binned, 2 |c|>1 pairs (NaN rule), 3 window errors,
 	                                4 kernel used (MIA_KERNEL_*), 5 cells, 6 warp tasks, 7 kernels launched by the library
 	                                (its own kernels; the CUB radix-sort / scan launches are not counted) */
+	double *var;          /* [n_r][n_2] sum (w_D w_S e_+)^2 -> variance * (2R)^2; written iff params->variance (may be NULL otherwise) */
 } mia_hist;
 
 /* Shard of the shape sample handled by this call (multi-GPU: rank r of w takes the r-th of w work-balanced slices of

@@ -440,9 +440,16 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 			# per realisation: the same ratio over the shapes NOT in region k (measure_w_box_jk.py:463-466).  Masked
 			# torch.sum calls (fixed reduction tree) instead of index_add_/bincount-with-weights, whose atomics would make
 			# the last bit of R_jk vary from run to run
+			# (one masked [regions, N] reduction per quantity, in blocks of regions to bound the temporary)
 			zero = torch.zeros((), dtype=f64, device=dev)
-			num = torch.stack([torch.where(js != k, t, zero).sum() for k in range(num_box)])
-			den = torch.stack([torch.where(js != k, w_s, zero).sum() for k in range(num_box)])
+			blk = max(1, min(num_box, (1 << 26) // max(1, js.numel())))
+			num, den = [], []
+			for k0 in range(0, num_box, blk):
+				ks = torch.arange(k0, min(k0 + blk, num_box), device=dev)[:, None]
+				keep = js[None, :] != ks
+				num.append(torch.where(keep, t[None, :], zero).sum(dim=1))
+				den.append(torch.where(keep, w_s[None, :], zero).sum(dim=1))
+			num, den = torch.cat(num), torch.cat(den)
 			with np.errstate(invalid="ignore", divide="ignore"):
 				R_jk = num.cpu().numpy() / den.cpu().numpy()
 			n_p_k = pos.shape[0] - torch.bincount(jk_p.to(torch.int64), minlength=num_box).cpu().numpy()
@@ -454,7 +461,7 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 					same=same, R=R, R_jk=R_jk, n_p_k=n_p_k, n_s_k=n_s_k, Np=int(pos.shape[0]), Ns=int(pos_s.shape[0]))
 
 	# ---- the pair loop: ONE operator call replaces the reference's twelve variants -----------------------------------------
-	def _pair_sums(self, geom, masks, L_subboxes, ellipticity, rp_cut=None):
+	def _pair_sums(self, geom, masks, L_subboxes, ellipticity, rp_cut=None, variance=False):
 		import torch
 
 		from . import ops
@@ -478,16 +485,17 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 		out = torch.ops.measure_ia_b200.paircount(
 			P["pos"], P["w"], P["jk_p"], P["pos_s"], P["w_s"], P["jk_s"], P["axis"], P["e"], torch.from_numpy(r2_thr),
 			torch.from_numpy(thr2), ops.GEOM_RPPI if geom == "rppi" else ops.GEOM_RMU, int(self.data["LOS"]),
-			bool(self.periodicity), num_box, float(self.boxsize), float(self.r_bins[-1]), float(rp2_cut), kernel, rank, world)
-		dd_count, dd_w, spd, scd, jk_count, jk_w, spd_jk, stats = out
+			bool(self.periodicity), num_box, float(self.boxsize), float(self.r_bins[-1]), float(rp2_cut), kernel, rank, world,
+			bool(variance))
+		dd_count, dd_w, spd, scd, jk_count, jk_w, spd_jk, stats, var = out
 		if world > 1:
-			dd_count, dd_w, spd, scd, jk_count, jk_w, spd_jk, stats = combine_across_ranks(
-				dd_count, dd_w, spd, scd, jk_count, jk_w, spd_jk, stats)
+			dd_count, dd_w, spd, scd, jk_count, jk_w, spd_jk, stats, var = combine_across_ranks(
+				dd_count, dd_w, spd, scd, jk_count, jk_w, spd_jk, stats, var)
 		torch.cuda.synchronize(dev)
 		t2 = time.perf_counter()
 		res = dict(count=dd_count.cpu().numpy(), DD=dd_w.cpu().numpy(), SpD_raw=spd.cpu().numpy(),
 				   ScD_raw=scd.cpu().numpy(), count_jk=jk_count.cpu().numpy(), DD_jk=jk_w.cpu().numpy(),
-				   SpD_jk=spd_jk.cpu().numpy(), R=P["R"], R_jk=P["R_jk"], n_p_k=P["n_p_k"], n_s_k=P["n_s_k"], Np=P["Np"],
+				   SpD_jk=spd_jk.cpu().numpy(), var_raw=var.cpu().numpy() if variance else None, R=P["R"], R_jk=P["R_jk"], n_p_k=P["n_p_k"], n_s_k=P["n_s_k"], Np=P["Np"],
 				   Ns=P["Ns"])
 		st = stats.cpu().numpy()
 		self.last_stats = dict(tested=int(st[0]), binned=int(st[1]), nan_rule=int(st[2]), kernel=int(st[4]),
@@ -506,6 +514,10 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 		rr_grid = self._rr_grid_rppi if geom == "rppi" else self._rr_grid_rmu
 		bins2 = self.pi_bins if geom == "rppi" else self.mu_r_bins
 		RR = rr_grid(L3, res["Np"], res["Ns"])
+		# `_sigmasq`: the brute variants accumulate sum (w_D w_S e+ / 2R)^2 and store it over RR^2 (measure_w_box_jk.py:196,242);
+		# the tree / multiprocessing variants never touch their `variance` array and store zeros (:374,492)
+		with np.errstate(divide="ignore", invalid="ignore"):
+			sigsq = (res["var_raw"] / (2 * R) ** 2) / RR ** 2 if res.get("var_raw") is not None else np.zeros_like(DD)
 		sep = self.r_bins[:-1] + abs((self.r_bins[1:] - self.r_bins[:-1]) / 2.0)
 		mid2 = bins2[:-1] + abs((bins2[1:] - bins2[:-1]) / 2.0)
 		top = "w" if geom == "rppi" else "multipoles"
@@ -531,7 +543,7 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 				write_dataset_hdf5(g, X + "_SplusD", data=SpD)
 				write_dataset_hdf5(g, X + "_RR_g_plus", data=RR)
 				if num_box:
-					write_dataset_hdf5(g, X + "_sigmasq", data=np.zeros_like(DD))
+					write_dataset_hdf5(g, X + "_sigmasq", data=sigsq)
 				write_dataset_hdf5(g, X + n1, data=sep)
 				write_dataset_hdf5(g, X + n2, data=mid2)
 				g = create_group_hdf5(f, f"{snap}/{top}/xi_g_cross/{jk_group_name}")
@@ -539,7 +551,7 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 				write_dataset_hdf5(g, X, data=xi_gx)
 				write_dataset_hdf5(g, X + "_RR_g_cross", data=RR)
 				if num_box:
-					write_dataset_hdf5(g, X + "_sigmasq", data=np.zeros_like(DD))
+					write_dataset_hdf5(g, X + "_sigmasq", data=sigsq)
 				write_dataset_hdf5(g, X + n1, data=sep)
 				write_dataset_hdf5(g, X + n2, data=mid2)
 				g = create_group_hdf5(f, f"{snap}/{top}/xi_gg/")
@@ -547,7 +559,7 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 				write_dataset_hdf5(g, X + "_DD", data=DD)
 				write_dataset_hdf5(g, X + "_RR_gg", data=RR)
 				if num_box:
-					write_dataset_hdf5(g, X + "_sigmasq", data=np.zeros_like(DD))
+					write_dataset_hdf5(g, X + "_sigmasq", data=sigsq)
 				write_dataset_hdf5(g, X + n1, data=sep)
 				write_dataset_hdf5(g, X + n2, data=mid2)
 
@@ -614,7 +626,10 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 		if corr_type not in ("both", "g+", "gg"):
 			raise KeyError("Unknown value for corr_type. Choose from [g+, gg, both]")
 		t0 = time.perf_counter()
-		res = self._pair_sums(geom, masks, L, ellipticity, rp_cut)
+		# temp_file_path=False selects the reference's brute variants (measure_IA.py:102-131), whose jackknife flavour also
+		# accumulates the `_sigmasq` variance; any temporary path selects the tree / multiprocessing variants (zeros)
+		want_var = isinstance(temp_file_path, (bool, int)) and temp_file_path == False and num_jk > 0  # noqa: E712
+		res = self._pair_sums(geom, masks, L, ellipticity, rp_cut, variance=want_var)
 		t1 = time.perf_counter()
 		is_writer = self.last_stats["rank"] == 0
 		if is_writer and self.output_file_name is not None:
@@ -638,10 +653,12 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 		self._measure("rmu", dataset_name, corr_type, num_jk, temp_file_path, masks, ellipticity, rp_cut=None)
 
 
-def combine_across_ranks(dd_count, dd_w, spd, scd, jk_count, jk_w, spd_jk, stats):
+def combine_across_ranks(dd_count, dd_w, spd, scd, jk_count, jk_w, spd_jk, stats, var=None):
 	"""The one exchange step of the sharded path (reference: parent-side `+=` over worker results,
-	measure_w_box_jk.py:775-780): integer counts by an all-reduce (exact in any order), fp64 sums by an all-gather
-	followed by a fixed rank-order sum so that the result does not depend on arrival order."""
+	measure_w_box_jk.py:775-780).  ONE collective: the integer counts and the bit patterns of the fp64 sums travel in a
+	single int64 all-gather (<= 0.25 MB per rank over NVLink; latency-bound, so one call instead of two); the counts are then
+	summed as integers (exact in any order) and the fp64 sums in fixed rank order (`mia_combine_partials_f64`), so the
+	result does not depend on arrival order."""
 	import torch
 	import torch.distributed as dist
 
@@ -649,26 +666,30 @@ def combine_across_ranks(dd_count, dd_w, spd, scd, jk_count, jk_w, spd_jk, stats
 
 	world = dist.get_world_size()
 	ints = torch.cat([dd_count.flatten(), jk_count.flatten(), stats.flatten()])
-	dist.all_reduce(ints, op=dist.ReduceOp.SUM)
+	f_parts = (dd_w, spd, scd, jk_w, spd_jk) + ((var,) if var is not None else ())
+	floats = torch.cat([t.flatten() for t in f_parts])
+	packed = torch.cat([ints, floats.view(torch.int64)])
+	flat = torch.empty(world * packed.numel(), dtype=torch.int64, device=packed.device)
+	dist.all_gather_into_tensor(flat, packed)
+	gathered = flat.view(world, packed.numel())
+	ints = gathered[:, :ints.numel()].sum(dim=0)
 	n0, n1 = dd_count.numel(), jk_count.numel()
 	dd_count = ints[:n0].view_as(dd_count)
 	jk_count = ints[n0:n0 + n1].view_as(jk_count)
 	stats_sum = ints[n0 + n1:].view_as(stats)
-	floats = torch.cat([t.flatten() for t in (dd_w, spd, scd, jk_w, spd_jk)])
-	flat = torch.empty(world * floats.numel(), dtype=floats.dtype, device=floats.device)
-	dist.all_gather_into_tensor(flat, floats)
-	gathered = flat.view(world, floats.numel())
+	parts = gathered[:, packed.numel() - floats.numel():].contiguous().view(torch.float64)
 	if floats.is_cuda:
-		total = ops.combine_partials(gathered)
+		total = ops.combine_partials(parts)
 	else:  # gloo tests of the host logic
-		total = gathered[0].clone()
+		total = parts[0].clone()
 		for r in range(1, world):
-			total += gathered[r]
+			total += parts[r]
 	outs, o = [], 0
-	for t in (dd_w, spd, scd, jk_w, spd_jk):
+	for t in f_parts:
 		outs.append(total[o:o + t.numel()].view_as(t))
 		o += t.numel()
 	stats_out = stats_sum.clone()
 	stats_out[4] = stats[4]  # kernel id is not additive
 	stats_out[5] = stats[5]
-	return dd_count, outs[0], outs[1], outs[2], jk_count, outs[3], outs[4], stats_out
+	res = (dd_count, outs[0], outs[1], outs[2], jk_count, outs[3], outs[4], stats_out)
+	return res + (outs[5],) if var is not None else res

@@ -33,7 +33,7 @@ struct Plan {
 	TiledConfig tiled;
 	// workspace offsets
 	size_t off_cand, off_cand_jk, off_prim, off_cell_start, off_prim_cell_start, off_keys_in, off_keys_out, off_idx_in,
-		off_idx_out, off_cub, cub_bytes, off_red_cnt, off_red_f, off_cnt, off_ddw, off_sp, off_sc, off_stats, off_flags,
+		off_idx_out, off_cub, cub_bytes, off_red_cnt, off_red_f, off_cnt, off_ddw, off_sp, off_sc, off_var, off_stats, off_flags,
 		off_tiled, total;
 };
 
@@ -103,7 +103,7 @@ int make_plan(const mia_params *p, int64_t nD, int64_t nS, Plan &pl) {
 	} else {
 		pl.n_partials = pl.tiled.n_partials;
 		pl.g.order = pl.tiled.v2 ? 1 : 0;  // row-streaming (r_p, Pi) kernel: candidates sorted by (u row, slab, v cell)
-		if (ordered_only || env_int("MIA_SYM", 1) == 0) pl.tiled.sym_ok = 0;
+		if (ordered_only || p->variance || env_int("MIA_SYM", 1) == 0) pl.tiled.sym_ok = 0;
 	}
 	// the symmetric auto-correlation kernel needs 64-byte candidate records; whether the two samples really are the same
 	// catalogue is only known at call time, so the workspace is sized for it whenever the sizes agree
@@ -138,6 +138,7 @@ int make_plan(const mia_params *p, int64_t nD, int64_t nS, Plan &pl) {
 	pl.off_ddw = take(sizeof(double) * acc);
 	pl.off_sp = take(sizeof(double) * acc);
 	pl.off_sc = take(sizeof(double) * acc);
+	pl.off_var = take(p->variance ? sizeof(double) * (size_t)pl.n_partials * pl.nb : 0);
 	pl.off_stats = take(sizeof(unsigned long long) * 8);
 	pl.off_flags = take(sizeof(int) * 8);
 	pl.off_tiled = take(pl.kernel == MIA_KERNEL_TILED ? tiled_workspace_bytes(pl.tiled, pl.g, nD, nS) : 0);
@@ -252,6 +253,15 @@ __global__ void k_reduce_partials_stage2(unsigned long long *__restrict__ cnt, d
 	sc[e] = d;
 }
 
+// Fixed-order sum of the per-warp variance copies.
+__global__ void k_reduce_var(const double *__restrict__ var, int n_partials, int nb, double *__restrict__ out) {
+	const int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= nb) return;
+	double s = 0.0;
+	for (int p = 0; p < n_partials; p++) s += var[(size_t)p * nb + b];
+	out[b] = s;
+}
+
 __global__ void k_copy_stats(const unsigned long long *in, uint64_t *out, unsigned long long kernel,
 							 unsigned long long cells, unsigned long long tasks, unsigned long long launches) {
 	if (threadIdx.x < 4) out[threadIdx.x] = in[threadIdx.x];
@@ -302,6 +312,7 @@ int mia_paircount(const mia_params *params, const mia_sample *D, const mia_sampl
 	if ((D->n > 0 && !D->pos) || (S->n > 0 && (!S->pos || !S->axis || !S->e))) return MIA_ERR_ARG;
 	if (!out->dd_count || !out->dd_w || !out->spd || !out->scd) return MIA_ERR_ARG;
 	if (params->num_jk > 0 && (!D->jk || !S->jk)) return MIA_ERR_ARG;
+	if (params->variance && !out->var) return MIA_ERR_ARG;
 	if (shard.count < 1 || shard.index < 0 || shard.index >= shard.count) return MIA_ERR_ARG;
 	cudaStream_t st = (cudaStream_t)stream;
 	const int64_t nD = D->n, nS = S->n;
@@ -338,6 +349,7 @@ int mia_paircount(const mia_params *params, const mia_sample *D, const mia_sampl
 	A.ddw = (double *)(ws + pl.off_ddw);
 	A.sp = (double *)(ws + pl.off_sp);
 	A.sc = (double *)(ws + pl.off_sc);
+	A.var = params->variance ? (double *)(ws + pl.off_var) : nullptr;
 	A.stats = (unsigned long long *)(ws + pl.off_stats);
 	A.rows = pl.rows;
 	int *flags = (int *)(ws + pl.off_flags);
@@ -453,6 +465,11 @@ int mia_paircount(const mia_params *params, const mia_sample *D, const mia_sampl
 	const int J = params->num_jk > 0 ? params->num_jk : 1;
 	k_finalize<<<(pl.nb + 127) / 128, 128, 0, st>>>(A.cnt, A.ddw, A.sp, A.sc, 1, J, pl.nb, params->num_jk, *out);
 	MIA_CUDA_CHECK(cudaGetLastError());
+	if (params->variance) {
+		k_reduce_var<<<(pl.nb + 127) / 128, 128, 0, st>>>(A.var, pl.n_partials, pl.nb, out->var);
+		MIA_CUDA_CHECK(cudaGetLastError());
+		n_launches += 1;
+	}
 	if (out->stats) {
 		n_launches += 2;  // finalize + copy_stats
 		k_copy_stats<<<1, 32, 0, st>>>(A.stats, out->stats,
@@ -508,6 +525,7 @@ int mia_paircount_host(const mia_params *params, const mia_sample *Dh, const mia
 	const size_t o_jcnt = take(sizeof(int64_t) * (size_t)J * nb), o_jddw = take(sizeof(double) * (size_t)J * nb),
 				 o_jsp = take(sizeof(double) * (size_t)J * nb);
 	const size_t o_stats = take(sizeof(uint64_t) * 8);
+	const size_t o_var = take(params->variance ? sizeof(double) * nb : 0);
 	const size_t o_ws = take(ws_bytes);
 	unsigned char *d = nullptr;
 	MIA_CUDA_CHECK(cudaMalloc(&d, o + 256));
@@ -548,6 +566,7 @@ int mia_paircount_host(const mia_params *params, const mia_sample *Dh, const mia
 		od.dd_jk_w = J > 0 ? (double *)(d + o_jddw) : nullptr;
 		od.spd_jk = J > 0 ? (double *)(d + o_jsp) : nullptr;
 		od.stats = (uint64_t *)(d + o_stats);
+		od.var = params->variance ? (double *)(d + o_var) : nullptr;
 		rc = mia_paircount(params, &Dd, &Sd, shard, &od, d + o_ws, ws_bytes, (void *)st);
 	}
 #define D2H(dst, off, bytes)                                                                         \
@@ -563,6 +582,7 @@ int mia_paircount_host(const mia_params *params, const mia_sample *Dh, const mia
 	D2H(out_h->dd_jk_w, o_jddw, sizeof(double) * (size_t)J * nb);
 	D2H(out_h->spd_jk, o_jsp, sizeof(double) * (size_t)J * nb);
 	D2H(out_h->stats, o_stats, sizeof(uint64_t) * 8);
+	if (params->variance) D2H(out_h->var, o_var, sizeof(double) * nb);
 #undef D2H
 	cudaError_t se = cudaStreamSynchronize(st);
 	if (rc == MIA_OK && se != cudaSuccess) rc = (int)se;

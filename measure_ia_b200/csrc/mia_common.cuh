@@ -59,6 +59,7 @@ struct Grid {
 struct Accum {
 	unsigned long long *cnt;  // [rows][nb]
 	double *ddw, *sp, *sc;    // [rows][nb]
+	double *var;              // [nb] per accumulator copy (no jackknife rows): sum (w_D w_S e+)^2, or NULL
 	unsigned long long *stats;
 	int rows;                 // 2 * max(num_jk, 1)
 };

@@ -82,12 +82,14 @@ __global__ void __launch_bounds__(128) k_general(DevParams P, Grid G, const Prim
 							atomicAdd(&s_ddw[b], ww);
 							atomicAdd(&s_sp[b], tp);
 							atomicAdd(&s_sc[b], tc);
+							if (A.var) atomicAdd(&A.var[b], tp * tp);  // brute variants' `variance`, measure_w_box_jk.py:196
 						} else {
 							const size_t ra = (size_t)p.jk * nb + b;
 							atomicAdd(&A.cnt[ra], 1ull);
 							atomicAdd(&A.ddw[ra], ww);
 							atomicAdd(&A.sp[ra], tp);
 							atomicAdd(&A.sc[ra], tc);
+							if (A.var) atomicAdd(&A.var[b], tp * tp);
 							const int jd = G.cand_jk[j];
 							if (jd != p.jk) {
 								const size_t rb = (size_t)(J + jd) * nb + b;

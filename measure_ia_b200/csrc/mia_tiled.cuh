@@ -97,6 +97,7 @@ struct TiledConfig {
 	int n_lr;        // (r, mu_r): line-of-sight regions (= jackknife sub-boxes per side when the slabs are aligned with them)
 	int v2;          // (r_p, Pi): row-streaming kernel (mia_tiled_rppi2.cuh); n_lr then counts the regions along v
 	int sym_ok;      // (r_p, Pi), row-streaming: the grid admits the symmetric auto-correlation kernel (mia_tiled_rppi2s.cuh)
+	int sig;         // also accumulate sum (w_D w_S e+)^2 per bin (mia_params.variance)
 	int sym;         // ... and this call uses it (position sample == shape sample): bytes per candidate record (CandSU / CandSW), else 0
 	int n_partials;  // accumulator copies = worker warps
 	int n_ctas;
@@ -135,18 +136,18 @@ struct TiledArgs {
 
 // defined in mia_tiled_rmu.cuh
 inline bool rmu_supported(const mia_params *p, int &w_r);
-inline size_t tiled_rmu_smem_bytes(bool unit_w);
-inline int launch_rmu(const TiledArgs &a, bool unit_w, bool los2, int n_ctas, size_t smem, cudaStream_t st);
+inline size_t tiled_rmu_smem_bytes(bool unit_w, bool sig);
+inline int launch_rmu(const TiledArgs &a, bool unit_w, bool los2, bool sig, int n_ctas, size_t smem, cudaStream_t st);
 inline bool plan_rmu_grid(const mia_params *p, int n_side, TiledConfig &cfg, int &nc, int &nz, int &k);
 // defined in mia_tiled_rppi2.cuh
 struct TiledWorkspace;
 inline bool plan_rppi2_grid(const mia_params *p, int n_side, TiledConfig &cfg, int &nc, int nz, int &k);
-inline size_t tiled_rppi2_smem_bytes(bool unit_w);
+inline size_t tiled_rppi2_smem_bytes(bool unit_w, bool sig);
 inline int rppi2_prepare(const TiledConfig &cfg, const GridDims &g, const TiledWorkspace &w, cudaStream_t st);
 inline int rppi2_fill_tasks(const TiledArgs &a, const int64_t *prim_cell_start, const int64_t *cell_start, const int32_t *task_off,
 							int ncol_s, int nzs, int k, int split, int sym, int32_t *task_col, int64_t *task_first, int32_t *task_n,
 							int32_t *task_slab, unsigned long long *task_cost, int32_t *n_tasks, cudaStream_t st);
-inline int launch_rppi2(const TiledArgs &a, bool unit_w, int n_ctas, size_t smem, cudaStream_t st);
+inline int launch_rppi2(const TiledArgs &a, bool unit_w, bool sig, int n_ctas, size_t smem, cudaStream_t st);
 // defined in mia_tiled_rppi2s.cuh
 inline bool rppi2s_supported(int ncu, int k, int ratio);
 inline size_t tiled_rppi2s_smem_bytes(bool unit_w);
@@ -224,6 +225,7 @@ inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g,
 	cfg.v2 = 0;
 	cfg.sym_ok = 0;
 	cfg.sym = 0;
+	cfg.sig = p->variance ? 1 : 0;
 	// columns: about a quarter of the search radius wide
 	int nc = (int)floor(L / (reach / 4.0));
 	if (nc > 2048) nc = 2048;
@@ -266,6 +268,8 @@ inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g,
 		const char *ev = getenv("MIA_RPPI_V2");
 		int v2 = ev ? atoi(ev) : MIA_RPPI_V2;
 		int div2 = 0;
+		if (cfg.sig && v2 == 0) v2 = 1;
+		const bool must_rows = cfg.sig;  // only the row-streaming kernel has the variance variant
 		if (v2 == 1) {
 			const double rho = (double)nD / (L * L * L);
 			auto piece = [&](int d) { return rho * (reach / d) * (1.6 * reach) * (L / nz); };  // candidates per streamed range
@@ -273,6 +277,10 @@ inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g,
 			else if (piece(10) >= 100.0) div2 = 10;
 			else if (piece(6) >= 15.0) div2 = 6;
 			else v2 = 0;
+			if (v2 == 0 && must_rows) {
+				v2 = 2;
+				div2 = 6;
+			}
 		}
 		if (v2) {  // row-streaming kernel: finer columns, coarser shape columns
 			cfg.w_r = div2;  // (r_p, Pi): carries the chosen cells per r_max to plan_rppi2_grid (0 = default)
@@ -745,8 +753,9 @@ __device__ __forceinline__ void sts_u32_if(bool p, uint32_t addr, unsigned a) {
 // ------------------------------------------------------------------------------------------------------------------
 // Shared-memory addresses (bytes, shared window) of the thread-private accumulators:
 //   a2 : [slot][thread] double2 {sum e+ , sum ex}     ac : [slot][thread] u32 pair count     aw : [slot][thread] sum w_D
+//   av : [slot][thread] sum (w_D e+)^2 (SIG variants: the brute variants' `variance`, measure_w_box_jk.py:196)
 struct PrivAcc {
-	uint32_t a2, ac, aw;
+	uint32_t a2, ac, aw, av;
 };
 
 // One accumulation window of r bins [ra, ra + W_R): its squared-separation limits and interior thresholds.
@@ -764,7 +773,7 @@ struct RWindow {
 // All of these are exactly the reference's `sep -= L` / `sep += L` (measure_w_box_jk.py:403-404): x + 0.0 == x.
 // Returns true when some candidate has |cos| within 1e-11 of 1 for this lane: those pairs are NOT accumulated here
 // but re-evaluated with the reference's exact operation sequence by slow_pairs() (its NaN rule, :416-417).
-template <bool UNITW, bool XYS, bool ZW, bool GEN>
+template <bool UNITW, bool XYS, bool ZW, bool GEN, bool SIG = false>
 __device__ __forceinline__ bool pair_loop(uint32_t cb, int n, int periodic, double L, double halfL, double pu, double pv,
 										  double pl, double a0, double a1, double su, double sv, const RWindow &rw,
 										  double hi_lane, const ZWindow &zw, const PrivAcc &acc) {
@@ -819,10 +828,11 @@ __device__ __forceinline__ bool pair_loop(uint32_t cb, int n, int periodic, doub
 		const uint32_t so = (uint32_t)slot * (uint32_t)TP;
 #if !MIA_SWP
 		// private slots: loads first, the arithmetic below hides their latency
-		double s0, s1, sw = 0.0;
+		double s0, s1, sw = 0.0, sq = 0.0;
 		lds_v2(s0, s1, acc.a2 + so * 16u);
 		const unsigned c0 = lds_u32(acc.ac + so * 4u);
 		if (!UNITW) sw = lds_f64(acc.aw + so * 8u);
+		if (SIG) sq = lds_f64(acc.av + so * 8u);
 #endif
 		const double cr = fma(du, a0, __dmul_rn(dv, a1));   // r_p cos(phi)
 		const double sr = fma(du, a1, -__dmul_rn(dv, a0));  // r_p sin(phi) (sign irrelevant)
@@ -866,6 +876,7 @@ __device__ __forceinline__ bool pair_loop(uint32_t cb, int n, int periodic, doub
 			gc *= cw;
 			sts_f64_if(ok, acc.aw + so * 8u, sw + cw);
 		}
+		if (SIG) sts_f64_if(ok, acc.av + so * 8u, fma(gp, gp, sq));
 		sts_v2_if(ok, acc.a2 + so * 16u, s0 + gp, s1 + gc);
 		sts_u32_if(ok, acc.ac + so * 4u, c0 + 1u);
 #endif
@@ -888,7 +899,7 @@ __device__ __forceinline__ bool pair_loop(uint32_t cb, int n, int periodic, doub
 
 // Rare path: rescan the chunk for the pairs pair_loop skipped (|cos| ~ 1), with the reference's exact operation
 // sequence for the separation, cos and its NaN rule.
-template <bool UNITW>
+template <bool UNITW, bool SIG = false>
 __device__ __noinline__ void slow_pairs(bool lane_susp, uint32_t cb, int n, int periodic, double L, double halfL, double pu,
 										double pv, double pl, double a0, double a1, const RWindow rw, double w_hi, double t_lo,
 										double t_hi, double t_split, PrivAcc acc, unsigned long long &nan_pairs) {
@@ -936,6 +947,7 @@ __device__ __noinline__ void slow_pairs(bool lane_susp, uint32_t cb, int n, int 
 			gc *= cw;
 			sts_f64(acc.aw + so * 8u, lds_f64(acc.aw + so * 8u) + cw);
 		}
+		if (SIG) sts_f64(acc.av + so * 8u, fma(gp, gp, lds_f64(acc.av + so * 8u)));
 		sts_v2(acc.a2 + so * 16u, s0 + gp, s1 + gc);
 		sts_u32(acc.ac + so * 4u, c0 + 1u);
 	}
@@ -947,11 +959,12 @@ __device__ __noinline__ void slow_pairs(bool lane_susp, uint32_t cb, int n, int 
 struct FlushCtx {
 	unsigned long long *pcnt;
 	double *pddw, *psp, *psc;
+	double *pvar;  // [nb] of this warp's copy (SIG variants), else NULL
 	int *flags;
 	int n_2, nb, J, num_jk;
 };
 
-template <bool UNITW>
+template <bool UNITW, bool SIG = false>
 __device__ __noinline__ unsigned flush_slots(const FlushCtx &fc, PrivAcc acc, unsigned key, bool dead, double pe, double pw,
 											 int ra, int rb, int jkD) {
 	const int lane = threadIdx.x & 31;
@@ -963,7 +976,7 @@ __device__ __noinline__ unsigned flush_slots(const FlushCtx &fc, PrivAcc acc, un
 		const unsigned grp = __ballot_sync(0xffffffffu, key == k) & todo;
 		const bool in = (grp >> lane) & 1u;
 		unsigned tot_cnt = 0;
-		double tot_sp = 0.0, tot_sc = 0.0, tot_dw = 0.0;
+		double tot_sp = 0.0, tot_sc = 0.0, tot_dw = 0.0, tot_sq = 0.0;
 #pragma unroll 1
 		for (int sl = 0; sl < NSLOT; sl++) {
 			const uint32_t so = (uint32_t)sl * TP;
@@ -975,11 +988,13 @@ __device__ __noinline__ unsigned flush_slots(const FlushCtx &fc, PrivAcc acc, un
 			const double xs = warp_sum(v0 * pe);
 			const double ys = warp_sum(v1 * pe);
 			const double zs = UNITW ? (double)csum : warp_sum(in ? lds_f64(acc.aw + so * 8u) * pw : 0.0);
+			const double qs = SIG ? warp_sum(in ? lds_f64(acc.av + so * 8u) * (pe * pe) : 0.0) : 0.0;
 			if (lane == sl) {
 				tot_cnt = csum;
 				tot_sp = xs;
 				tot_sc = ys;
 				tot_dw = zs;
+				tot_sq = qs;
 			}
 		}
 		if (lane < NSLOT && tot_cnt) {
@@ -1006,6 +1021,7 @@ __device__ __noinline__ unsigned flush_slots(const FlushCtx &fc, PrivAcc acc, un
 					fc.pddw[ib] = d_b + tot_dw;
 					fc.psp[ib] = p_b + tot_sp;
 				}
+				if (SIG) fc.pvar[bin] += tot_sq;
 				binned += tot_cnt;
 			}
 		}
@@ -1016,6 +1032,7 @@ __device__ __noinline__ unsigned flush_slots(const FlushCtx &fc, PrivAcc acc, un
 	for (int sl = 0; sl < NSLOT; sl++) {
 		sts_v2(acc.a2 + (uint32_t)sl * TP * 16u, 0.0, 0.0);
 		if (!UNITW) sts_f64(acc.aw + (uint32_t)sl * TP * 8u, 0.0);
+		if (SIG) sts_f64(acc.av + (uint32_t)sl * TP * 8u, 0.0);
 		sts_u32(acc.ac + (uint32_t)sl * TP * 4u, 0u);
 	}
 	return binned;
@@ -1109,6 +1126,7 @@ __global__ void __launch_bounds__(TP, MIA_MIN_CTAS) k_tiled_rppi(const TiledArgs
 	acc.a2 = acc_u32 + (uint32_t)tid * 16u;
 	acc.aw = acc_u32 + (uint32_t)NSLOT * TP * 16u + (uint32_t)tid * 8u;
 	acc.ac = acc_u32 + (uint32_t)NSLOT * TP * (UNITW ? 16u : 24u) + (uint32_t)tid * 4u;
+	acc.av = 0u;  // (the cell-by-cell kernel has no variance variant: such calls are planned onto the row-streaming kernel)
 
 	if (tid == 0) {
 		for (int s = 0; s < TW * STAGES; s++) mbar_init(&full[s], 1);
@@ -1131,7 +1149,7 @@ __global__ void __launch_bounds__(TP, MIA_MIN_CTAS) k_tiled_rppi(const TiledArgs
 		if (nt > 0) {
 			const double total2 = 2.0 * (double)a.task_cum[nt - 1];
 			const int RG = a.shard_count * a.n_workers;
-			const int mine = a.shard_index * a.n_workers + (int)blockIdx.x * TW + warp;
+			const int mine = ((int)blockIdx.x * TW + warp) * a.shard_count + a.shard_index;  // slots interleaved across ranks
 			auto slot_of = [&](int t) {
 				const double mid2 = 2.0 * (double)a.task_cum[t] - (double)a.task_cost[t];
 				int s = (int)(mid2 / total2 * (double)RG);
@@ -1167,6 +1185,7 @@ __global__ void __launch_bounds__(TP, MIA_MIN_CTAS) k_tiled_rppi(const TiledArgs
 	fc.pddw = pddw;
 	fc.psp = psp;
 	fc.psc = psc;
+	fc.pvar = nullptr;
 	fc.flags = a.flags;
 	fc.n_2 = P.n_2;
 	fc.nb = nb;
@@ -1506,8 +1525,11 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &gc, const GridDi
 	// grouping of the fp64 sums, hence every output bit, is the same for the weighted and the unit-weight kernel variants,
 	// which is what lets w = 0.5 scale the results by exactly 1/4 (reference tests/test_weights.py:34-35). ---------------
 	const bool rmu = cfg.geom == MIA_GEOM_RMU;
-	const size_t smem = rmu ? tiled_rmu_smem_bytes(unit_w)
-							: (cfg.sym ? tiled_rppi2s_smem_bytes(unit_w) : (cfg.v2 ? tiled_rppi2_smem_bytes(unit_w) : tiled_smem_bytes(unit_w)));
+	const bool sig = cfg.sig != 0;
+	if (sig && !rmu && !cfg.v2) return MIA_ERR_UNSUPPORTED;  // (plan_tiled never selects the cell-by-cell kernel for such calls)
+	const size_t smem = rmu ? tiled_rmu_smem_bytes(unit_w, sig)
+							: (cfg.sym ? tiled_rppi2s_smem_bytes(unit_w)
+									   : (cfg.v2 ? tiled_rppi2_smem_bytes(unit_w, sig) : tiled_smem_bytes(unit_w)));
 	if (rmu || cfg.v2) {
 	} else if (unit_w) {
 		MIA_CUDA_CHECK(cudaFuncSetAttribute(k_tiled_rppi<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1548,13 +1570,13 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &gc, const GridDi
 	a.flags = flags;
 	if (ev_before) MIA_CUDA_CHECK(cudaEventRecord(ev_before, st));
 	if (rmu) {
-		const int rc = launch_rmu(a, unit_w, P.los == 2, cfg.n_ctas, smem, st);
+		const int rc = launch_rmu(a, unit_w, P.los == 2, sig, cfg.n_ctas, smem, st);
 		if (rc) return rc;
 	} else if (cfg.sym) {
 		const int rc = launch_rppi2s(a, unit_w, cfg.n_ctas, smem, st);
 		if (rc) return rc;
 	} else if (cfg.v2) {
-		const int rc = launch_rppi2(a, unit_w, cfg.n_ctas, smem, st);
+		const int rc = launch_rppi2(a, unit_w, sig, cfg.n_ctas, smem, st);
 		if (rc) return rc;
 	} else if (unit_w) {
 		k_tiled_rppi<true><<<cfg.n_ctas, TP, smem, st>>>(a);

@@ -50,9 +50,9 @@ constexpr int MAX_NEIGH_RMU = 384;  // neighbour (candidate) columns per task
 #define MIA_UNROLL_RMU 2
 #endif
 
-inline size_t tiled_rmu_smem_bytes(bool unit_w) {
+inline size_t tiled_rmu_smem_bytes(bool unit_w, bool sig) {
 	const size_t fixed = sizeof(Cand) * TW * STAGES * CH_RMU + sizeof(int) * TW * MAX_NEIGH_RMU + 256 + 768;
-	const size_t per_slot = (size_t)TP * (8 + 8 + 4 + (unit_w ? 0 : 8));
+	const size_t per_slot = (size_t)TP * (8 + 8 + 4 + (unit_w ? 0 : 8) + (sig ? 8 : 0));
 	return fixed + per_slot * NS_RMU;
 }
 
@@ -309,7 +309,7 @@ struct RmuWindow {
 // (su, sv, sl); 2: every separation wrapped per pair (the chunk straddles +-L/2 for the warp: tiny boxes only).
 // A warp works on hsplit candidates at a time (one per group of 32 / hsplit lanes): cb = address of this lane's first
 // candidate, n = number of candidates of this lane, hstep = bytes between them.
-template <bool UNITW, bool LOS2, int VAR>
+template <bool UNITW, bool LOS2, int VAR, bool SIG>
 __device__ __forceinline__ bool pair_loop_rmu(uint32_t cb, int n, uint32_t hstep, double L, double halfL, double pu, double pv,
 											  double pl, double a0, double a1, double su, double sv, double sl, double w_lo,
 											  double w_hi, double w_thr, double w_cut, double hn, double tbias, int n_mu,
@@ -352,10 +352,11 @@ __device__ __forceinline__ bool pair_loop_rmu(uint32_t cb, int n, uint32_t hstep
 		const RmuApprox ap = rmu_approx(du, dv, dz, rp2, s, a0, a1, hn, tbias, n_mu);
 		const int slot = ap.idx + ((s >= w_thr) ? n_mu : 0);
 		const uint32_t so = (uint32_t)slot * (uint32_t)TP;
-		double s0, s1, sw = 0.0;
+		double s0, s1, sw = 0.0, sq = 0.0;
 		lds_v2(s0, s1, acc.a2 + so * 16u);
 		const unsigned c0 = lds_u32(acc.ac + so * 4u);
 		if (!UNITW) sw = lds_f64(acc.aw + so * 8u);
+		if (SIG) sq = lds_f64(acc.av + so * 8u);
 		lane_susp = lane_susp || (ok && ap.susp);
 		ok = ok && !ap.susp;
 		double gp = ap.gp, gc = ap.gc;
@@ -364,6 +365,7 @@ __device__ __forceinline__ bool pair_loop_rmu(uint32_t cb, int n, uint32_t hstep
 			gc *= cw;
 			sts_f64_if(ok, acc.aw + so * 8u, sw + cw);
 		}
+		if (SIG) sts_f64_if(ok, acc.av + so * 8u, fma(gp, gp, sq));  // (w_D e+)^2: measure_m_box_jk.py:207
 		sts_v2_if(ok, acc.a2 + so * 16u, s0 + gp, s1 + gc);
 		sts_u32_if(ok, acc.ac + so * 4u, c0 + 1u);
 		cu = mu_;
@@ -379,7 +381,7 @@ __device__ __forceinline__ bool pair_loop_rmu(uint32_t cb, int n, uint32_t hstep
 }
 
 // Rare path: rescan the chunk for the pairs the fast loop skipped and evaluate them exactly as the reference does.
-template <bool UNITW, bool LOS2>
+template <bool UNITW, bool LOS2, bool SIG>
 __device__ __noinline__ void slow_pairs_rmu(bool lane_susp, uint32_t cb, int n, int periodic, double L, double halfL,
 											double pu, double pv, double pl, double a0, double a1, const RmuWindow rw,
 											double hi_lane, double hn, double tbias, int n_mu, const double *thr2,
@@ -422,6 +424,7 @@ __device__ __noinline__ void slow_pairs_rmu(bool lane_susp, uint32_t cb, int n, 
 			gc *= cw;
 			sts_f64(acc.aw + so * 8u, lds_f64(acc.aw + so * 8u) + cw);
 		}
+		if (SIG) sts_f64(acc.av + so * 8u, fma(gp, gp, lds_f64(acc.av + so * 8u)));
 		sts_v2(acc.a2 + so * 16u, s0 + gp, s1 + gc);
 		sts_u32(acc.ac + so * 4u, c0 + 1u);
 	}
@@ -429,7 +432,7 @@ __device__ __noinline__ void slow_pairs_rmu(bool lane_susp, uint32_t cb, int n, 
 
 // Flush: fixed-order warp reduction of the private slots into this warp's accumulator copy in HBM.  All lanes share the
 // slot -> bin map (slot = r_offset * n_mu + mu bin); lanes are grouped by the jackknife label of their shape galaxy.
-template <bool UNITW>
+template <bool UNITW, bool SIG>
 __device__ __noinline__ unsigned flush_slots_rmu(const FlushCtx &fc, PrivAcc acc, int jkS, bool dead, double pe, double pw,
 												 int ra, int rb, int n_mu, int ns, int jkD) {
 	const int lane = threadIdx.x & 31;
@@ -441,7 +444,7 @@ __device__ __noinline__ unsigned flush_slots_rmu(const FlushCtx &fc, PrivAcc acc
 		const unsigned grp = __ballot_sync(0xffffffffu, jkS == k) & todo;
 		const bool in = (grp >> lane) & 1u;
 		unsigned tot_cnt = 0;
-		double tot_sp = 0.0, tot_sc = 0.0, tot_dw = 0.0;
+		double tot_sp = 0.0, tot_sc = 0.0, tot_dw = 0.0, tot_sq = 0.0;
 #pragma unroll 1
 		for (int sl = 0; sl < ns; sl++) {
 			const uint32_t so = (uint32_t)sl * TP;
@@ -453,11 +456,13 @@ __device__ __noinline__ unsigned flush_slots_rmu(const FlushCtx &fc, PrivAcc acc
 			const double xs = warp_sum(v0 * pe);
 			const double ys = warp_sum(v1 * pe);
 			const double zs = UNITW ? (double)csum : warp_sum(in ? lds_f64(acc.aw + so * 8u) * pw : 0.0);
+			const double qs = SIG ? warp_sum(in ? lds_f64(acc.av + so * 8u) * (pe * pe) : 0.0) : 0.0;
 			if (lane == sl) {
 				tot_cnt = csum;
 				tot_sp = xs;
 				tot_sc = ys;
 				tot_dw = zs;
+				tot_sq = qs;
 			}
 		}
 		if (lane < ns && tot_cnt) {
@@ -482,6 +487,7 @@ __device__ __noinline__ unsigned flush_slots_rmu(const FlushCtx &fc, PrivAcc acc
 					fc.pddw[ib] = d_b + tot_dw;
 					fc.psp[ib] = p_b + tot_sp;
 				}
+				if (SIG) fc.pvar[bin] += tot_sq;
 				binned += tot_cnt;
 			}
 		}
@@ -492,6 +498,7 @@ __device__ __noinline__ unsigned flush_slots_rmu(const FlushCtx &fc, PrivAcc acc
 	for (int sl = 0; sl < ns; sl++) {
 		sts_v2(acc.a2 + (uint32_t)sl * TP * 16u, 0.0, 0.0);
 		if (!UNITW) sts_f64(acc.aw + (uint32_t)sl * TP * 8u, 0.0);
+		if (SIG) sts_f64(acc.av + (uint32_t)sl * TP * 8u, 0.0);
 		sts_u32(acc.ac + (uint32_t)sl * TP * 4u, 0u);
 	}
 	return binned;
@@ -517,7 +524,7 @@ struct RmuCtx {
 	// per (task, window)
 	double L, halfL, lo, hi, thr, cut, hn, tbias;
 	int n_mu, ns, ra, rb, periodic, hlog, half;
-	uint32_t a2, aw, ac, ring_u32, hstep;
+	uint32_t a2, aw, ac, av, ring_u32, hstep;
 	const Cand *cand;
 	Cand *ring;
 	uint64_t *full;
@@ -536,7 +543,7 @@ __device__ __forceinline__ double code_shift(int code, double L) { return code =
 // Consume one round: lane e (bit e of mask) holds a column descriptor = up to two contiguous candidate ranges [sA, eA),
 // [sB, eB) with ONE jackknife label `lab` and warp-constant image codes.  Ranges are cut into chunks of <= CH_RMU,
 // streamed through the warp's double buffer (bulk copy of chunk k+1 in flight while chunk k is processed).
-template <bool UNITW, bool LOS2>
+template <bool UNITW, bool LOS2, bool SIG>
 __device__ __noinline__ void process_round(RmuCtx *cx, int sA, int eA, int sB, int eB, int lab, int codes, unsigned mask) {
 	const int lane = threadIdx.x & 31;
 	const double L = cx->L, halfL = cx->halfL, pu = cx->pu, pv = cx->pv, pl = cx->pl, a0 = cx->a0, a1 = cx->a1;
@@ -553,6 +560,7 @@ __device__ __noinline__ void process_round(RmuCtx *cx, int sA, int eA, int sB, i
 	acc.a2 = cx->a2;
 	acc.aw = cx->aw;
 	acc.ac = cx->ac;
+	acc.av = cx->av;
 	const uint32_t ring_u32 = cx->ring_u32, hstep = cx->hstep;
 	const Cand *cand = cx->cand;
 	Cand *ring = cx->ring;
@@ -566,7 +574,7 @@ __device__ __noinline__ void process_round(RmuCtx *cx, int sA, int eA, int sB, i
 	auto consume = [&]() {
 		if (pend_label != cur_label) {  // candidates of another jackknife region: flush the private slots
 			if (cur_label >= 0)
-				binned += flush_slots_rmu<UNITW>(cx->fc, acc, cx->jk, dead, cx->pe, cx->pw, rw.ra, cx->rb, n_mu, cx->ns, cur_label);
+				binned += flush_slots_rmu<UNITW, SIG>(cx->fc, acc, cx->jk, dead, cx->pe, cx->pw, rw.ra, cx->rb, n_mu, cx->ns, cur_label);
 			cur_label = pend_label;
 		}
 		const int cu_ = pend_codes & 3, cv_ = (pend_codes >> 2) & 3, cl_ = (pend_codes >> 4) & 3;
@@ -582,17 +590,17 @@ __device__ __noinline__ void process_round(RmuCtx *cx, int sA, int eA, int sB, i
 		const uint32_t cb = ring_u32 + (uint32_t)pend_st * (uint32_t)(CH_RMU * sizeof(Cand)) + (uint32_t)half * (uint32_t)sizeof(Cand);
 		bool susp;
 		if (cu_ == 3 || cv_ == 3 || cl_ == 3)
-			susp = pair_loop_rmu<UNITW, LOS2, 2>(cb, n_mine, hstep, L, halfL, pu, pv, pl, a0, a1, 0.0, 0.0, 0.0, rw.lo, hi_lane, rw.thr,
+			susp = pair_loop_rmu<UNITW, LOS2, 2, SIG>(cb, n_mine, hstep, L, halfL, pu, pv, pl, a0, a1, 0.0, 0.0, 0.0, rw.lo, hi_lane, rw.thr,
 												 rw.cut, hn, tbias, n_mu, acc);
 		else if (pend_codes & 63)
-			susp = pair_loop_rmu<UNITW, LOS2, 1>(cb, n_mine, hstep, L, halfL, pu, pv, pl, a0, a1, code_shift(cu_, L),
+			susp = pair_loop_rmu<UNITW, LOS2, 1, SIG>(cb, n_mine, hstep, L, halfL, pu, pv, pl, a0, a1, code_shift(cu_, L),
 												 code_shift(cv_, L), code_shift(cl_, L), rw.lo, hi_lane, rw.thr, rw.cut, hn, tbias,
 												 n_mu, acc);
 		else
-			susp = pair_loop_rmu<UNITW, LOS2, 0>(cb, n_mine, hstep, L, halfL, pu, pv, pl, a0, a1, 0.0, 0.0, 0.0, rw.lo, hi_lane, rw.thr,
+			susp = pair_loop_rmu<UNITW, LOS2, 0, SIG>(cb, n_mine, hstep, L, halfL, pu, pv, pl, a0, a1, 0.0, 0.0, 0.0, rw.lo, hi_lane, rw.thr,
 												 rw.cut, hn, tbias, n_mu, acc);
 		if (__any_sync(0xffffffffu, susp))
-			slow_pairs_rmu<UNITW, LOS2>(susp, cb, n_mine, cx->periodic, L, halfL, pu, pv, pl, a0, a1, rw, hi_lane, hn, tbias, n_mu,
+			slow_pairs_rmu<UNITW, LOS2, SIG>(susp, cb, n_mine, cx->periodic, L, halfL, pu, pv, pl, a0, a1, rw, hi_lane, hn, tbias, n_mu,
 										cx->thr2, acc, hstep, nan_pairs);
 		__syncwarp();  // every lane is done with the stage before it is refilled
 	};
@@ -636,7 +644,7 @@ __device__ __noinline__ void process_round(RmuCtx *cx, int sA, int eA, int sB, i
 	cx->nan_pairs += nan_pairs;
 }
 
-template <bool UNITW, bool LOS2>
+template <bool UNITW, bool LOS2, bool SIG>
 __global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	const DevParams &P = a.P;
@@ -664,7 +672,8 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 	RmuCtx cx;
 	cx.a2 = acc_u32 + (uint32_t)tid * 16u;
 	cx.aw = acc_u32 + (uint32_t)NS_RMU * TP * 16u + (uint32_t)tid * 8u;
-	cx.ac = acc_u32 + (uint32_t)NS_RMU * TP * (UNITW ? 16u : 24u) + (uint32_t)tid * 4u;
+	cx.av = acc_u32 + (uint32_t)NS_RMU * TP * (UNITW ? 16u : 24u) + (uint32_t)tid * 8u;
+	cx.ac = acc_u32 + (uint32_t)NS_RMU * TP * ((UNITW ? 16u : 24u) + (SIG ? 8u : 0u)) + (uint32_t)tid * 4u;
 	cx.ring_u32 = smem_u32(my_ring);
 	cx.ring = my_ring;
 	cx.full = full + warp * STAGES;
@@ -696,6 +705,7 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 	for (int s = 0; s < NS_RMU; s++) {
 		sts_v2(cx.a2 + (uint32_t)s * TP * 16u, 0.0, 0.0);
 		if (!UNITW) sts_f64(cx.aw + (uint32_t)s * TP * 8u, 0.0);
+		if (SIG) sts_f64(cx.av + (uint32_t)s * TP * 8u, 0.0);
 		sts_u32(cx.ac + (uint32_t)s * TP * 4u, 0u);
 	}
 	__syncthreads();  // the only CTA-wide synchronisation
@@ -707,7 +717,7 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 		if (nt > 0) {
 			const double total2 = 2.0 * (double)a.task_cum[nt - 1];
 			const int RG = a.shard_count * a.n_workers;
-			const int mine = a.shard_index * a.n_workers + (int)blockIdx.x * TW + warp;
+			const int mine = ((int)blockIdx.x * TW + warp) * a.shard_count + a.shard_index;  // slots interleaved across ranks
 			auto slot_of = [&](int t) {
 				const double mid2 = 2.0 * (double)a.task_cum[t] - (double)a.task_cost[t];
 				int s = (int)(mid2 / total2 * (double)RG);
@@ -732,6 +742,7 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 	cx.fc.pddw = a.A.ddw + part;
 	cx.fc.psp = a.A.sp + part;
 	cx.fc.psc = a.A.sc + part;
+	cx.fc.pvar = SIG ? a.A.var + (size_t)(blockIdx.x * TW + warp) * nb : nullptr;
 	cx.fc.flags = a.flags;
 	cx.fc.n_2 = P.n_2;
 	cx.fc.nb = nb;
@@ -950,7 +961,7 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 						if (r_eA > r_sA || r_eB > r_sB) r_lab = a.colreg[(long long)r_c * n_lr + g_r];
 					}
 					const unsigned m_simple = __ballot_sync(0xffffffffu, r_lab >= 0);
-					if (m_simple) process_round<UNITW, LOS2>(&cx, r_sA, r_eA, r_sB, r_eB, r_lab, r_codes, m_simple);
+					if (m_simple) process_round<UNITW, LOS2, SIG>(&cx, r_sA, r_eA, r_sB, r_eB, r_lab, r_codes, m_simple);
 					// ---- column-regions holding several labels (cells cut by a jackknife face: unaligned grids only) ------------
 					unsigned m_cplx = __ballot_sync(0xffffffffu, r_lab == -1);
 					while (m_cplx) {
@@ -974,7 +985,7 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 									c_lab = (c_nlab == 1) ? cinf->label : -2;
 								}
 								const unsigned m1 = __ballot_sync(0xffffffffu, c_nlab == 1);
-								if (m1) process_round<UNITW, LOS2>(&cx, c_s, c_e, 0, 0, c_lab, pc, m1);
+								if (m1) process_round<UNITW, LOS2, SIG>(&cx, c_s, c_e, 0, 0, c_lab, pc, m1);
 								unsigned mm = __ballot_sync(0xffffffffu, c_nlab > 1);
 								while (mm) {  // a cell with several labels: one label run at a time
 									const int f = __ffs(mm) - 1;
@@ -985,7 +996,7 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 										const int lb = a.cand_jk[pos];
 										int qq = pos + 1;
 										while (qq < end && a.cand_jk[qq] == lb) qq++;
-										process_round<UNITW, LOS2>(&cx, pos, qq, 0, 0, lb, pc, 1u);  // lane 0 carries the run
+										process_round<UNITW, LOS2, SIG>(&cx, pos, qq, 0, 0, lb, pc, 1u);  // lane 0 carries the run
 										pos = qq;
 									}
 								}
@@ -1000,7 +1011,8 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 				acc.a2 = cx.a2;
 				acc.aw = cx.aw;
 				acc.ac = cx.ac;
-				cx.binned += flush_slots_rmu<UNITW>(cx.fc, acc, p.jk, dead, cx.pe, p.w, ra, rb, n_mu, ns, cx.cur_label);
+				acc.av = cx.av;
+				cx.binned += flush_slots_rmu<UNITW, SIG>(cx.fc, acc, p.jk, dead, cx.pe, p.w, ra, rb, n_mu, ns, cx.cur_label);
 				cx.cur_label = -1;
 			}
 		}
@@ -1019,16 +1031,21 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 	}
 }
 
-template <bool UNITW, bool LOS2>
+template <bool UNITW, bool LOS2, bool SIG>
 inline int launch_rmu_variant(const TiledArgs &a, int n_ctas, size_t smem, cudaStream_t st) {
-	MIA_CUDA_CHECK(cudaFuncSetAttribute(k_tiled_rmu<UNITW, LOS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	k_tiled_rmu<UNITW, LOS2><<<n_ctas, TP, smem, st>>>(a);
+	MIA_CUDA_CHECK(cudaFuncSetAttribute(k_tiled_rmu<UNITW, LOS2, SIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	k_tiled_rmu<UNITW, LOS2, SIG><<<n_ctas, TP, smem, st>>>(a);
 	return (int)cudaGetLastError();
 }
 
-inline int launch_rmu(const TiledArgs &a, bool unit_w, bool los2, int n_ctas, size_t smem, cudaStream_t st) {
-	if (unit_w) return los2 ? launch_rmu_variant<true, true>(a, n_ctas, smem, st) : launch_rmu_variant<true, false>(a, n_ctas, smem, st);
-	return los2 ? launch_rmu_variant<false, true>(a, n_ctas, smem, st) : launch_rmu_variant<false, false>(a, n_ctas, smem, st);
+template <bool SIG>
+inline int launch_rmu_sig(const TiledArgs &a, bool unit_w, bool los2, int n_ctas, size_t smem, cudaStream_t st) {
+	if (unit_w) return los2 ? launch_rmu_variant<true, true, SIG>(a, n_ctas, smem, st) : launch_rmu_variant<true, false, SIG>(a, n_ctas, smem, st);
+	return los2 ? launch_rmu_variant<false, true, SIG>(a, n_ctas, smem, st) : launch_rmu_variant<false, false, SIG>(a, n_ctas, smem, st);
+}
+
+inline int launch_rmu(const TiledArgs &a, bool unit_w, bool los2, bool sig, int n_ctas, size_t smem, cudaStream_t st) {
+	return sig ? launch_rmu_sig<true>(a, unit_w, los2, n_ctas, smem, st) : launch_rmu_sig<false>(a, unit_w, los2, n_ctas, smem, st);
 }
 
 }  // namespace mia

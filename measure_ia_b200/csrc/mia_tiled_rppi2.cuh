@@ -26,9 +26,9 @@ namespace mia {
 #define MIA_RPPI2_RATIO 2
 #endif
 
-inline size_t tiled_rppi2_smem_bytes(bool unit_w) {
+inline size_t tiled_rppi2_smem_bytes(bool unit_w, bool sig) {
 	const size_t fixed = sizeof(Cand) * TW * STAGES * CH + 256 + 768;
-	const size_t per_slot = (size_t)TP * (8 + 8 + 4 + (unit_w ? 0 : 8));
+	const size_t per_slot = (size_t)TP * (8 + 8 + 4 + (unit_w ? 0 : 8) + (sig ? 8 : 0));
 	return fixed + per_slot * NSLOT;
 }
 
@@ -195,7 +195,7 @@ struct R2Ctx {
 #else
 #define MIA_R2_ATTR __noinline__
 #endif
-template <bool UNITW>
+template <bool UNITW, bool SIG>
 __device__ MIA_R2_ATTR void process_round2(R2Ctx *cx, int sA, int eA, int sB, int eB, int lab, int codes, unsigned mask) {
 	const int lane = threadIdx.x & 31;
 	const double L = cx->L, halfL = cx->halfL, pu = cx->pu, pv = cx->pv, pl = cx->pl, a0 = cx->a0, a1 = cx->a1;
@@ -217,7 +217,7 @@ __device__ MIA_R2_ATTR void process_round2(R2Ctx *cx, int sA, int eA, int sB, in
 	auto consume = [&]() {
 		if (pend_label != cur_label) {
 			if (cur_label >= 0)
-				binned += flush_slots<UNITW>(cx->fc, acc, cx->key, zw.dead, cx->pe, cx->pw, rw.ra, cx->rb, cur_label);
+				binned += flush_slots<UNITW, SIG>(cx->fc, acc, cx->key, zw.dead, cx->pe, cx->pw, rw.ra, cx->rb, cur_label);
 			cur_label = pend_label;
 		}
 		const int cu_ = pend_codes & 3, cv_ = (pend_codes >> 2) & 3;
@@ -233,18 +233,18 @@ __device__ MIA_R2_ATTR void process_round2(R2Ctx *cx, int sA, int eA, int sB, in
 		const double su = code_shift(cu_, L), sv = code_shift(cv_, L);
 		bool susp;
 		if (cu_ == 3 || cv_ == 3)
-			susp = pair_loop<UNITW, false, false, true>(cb, pend_n, periodic, L, halfL, pu, pv, pl, a0, a1, 0.0, 0.0, rw, hi_lane, zw, acc);
+			susp = pair_loop<UNITW, false, false, true, SIG>(cb, pend_n, periodic, L, halfL, pu, pv, pl, a0, a1, 0.0, 0.0, rw, hi_lane, zw, acc);
 		else if ((cu_ | cv_) && warp_zg)
-			susp = pair_loop<UNITW, true, true, false>(cb, pend_n, periodic, L, halfL, pu, pv, pl, a0, a1, su, sv, rw, hi_lane, zw, acc);
+			susp = pair_loop<UNITW, true, true, false, SIG>(cb, pend_n, periodic, L, halfL, pu, pv, pl, a0, a1, su, sv, rw, hi_lane, zw, acc);
 		else if (cu_ | cv_)
-			susp = pair_loop<UNITW, true, false, false>(cb, pend_n, periodic, L, halfL, pu, pv, pl, a0, a1, su, sv, rw, hi_lane, zw, acc);
+			susp = pair_loop<UNITW, true, false, false, SIG>(cb, pend_n, periodic, L, halfL, pu, pv, pl, a0, a1, su, sv, rw, hi_lane, zw, acc);
 		else if (warp_zg)
-			susp = pair_loop<UNITW, false, true, false>(cb, pend_n, periodic, L, halfL, pu, pv, pl, a0, a1, 0.0, 0.0, rw, hi_lane, zw, acc);
+			susp = pair_loop<UNITW, false, true, false, SIG>(cb, pend_n, periodic, L, halfL, pu, pv, pl, a0, a1, 0.0, 0.0, rw, hi_lane, zw, acc);
 		else
-			susp = pair_loop<UNITW, false, false, false>(cb, pend_n, periodic, L, halfL, pu, pv, pl, a0, a1, 0.0, 0.0, rw, hi_lane, zw, acc);
+			susp = pair_loop<UNITW, false, false, false, SIG>(cb, pend_n, periodic, L, halfL, pu, pv, pl, a0, a1, 0.0, 0.0, rw, hi_lane, zw, acc);
 		if (__any_sync(0xffffffffu, susp))
-			slow_pairs<UNITW>(susp, cb, pend_n, periodic, L, halfL, pu, pv, pl, a0, a1, rw, hi_lane, zw.t_lo, zw.t_hi, zw.t_split, acc,
-							  cx->nan_pairs);
+			slow_pairs<UNITW, SIG>(susp, cb, pend_n, periodic, L, halfL, pu, pv, pl, a0, a1, rw, hi_lane, zw.t_lo, zw.t_hi, zw.t_split,
+								   acc, cx->nan_pairs);
 		__syncwarp();
 	};
 
@@ -286,12 +286,13 @@ __device__ MIA_R2_ATTR void process_round2(R2Ctx *cx, int sA, int eA, int sB, in
 
 // Out-of-line copy for the rare cell-by-cell path: the consumer is inlined ONCE into the kernel (three inlined copies of
 // its five loop variants cost 0.6 stall cycles per instruction in instruction-cache misses).
-template <bool UNITW>
+template <bool UNITW, bool SIG>
 __device__ __noinline__ void process_round2_cold(R2Ctx *cx, int sA, int eA, int sB, int eB, int lab, int codes, unsigned mask) {
-	process_round2<UNITW>(cx, sA, eA, sB, eB, lab, codes, mask);
+	process_round2<UNITW, SIG>(cx, sA, eA, sB, eB, lab, codes, mask);
 }
 
-template <bool UNITW>
+// SIG: also accumulate sum (w_D w_S e+)^2 per bin (the `variance` of the reference's brute variants, measure_w_box_jk.py:196)
+template <bool UNITW, bool SIG>
 __global__ void __launch_bounds__(TP, 3) k_tiled_rppi2(const TiledArgs a) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	const DevParams &P = a.P;
@@ -313,7 +314,8 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rppi2(const TiledArgs a) {
 	R2Ctx cx;
 	cx.acc.a2 = acc_u32 + (uint32_t)tid * 16u;
 	cx.acc.aw = acc_u32 + (uint32_t)NSLOT * TP * 16u + (uint32_t)tid * 8u;
-	cx.acc.ac = acc_u32 + (uint32_t)NSLOT * TP * (UNITW ? 16u : 24u) + (uint32_t)tid * 4u;
+	cx.acc.av = acc_u32 + (uint32_t)NSLOT * TP * (UNITW ? 16u : 24u) + (uint32_t)tid * 8u;
+	cx.acc.ac = acc_u32 + (uint32_t)NSLOT * TP * ((UNITW ? 16u : 24u) + (SIG ? 8u : 0u)) + (uint32_t)tid * 4u;
 	cx.ring_u32 = smem_u32(my_ring);
 	cx.ring = my_ring;
 	cx.full = full + warp * STAGES;
@@ -336,6 +338,7 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rppi2(const TiledArgs a) {
 	for (int s = 0; s < NSLOT; s++) {
 		sts_v2(cx.acc.a2 + (uint32_t)s * TP * 16u, 0.0, 0.0);
 		if (!UNITW) sts_f64(cx.acc.aw + (uint32_t)s * TP * 8u, 0.0);
+		if (SIG) sts_f64(cx.acc.av + (uint32_t)s * TP * 8u, 0.0);
 		sts_u32(cx.acc.ac + (uint32_t)s * TP * 4u, 0u);
 	}
 	__syncthreads();  // the only CTA-wide synchronisation
@@ -347,7 +350,7 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rppi2(const TiledArgs a) {
 		if (nt > 0) {
 			const double total2 = 2.0 * (double)a.task_cum[nt - 1];
 			const int RG = a.shard_count * a.n_workers;
-			const int mine = a.shard_index * a.n_workers + (int)blockIdx.x * TW + warp;
+			const int mine = ((int)blockIdx.x * TW + warp) * a.shard_count + a.shard_index;  // slots interleaved across ranks
 			auto slot_of = [&](int t) {
 				const double mid2 = 2.0 * (double)a.task_cum[t] - (double)a.task_cost[t];
 				int s = (int)(mid2 / total2 * (double)RG);
@@ -372,6 +375,7 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rppi2(const TiledArgs a) {
 	cx.fc.pddw = a.A.ddw + part;
 	cx.fc.psp = a.A.sp + part;
 	cx.fc.psc = a.A.sc + part;
+	cx.fc.pvar = SIG ? a.A.var + (size_t)(blockIdx.x * TW + warp) * nb : nullptr;
 	cx.fc.flags = a.flags;
 	cx.fc.n_2 = P.n_2;
 	cx.fc.nb = nb;
@@ -571,7 +575,7 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rppi2(const TiledArgs a) {
 							if (r_eA > r_sA || r_eB > r_sB) r_lab = a.colreg[row * n_vr + g_r];
 						}
 						const unsigned m_simple = __ballot_sync(0xffffffffu, r_lab >= 0);
-						if (m_simple) process_round2<UNITW>(&cx, r_sA, r_eA, r_sB, r_eB, r_lab, r_codes, m_simple);
+						if (m_simple) process_round2<UNITW, SIG>(&cx, r_sA, r_eA, r_sB, r_eB, r_lab, r_codes, m_simple);
 						// ---- (row, region) pairs holding several labels: cell by cell (unaligned grids only) -------------------
 						unsigned m_cplx = __ballot_sync(0xffffffffu, r_lab == -1);
 						while (m_cplx) {
@@ -595,7 +599,7 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rppi2(const TiledArgs a) {
 										c_lab = (c_nlab == 1) ? cinf->label : -2;
 									}
 									const unsigned m1 = __ballot_sync(0xffffffffu, c_nlab == 1);
-									if (m1) process_round2_cold<UNITW>(&cx, c_s, c_e, 0, 0, c_lab, pc, m1);
+									if (m1) process_round2_cold<UNITW, SIG>(&cx, c_s, c_e, 0, 0, c_lab, pc, m1);
 									unsigned mm = __ballot_sync(0xffffffffu, c_nlab > 1);
 									while (mm) {
 										const int f = __ffs(mm) - 1;
@@ -606,7 +610,7 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rppi2(const TiledArgs a) {
 											const int lb = a.cand_jk[pos];
 											int qq = pos + 1;
 											while (qq < end && a.cand_jk[qq] == lb) qq++;
-											process_round2_cold<UNITW>(&cx, pos, qq, 0, 0, lb, pc, 1u);
+											process_round2_cold<UNITW, SIG>(&cx, pos, qq, 0, 0, lb, pc, 1u);
 											pos = qq;
 										}
 									}
@@ -617,7 +621,7 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rppi2(const TiledArgs a) {
 				}
 				// ---- end of the window: flush what is left in the private slots ------------------------------------------------
 				if (cx.cur_label >= 0) {
-					cx.binned += flush_slots<UNITW>(cx.fc, cx.acc, cx.key, zw.dead, cx.pe, p.w, ra, rb, cx.cur_label);
+					cx.binned += flush_slots<UNITW, SIG>(cx.fc, cx.acc, cx.key, zw.dead, cx.pe, p.w, ra, rb, cx.cur_label);
 					cx.cur_label = -1;
 				}
 			}
@@ -659,15 +663,16 @@ inline int rppi2_fill_tasks(const TiledArgs &a, const int64_t *prim_cell_start, 
 	return (int)cudaGetLastError();
 }
 
-inline int launch_rppi2(const TiledArgs &a, bool unit_w, int n_ctas, size_t smem, cudaStream_t st) {
-	if (unit_w) {
-		MIA_CUDA_CHECK(cudaFuncSetAttribute(k_tiled_rppi2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		k_tiled_rppi2<true><<<n_ctas, TP, smem, st>>>(a);
-	} else {
-		MIA_CUDA_CHECK(cudaFuncSetAttribute(k_tiled_rppi2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		k_tiled_rppi2<false><<<n_ctas, TP, smem, st>>>(a);
-	}
+template <bool UNITW, bool SIG>
+inline int launch_rppi2_t(const TiledArgs &a, int n_ctas, size_t smem, cudaStream_t st) {
+	MIA_CUDA_CHECK(cudaFuncSetAttribute(k_tiled_rppi2<UNITW, SIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	k_tiled_rppi2<UNITW, SIG><<<n_ctas, TP, smem, st>>>(a);
 	return (int)cudaGetLastError();
+}
+
+inline int launch_rppi2(const TiledArgs &a, bool unit_w, bool sig, int n_ctas, size_t smem, cudaStream_t st) {
+	if (sig) return unit_w ? launch_rppi2_t<true, true>(a, n_ctas, smem, st) : launch_rppi2_t<false, true>(a, n_ctas, smem, st);
+	return unit_w ? launch_rppi2_t<true, false>(a, n_ctas, smem, st) : launch_rppi2_t<false, false>(a, n_ctas, smem, st);
 }
 
 }  // namespace mia

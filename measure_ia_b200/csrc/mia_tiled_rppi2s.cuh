@@ -668,7 +668,7 @@ __global__ void __launch_bounds__(TP, MIA_S_MIN_CTAS) k_tiled_rppi2s(const Tiled
 		if (nt > 0) {
 			const double total2 = 2.0 * (double)a.task_cum[nt - 1];
 			const int RG = a.shard_count * a.n_workers;
-			const int mine = a.shard_index * a.n_workers + (int)blockIdx.x * TW + warp;
+			const int mine = ((int)blockIdx.x * TW + warp) * a.shard_count + a.shard_index;  // slots interleaved across ranks
 			auto slot_of = [&](int t) {
 				const double mid2 = 2.0 * (double)a.task_cum[t] - (double)a.task_cost[t];
 				int s = (int)(mid2 / total2 * (double)RG);

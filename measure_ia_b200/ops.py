@@ -28,6 +28,7 @@ class MiaParams(ctypes.Structure):
 		("los", ctypes.c_int32), ("periodic", ctypes.c_int32), ("num_jk", ctypes.c_int32), ("kernel", ctypes.c_int32),
 		("boxsize", ctypes.c_double), ("r_search", ctypes.c_double), ("rp2_cut", ctypes.c_double),
 		("r2_thr_host", ctypes.c_void_p), ("thr2_host", ctypes.c_void_p), ("timings_host", ctypes.c_void_p),
+		("variance", ctypes.c_int32),
 	]
 
 
@@ -39,7 +40,7 @@ class MiaSample(ctypes.Structure):
 class MiaHist(ctypes.Structure):
 	_fields_ = [("dd_count", ctypes.c_void_p), ("dd_w", ctypes.c_void_p), ("spd", ctypes.c_void_p),
 				("scd", ctypes.c_void_p), ("dd_jk_count", ctypes.c_void_p), ("dd_jk_w", ctypes.c_void_p),
-				("spd_jk", ctypes.c_void_p), ("stats", ctypes.c_void_p)]
+				("spd_jk", ctypes.c_void_p), ("stats", ctypes.c_void_p), ("var", ctypes.c_void_p)]
 
 
 class MiaShard(ctypes.Structure):
@@ -90,12 +91,14 @@ LAST_TIMINGS_MS = [0.0, 0.0, 0.0, 0.0]  # [cell-list build, pair kernel, reducti
 _timing_buf = (ctypes.c_float * 4)()
 
 
-def make_params(geometry, n_r, n_2, los, periodic, num_jk, kernel, boxsize, r_search, rp2_cut, r2_thr, thr2, timings=None):
+def make_params(geometry, n_r, n_2, los, periodic, num_jk, kernel, boxsize, r_search, rp2_cut, r2_thr, thr2, timings=None,
+				variance=False):
 	"""r2_thr / thr2: CPU float64 tensors (kept alive by the caller for the duration of the call)."""
 	assert r2_thr.dtype == torch.float64 and thr2.dtype == torch.float64 and not r2_thr.is_cuda and not thr2.is_cuda
 	assert r2_thr.numel() == n_r + 1 and thr2.numel() == n_2 + 1
 	return MiaParams(MIA_ABI_VERSION, geometry, n_r, n_2, los, 1 if periodic else 0, num_jk, kernel, boxsize, r_search,
-					 rp2_cut, r2_thr.data_ptr(), thr2.data_ptr(), ctypes.addressof(timings) if timings is not None else None)
+					 rp2_cut, r2_thr.data_ptr(), thr2.data_ptr(), ctypes.addressof(timings) if timings is not None else None,
+					 1 if variance else 0)
 
 
 def _dev_ptr(t: Optional[torch.Tensor], dtype, shape_tail=None):
@@ -121,17 +124,18 @@ def paircount(pos_d: torch.Tensor, weight_d: Optional[torch.Tensor], jk_d: Optio
 			  pos_s: torch.Tensor, weight_s: Optional[torch.Tensor], jk_s: Optional[torch.Tensor],
 			  axis: torch.Tensor, e: torch.Tensor, r2_thr: torch.Tensor, thr2: torch.Tensor, geometry: int, los: int,
 			  periodic: bool, num_jk: int, boxsize: float, r_search: float, rp2_cut: float, kernel: int,
-			  shard_index: int, shard_count: int) -> List[torch.Tensor]:
+			  shard_index: int, shard_count: int, variance: bool = False) -> List[torch.Tensor]:
 	"""Binned pair sums of the position sample ``*_d`` around the shape sample ``*_s``.
 
-	Returns [dd_count i64 (n_r,n_2), dd_w, spd, scd, dd_jk_count i64 (num_jk,n_r,n_2), dd_jk_w, spd_jk, stats u64->i64 (8)].
+	Returns [dd_count i64 (n_r,n_2), dd_w, spd, scd, dd_jk_count i64 (num_jk,n_r,n_2), dd_jk_w, spd_jk, stats u64->i64 (8),
+	var (n_r,n_2) = sum (w_D w_S e+)^2 when ``variance`` else an empty tensor].
 	Semantics: include/mia_b200.h; reference seam: measure_w_box_jk.py:646 / measure_m_box_jk.py:682.
 	"""
 	lib = load_library()
 	dev = pos_d.device
 	n_r, n_2 = r2_thr.numel() - 1, thr2.numel() - 1
 	params = make_params(geometry, n_r, n_2, los, periodic, num_jk, kernel, boxsize, r_search, rp2_cut, r2_thr, thr2,
-						 _timing_buf)
+						 _timing_buf, variance)
 	f64, i32, i64 = torch.float64, torch.int32, torch.int64
 	# shapes are validated here, at the operator boundary: the library indexes pos as [n][3] and axis as [n][2]
 	D = MiaSample(pos_d.shape[0], _dev_ptr(pos_d, f64, (3,)), _dev_ptr(weight_d, f64, ()), _dev_ptr(jk_d, i32, ()), None, None)
@@ -146,28 +150,29 @@ def paircount(pos_d: torch.Tensor, weight_d: Optional[torch.Tensor], jk_d: Optio
 		jk_count = torch.empty((num_jk, n_r, n_2), dtype=i64, device=dev)
 		jk_w, spd_jk = (torch.empty((num_jk, n_r, n_2), dtype=f64, device=dev) for _ in range(2))
 		stats = torch.zeros(8, dtype=i64, device=dev)
+		var = torch.empty((n_r, n_2) if variance else (0,), dtype=f64, device=dev)
 		ws_bytes = lib.mia_workspace_bytes(ctypes.byref(params), D.n, S.n)
 		if ws_bytes == 0:
 			raise RuntimeError("libmia_b200: mia_workspace_bytes rejected the parameters")
 		ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
 		H = MiaHist(dd_count.data_ptr(), dd_w.data_ptr(), spd.data_ptr(), scd.data_ptr(),
 					jk_count.data_ptr() if num_jk else None, jk_w.data_ptr() if num_jk else None,
-					spd_jk.data_ptr() if num_jk else None, stats.data_ptr())
+					spd_jk.data_ptr() if num_jk else None, stats.data_ptr(), var.data_ptr() if variance else None)
 		stream = torch.cuda.current_stream(dev).cuda_stream
 		rc = lib.mia_paircount(ctypes.byref(params), ctypes.byref(D), ctypes.byref(S), MiaShard(shard_index, shard_count),
 							   ctypes.byref(H), ws.data_ptr(), ws_bytes, stream)
 	check(rc)
 	LAST_TIMINGS_MS[:] = list(_timing_buf)
-	return [dd_count, dd_w, spd, scd, jk_count, jk_w, spd_jk, stats]
+	return [dd_count, dd_w, spd, scd, jk_count, jk_w, spd_jk, stats, var]
 
 
 @paircount.register_fake
 def _(pos_d, weight_d, jk_d, pos_s, weight_s, jk_s, axis, e, r2_thr, thr2, geometry, los, periodic, num_jk, boxsize,
-	  r_search, rp2_cut, kernel, shard_index, shard_count):
+	  r_search, rp2_cut, kernel, shard_index, shard_count, variance=False):
 	n_r, n_2 = r2_thr.numel() - 1, thr2.numel() - 1
 	f = lambda *s, dt=torch.float64: torch.empty(s, dtype=dt, device=pos_d.device)  # noqa: E731
 	return [f(n_r, n_2, dt=torch.int64), f(n_r, n_2), f(n_r, n_2), f(n_r, n_2), f(num_jk, n_r, n_2, dt=torch.int64),
-			f(num_jk, n_r, n_2), f(num_jk, n_r, n_2), f(8, dt=torch.int64)]
+			f(num_jk, n_r, n_2), f(num_jk, n_r, n_2), f(8, dt=torch.int64), f(n_r, n_2) if variance else f(0)]
 
 
 def paircount_host(params: MiaParams, D: MiaSample, S: MiaSample, H: MiaHist, shard=(0, 1), device=0):

@@ -59,12 +59,11 @@ def test_cfg5_cross_weights_masks_three_projections(tmp_path, oracle):
 			run(name, "both", num_jk=NUM_JK, temp_file_path=False, masks=dict(masks))
 			assert box.last_stats["kernel"] == 2, "cross-correlations take the ordered tiled kernels"
 			want = oracle.measure(data, kind, dataset_name=name, num_jk=NUM_JK, boxsize=L, num_bins_r=10, num_bins_pi=8,
-								  masks=dict(masks), n_threads=oracle.max_threads())
+								  masks=dict(masks), n_threads=oracle.max_threads(), variant="brute")
 			count = want.pop("__meta__/count")
 			want.pop("__meta__/n_tested")
 			assert np.array_equal(box.last_result["count"], count), f"{name}/{kind}: pair counts differ"
-			pu.assert_datasets_match(_read_all(out), {k: v for k, v in want.items() if not k.endswith("_sigmasq")},
-									 exact_counts=False, label=f"cfg5 {name}/{kind}: ")
+			pu.assert_datasets_match(_read_all(out), want, exact_counts=False, label=f"cfg5 {name}/{kind}: ")
 			for k, v in want.items():  # the oracle's realisations, for the combination step below
 				if f"_jk{NUM_JK}/" in k or k.endswith(f"{name}_jackknife_cov_{NUM_JK}"):
 					if k not in written:

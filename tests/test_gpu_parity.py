@@ -45,7 +45,9 @@ def run_box(meta, data, masks, kw, out, kernel):
 	from measure_ia_b200 import MeasureIABox
 	kw = dict(kw)
 	kind = kw.pop("kind")
-	kw.pop("variant", None)
+	# the reference's brute variants (temp_file_path=False) also accumulate the `_sigmasq` variance; a temporary path selects
+	# the tree variants, which store zeros there (measure_IA.py:102-131)
+	temp = False if kw.pop("variant", None) == "brute" else os.path.dirname(out) + "/"
 	num_jk = kw.pop("num_jk", 0)
 	ellipticity = kw.pop("ellipticity", "distortion")
 	box = MeasureIABox(data, out, None, None, list(kw.pop("separation_limits", (0.1, 20.0))), kw.pop("num_bins_r", 8),
@@ -54,7 +56,7 @@ def run_box(meta, data, masks, kw, out, kernel):
 	assert not kw, kw
 	box.kernel = kernel
 	run = box.measure_xi_w if kind == "w" else box.measure_xi_multipoles
-	run("All", "both", num_jk=num_jk, temp_file_path=False, masks=masks, ellipticity=ellipticity)
+	run("All", "both", num_jk=num_jk, temp_file_path=temp, masks=masks, ellipticity=ellipticity)
 	return box
 
 
@@ -64,8 +66,6 @@ def test_reference_fixture(torch_cuda, tmp_path, name, kernel):
 	"""Whole API path on the GPU vs the files the unmodified reference wrote for the same inputs."""
 	meta, want = pu.load_fixture(name)
 	data, masks, kw = pu.rebuild_inputs(meta)
-	if kw.get("variant") == "brute":
-		want = {k: v for k, v in want.items() if not k.endswith("_sigmasq")}
 	out = str(tmp_path / "out.hdf5")
 	box = run_box(meta, data, masks, kw, out, kernel)
 	got = read_all(out)
@@ -73,6 +73,9 @@ def test_reference_fixture(torch_cuda, tmp_path, name, kernel):
 	if kernel != "general":
 		assert box.last_stats["kernel"] in TILED, "the tiled kernels should cover every (r_p, Pi) and (r, mu_r) fixture"
 		assert kernel == "auto" or box.last_stats["kernel"] == 2
+		if kw.get("variant") == "brute" and kw.get("num_jk", 0) > 0:
+			assert box.last_stats["kernel"] == 2, "variance calls use the ordered kernels"
+			assert any(k.endswith("_sigmasq") and np.any(v != 0) for k, v in want.items())
 	if "nan_rule" in name:
 		# the reference's NaN rule (measure_w_box_jk.py:411-417, measure_m_box_jk.py:431-438) must actually fire, in both
 		# kernels, on exactly the pairs the oracle zeroes
@@ -104,10 +107,11 @@ def test_against_oracle_100k(torch_cuda, oracle, tmp_path, geom, kind, kernel):
 	box.kernel = kernel
 	(box.measure_xi_w if kind == "w" else box.measure_xi_multipoles)("All", "both", num_jk=27, temp_file_path=False)
 	want = oracle.measure(data, kind, num_jk=27, boxsize=205.0, num_bins_r=10, num_bins_pi=8,
-						  n_threads=oracle.max_threads())
+						  n_threads=oracle.max_threads(), variant="brute")  # temp_file_path=False: `_sigmasq` is accumulated
 	count = want.pop("__meta__/count")
 	want.pop("__meta__/n_tested")
 	assert np.array_equal(box.last_result["count"], count)
+	assert np.any(want[("w" if kind == "w" else "multipoles") + "/xi_g_plus/All_sigmasq"] > 0)
 	pu.assert_datasets_match(read_all(out), want, exact_counts=(geom == "rppi"), label=f"{geom}[{kernel}]: ")
 	if kernel != "general":
 		assert box.last_stats["kernel"] in TILED
@@ -163,18 +167,22 @@ def test_shards_sum_to_whole(torch_cuda, oracle):
 	np.testing.assert_allclose(sum(p["spd"] for p in parts), whole["spd"], rtol=1e-10, atol=1e-9)
 
 
-def test_exact_quarter_scaling_with_half_weights(torch_cuda, tmp_path):
+@pytest.mark.parametrize("temp", [False, "tmp/"], ids=["brute_semantics", "tree_semantics"])
+def test_exact_quarter_scaling_with_half_weights(torch_cuda, tmp_path, monkeypatch, temp):
 	"""Reference tests/test_weights.py:34-35: weights 0.5 scale DD and w_g+ by EXACTLY 1/4 (needs run-to-run
 	deterministic accumulation order), covariances by 1/16."""
 	from measure_ia_b200 import MeasureIABox
 	from measure_ia_b200.synthetic import uniform_box
 	data = uniform_box(20000, 205.0, seed=31)
+	monkeypatch.setenv("MIA_RPPI_V2", "2")  # row-streaming kernels also for this sparse catalogue
 	out = str(tmp_path / "w.hdf5")
 	box = MeasureIABox(data, out, boxsize=205.0, num_bins_r=10, num_bins_pi=8)
-	box.measure_xi_w("A", "both", 8, temp_file_path=False)
+	box.measure_xi_w("A", "both", 8, temp_file_path=temp)
+	assert box.last_stats["kernel"] == (2 if temp is False else 4)  # ordered kernel with variance / symmetric kernel
 	box.data["weight"] = np.array([0.5] * 20000)
 	box.data["weight_shape_sample"] = np.array([0.5] * 20000)
-	box.measure_xi_w("B", "both", 8, temp_file_path=False)
+	box.measure_xi_w("B", "both", 8, temp_file_path=temp)
+	assert box.last_stats["kernel"] == (2 if temp is False else 4)
 	g = read_all(out)
 	assert np.array_equal(g["w/xi_gg/A_DD"], 4 * g["w/xi_gg/B_DD"])
 	if box.last_stats["kernel"] in TILED:  # the tiled kernels accumulate in a fixed order
@@ -269,7 +277,7 @@ def test_clustered_weighted_default_bins_vs_oracle(torch_cuda, oracle, tmp_path,
 	box = MeasureIABox(data, out, boxsize=300.0)
 	box.kernel = kernel
 	box.measure_xi_w("All", "both", num_jk=64, temp_file_path=False)
-	want = oracle.measure(data, "w", num_jk=64, boxsize=300.0, n_threads=oracle.max_threads())
+	want = oracle.measure(data, "w", num_jk=64, boxsize=300.0, n_threads=oracle.max_threads(), variant="brute")
 	count = want.pop("__meta__/count")
 	want.pop("__meta__/n_tested")
 	assert np.array_equal(box.last_result["count"], count)
@@ -278,16 +286,19 @@ def test_clustered_weighted_default_bins_vs_oracle(torch_cuda, oracle, tmp_path,
 		assert box.last_stats["kernel"] in TILED
 
 
-def test_tiled_kernel_is_bit_reproducible(torch_cuda):
+@pytest.mark.parametrize("temp", [False, "tmp/"], ids=["ordered_with_variance", "symmetric"])
+def test_tiled_kernel_is_bit_reproducible(torch_cuda, monkeypatch, temp):
 	"""Two runs of the tiled kernel give identical bits for every fp64 sum (fixed accumulation order)."""
 	from measure_ia_b200 import MeasureIABox
 	from measure_ia_b200.synthetic import uniform_box
 	data = uniform_box(60000, 205.0, seed=61, weights=True)
+	monkeypatch.setenv("MIA_RPPI_V2", "2")
 	box = MeasureIABox(data, None, boxsize=205.0, num_bins_r=10, num_bins_pi=8)
 	box.kernel = "tiled"
-	box.measure_xi_w("a", "both", 27, temp_file_path=False)
+	box.measure_xi_w("a", "both", 27, temp_file_path=temp)
+	assert box.last_stats["kernel"] == (2 if temp is False else 4)
 	first = {k: np.array(v) for k, v in box.last_result.items() if isinstance(v, np.ndarray)}
-	box.measure_xi_w("a", "both", 27, temp_file_path=False)
+	box.measure_xi_w("a", "both", 27, temp_file_path=temp)
 	for k, v in first.items():
 		assert np.array_equal(v, box.last_result[k]), k
 
@@ -324,7 +335,9 @@ def _run_cross(kind, case, kernel):
 	box = MeasureIABox(data, None, boxsize=L, separation_limits=limits, num_bins_r=n_r, num_bins_pi=n_2, periodicity=per,
 					   pi_max=pi_max)
 	box.kernel = kernel
-	(box.measure_xi_w if kind == "w" else box.measure_xi_multipoles)("a", "both", jk, temp_file_path=False)
+	# a temporary path = the reference's tree variants (no `_sigmasq` accumulation): auto-correlations may then take the
+	# symmetric kernel; temp_file_path=False (brute variants, variance accumulated) is covered by the fixture / oracle tests
+	(box.measure_xi_w if kind == "w" else box.measure_xi_multipoles)("a", "both", jk, temp_file_path="tmp/")
 	return box.last_result, box.last_stats
 
 

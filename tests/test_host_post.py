@@ -16,7 +16,7 @@ from measure_ia_b200.box import integer_cube_root
 
 def oracle_pair_sums(oracle):
 	"""A stand-in for MeasureIABox._pair_sums that gets the five accumulators from the CPU oracle."""
-	def _pair_sums(self, geom, masks, L_subboxes, ellipticity, rp_cut=None):
+	def _pair_sums(self, geom, masks, L_subboxes, ellipticity, rp_cut=None, variance=False):
 		pos, pos_s, axis, e, w, w_s, same = self._prepare(masks, ellipticity)
 		num_box = L_subboxes ** 3 if L_subboxes else 0
 		jk_p = jk_s = None
@@ -29,7 +29,8 @@ def oracle_pair_sums(oracle):
 							 self.boxsize, self.periodicity, int(self.data["LOS"]), 1.0, num_box=num_box, n_threads=4)
 		self.last_stats = dict(rank=0)
 		return dict(count=r["count"], DD=r["DD"], SpD_raw=r["SpD"], ScD_raw=r["ScD"], count_jk=None, DD_jk=r["DD_jk"],
-					SpD_jk=r["SpD_jk"], R=R, R_jk=R_jk, jk_p=jk_p, jk_s=jk_s, Np=len(pos), Ns=len(pos_s))
+					SpD_jk=r["SpD_jk"], var_raw=r["var"] if variance else None, R=R, R_jk=R_jk, jk_p=jk_p, jk_s=jk_s,
+					Np=len(pos), Ns=len(pos_s))
 	return _pair_sums
 
 
@@ -54,8 +55,6 @@ def test_host_pipeline_reproduces_reference_files(oracle, tmp_path, monkeypatch,
 	data, masks, kw = pu.rebuild_inputs(meta)
 	kind = kw.pop("kind")
 	variant = kw.pop("variant", "tree")
-	if variant == "brute":
-		want = {k: v for k, v in want.items() if not k.endswith("_sigmasq")}
 	num_jk = kw.pop("num_jk", 0)
 	ellipticity = kw.pop("ellipticity", "distortion")
 	out = str(tmp_path / "out.hdf5")
@@ -65,7 +64,9 @@ def test_host_pipeline_reproduces_reference_files(oracle, tmp_path, monkeypatch,
 					   kw.pop("periodicity", True))
 	assert not kw, kw
 	run = box.measure_xi_w if kind == "w" else box.measure_xi_multipoles
-	run("All", "both", num_jk=num_jk, temp_file_path=False, masks=masks, ellipticity=ellipticity)
+	# brute variants: temp_file_path=False, `_sigmasq` = sum (w_D w_S e+ / 2R)^2 / RR^2; tree variants: zeros
+	run("All", "both", num_jk=num_jk, temp_file_path=False if variant == "brute" else str(tmp_path) + "/", masks=masks,
+		ellipticity=ellipticity)
 	got = read_all(out)
 	assert set(got) == set(want) | {k for k in got if k.endswith("_sigmasq")} or set(want) <= set(got)
 	pu.assert_datasets_match(got, want, exact_counts="weight" not in meta["catalogue"] and not meta["catalogue"].get("weights"),
