@@ -575,6 +575,16 @@ __device__ __forceinline__ double warp_sum(double x) {
 	return x;
 }
 
+// Worker slots are handed out dynamically: a warp takes the next unprocessed slot until none is left.  A slot's tasks (fixed by
+// the prefix sum of estimated work) are accumulated in their fixed order into the SLOT's accumulator copy, so the result does
+// not depend on which warp ran which slot; what changes is that a warp that finishes early picks up more work (no tail behind
+// the slowest warp of a CTA, no dependence on how many CTAs are resident).
+__device__ __forceinline__ int next_slot(int *counter) {
+	int s = 0;
+	if ((threadIdx.x & 31) == 0) s = atomicAdd(counter, 1);
+	return __shfl_sync(0xffffffffu, s, 0);
+}
+
 // extended bin of x on the second axis: -1 below range, n_2 at/above the upper range edge
 __device__ __forceinline__ int ebin2(double x, const double *thr2, int n_2) {
 	int c = 0;

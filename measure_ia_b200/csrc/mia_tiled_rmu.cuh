@@ -711,13 +711,14 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 	__syncthreads();  // the only CTA-wide synchronisation
 
 	// ---- this warp's share of the tasks (same rule as the (r_p, Pi) kernel) -------------------------------------------
+	for (int slot = next_slot(a.flags + 2); slot < a.n_workers; slot = next_slot(a.flags + 2)) {  // (body not re-indented)
 	int task0 = 0, task1 = 0;
 	{
 		const int nt = a.n_tasks[0];
 		if (nt > 0) {
 			const double total2 = 2.0 * (double)a.task_cum[nt - 1];
 			const int RG = a.shard_count * a.n_workers;
-			const int mine = ((int)blockIdx.x * TW + warp) * a.shard_count + a.shard_index;  // slots interleaved across ranks
+			const int mine = slot * a.shard_count + a.shard_index;  // slots interleaved across ranks
 			auto slot_of = [&](int t) {
 				const double mid2 = 2.0 * (double)a.task_cum[t] - (double)a.task_cost[t];
 				int s = (int)(mid2 / total2 * (double)RG);
@@ -737,12 +738,12 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 		}
 	}
 
-	const size_t part = (size_t)(blockIdx.x * TW + warp) * (size_t)a.A.rows * nb;
+	const size_t part = (size_t)slot * (size_t)a.A.rows * nb;  // the slot's accumulator copy
 	cx.fc.pcnt = a.A.cnt + part;
 	cx.fc.pddw = a.A.ddw + part;
 	cx.fc.psp = a.A.sp + part;
 	cx.fc.psc = a.A.sc + part;
-	cx.fc.pvar = SIG ? a.A.var + (size_t)(blockIdx.x * TW + warp) * nb : nullptr;
+	cx.fc.pvar = SIG ? a.A.var + (size_t)slot * nb : nullptr;
 	cx.fc.flags = a.flags;
 	cx.fc.n_2 = P.n_2;
 	cx.fc.nb = nb;
@@ -1017,6 +1018,8 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 			}
 		}
 	}
+
+	}  // next slot
 
 	unsigned long long tested = cx.tested, binned = cx.binned, nan_pairs = cx.nan_pairs;
 	for (int o = 16; o > 0; o >>= 1) {
