@@ -40,19 +40,32 @@ FLOP_PER_PAIR = {"w": 64.0, "multipoles": 80.0}  # algor
 
 
 def sample_clocks(stop, out):
-	"""nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md clocks line)."""
+	"""nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md clocks line).  ONE nvidia-smi
+	process in loop mode (-lms 200) is read line by line: spawning a process per sample forks this (large) interpreter every
+	200 ms, which showed up as a few ms of jitter on rank 0's short multi-GPU steps."""
 	q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
 		 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 	dev = os.environ.get("LOCAL_RANK", "0")
-	while not stop.is_set():
+	try:
+		proc = subprocess.Popen(["nvidia-smi", "-i", dev, f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+								stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+	except Exception:  # noqa: BLE001
+		return
+	try:
+		import select
+		while not stop.is_set():
+			r, _, _ = select.select([proc.stdout], [], [], 0.2)
+			if r:
+				line = proc.stdout.readline()
+				if not line:
+					break
+				out.append([x.strip() for x in line.strip().split(",")])
+	finally:
+		proc.terminate()
 		try:
-			r = subprocess.run(["nvidia-smi", "-i", dev, f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-							   capture_output=True, text=True, timeout=5)
-			if r.returncode == 0 and r.stdout.strip():
-				out.append([x.strip() for x in r.stdout.strip().splitlines()[0].split(",")])
+			proc.wait(timeout=2)
 		except Exception:  # noqa: BLE001
-			pass
-		stop.wait(0.2)
+			proc.kill()
 
 
 def summarise_clocks(samples):
@@ -72,6 +85,7 @@ class ClockSampler:
 		self.samples, self.stop = [], threading.Event()
 		self.th = threading.Thread(target=sample_clocks, args=(self.stop, self.samples), daemon=True)
 		self.th.start()
+		time.sleep(0.25)  # the sampler process is up (and its fork behind us) before the timed region starts
 		return self
 
 	def __exit__(self, *exc):
@@ -188,8 +202,9 @@ class Workload:
 		barrier()
 		ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
 		kernel_ms, build_ms, reduce_ms = [], [], []
-		wall0 = time.perf_counter()
 		with ClockSampler() as clk:
+			barrier()
+			wall0 = time.perf_counter()
 			for k in range(steps):
 				flush.zero_()  # L2 flush between timed iterations (outside the per-step events)
 				ev[k][0].record()
@@ -247,6 +262,47 @@ class Workload:
 				"dd_and_dd_jk_bit_exact": exact, "sums_within_1e-10": bool(worst <= 1.0), "worst_err_over_tol": worst, "worst_abs_err_over_largest_bin": worst_rel,
 				"nan_rule_pairs": int(out[7][2].item()), "nan_rule_pairs_general": int(ref[7][2].item()),
 				"compared": list(names)}
+
+
+def run_cfg5(dev, rank, world, barrier, kernel):
+	"""BASELINE.json configs[4] through the public API: a shape sample x density sample cross-correlation with weights and
+	boolean masks (Np = 2e6, Ns = 5e5, masks keeping 70 % / 60 %), measured along the three lines of
+	sight as the datasets LOS_x / LOS_y / LOS_z with 27 jackknife regions, then the full jackknife covariance of the three
+	projections (measure_jackknife.py:573-648).  Host numpy inputs; everything (H2D, prep, kernels, D2H, HDF5, covariance
+	combination) is inside the timed wall clock.  One warm-up pass, one timed pass."""
+	import numpy as np
+	from measure_ia_b200 import MeasureIABox
+	from measure_ia_b200.synthetic import uniform_box
+	n_p, n_s, L = 2_000_000, 500_000, 205.0
+	data = uniform_box(n_p, L, seed=505, n_shape=n_s, weights=True)
+	rng = np.random.default_rng(506)
+	masks = {"Position": rng.random(n_p) < 0.7, "Position_shape_sample": rng.random(n_s) < 0.6}
+	masks["Axis_Direction"] = masks["q"] = masks["Position_shape_sample"]
+	masks["weight"], masks["weight_shape_sample"] = masks["Position"], masks["Position_shape_sample"]
+	tmp = tempfile.mkdtemp(prefix="mia_cfg5_")
+	box = MeasureIABox(data, os.path.join(tmp, f"cfg5_{rank}.hdf5"), boxsize=L, num_bins_r=10, num_bins_pi=8)
+	box.kernel = kernel
+	names = ["LOS_x", "LOS_y", "LOS_z"]
+	wall, pairs, kernel_ms = 0.0, 0, 0.0
+	for timed in (False, True):
+		barrier()
+		t0 = time.perf_counter()
+		pairs, kernel_ms = 0, 0.0
+		for los, name in enumerate(names):
+			data["LOS"] = los
+			box.measure_xi_w(name, "both", num_jk=27, temp_file_path=tmp + "/", masks=dict(masks))
+			pairs += int(box.last_result["count"].sum())
+			kernel_ms += box.last_stats["phases_ms"]["pairs"]
+		if rank == 0:
+			for corr in ("w_g_plus", "w_gg"):
+				box.create_full_cov_matrix_projections(corr, names, num_box=27)
+		barrier()
+		wall = time.perf_counter() - t0
+	return {"value": pairs / wall, "unit": "pairs/s", "wall_s": wall, "pairs": pairs, "pair_kernel_ms_rank0": kernel_ms,
+			"config": {"n_position": n_p, "n_shape": n_s, "masks": "70 % / 60 % kept", "weights": "U(0.5, 1.5)", "boxsize": L,
+					   "num_jk": 27, "bins": [10, 8], "datasets": names,
+					   "steps": "3 x measure_xi_w(host numpy dict) + create_full_cov_matrix_projections(w_g_plus, w_gg)"},
+			"kernel": box.last_stats["kernel"]}
 
 
 def fp64_peak(torch, dev):
@@ -433,13 +489,17 @@ def main():
 					rec["clocks"] = r["clocks"]
 					rec["roofline"] = roofline(r, Ws.kind, world, peak, peak_clocks, Ws.N, name)
 					rec["roofline"].pop("note", None)
-				if not args.no_parity and name != "cfg4":
+				if not args.no_parity and (name != "cfg4" or world >= 8):  # (1e7 galaxies: the general kernel needs 8 GPUs)
 					rec["parity_check"] = Ws.parity_vs_general(r["out"])
 				sec[name] = rec
 				del Ws, r
 				torch.cuda.empty_cache()
 			except Exception as exc:  # noqa: BLE001  (a failed secondary run must not lose the headline line)
 				sec[name] = {"error": f"{type(exc).__name__}: {exc}"}
+		try:
+			sec["cfg5"] = run_cfg5(dev, rank, world, barrier, args.kernel)
+		except Exception as exc:  # noqa: BLE001
+			sec["cfg5"] = {"error": f"{type(exc).__name__}: {exc}"}
 		line["secondary"] = sec
 
 	if rank == 0:

@@ -311,6 +311,17 @@ inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g,
 	cfg.num_sms = sms;
 	cfg.n_ctas = sms * SLOTS_PER_SM;
 	cfg.n_partials = cfg.n_ctas * TW;
+	{
+		// one accumulator copy per worker slot: [2 * regions][bins] x 32 bytes.  Cap the total (default 4 GiB, MIA_ACC_CAP_MB)
+		// by using fewer slots -- many jackknife regions x many bins would otherwise ask for tens of GB; slots are handed out
+		// dynamically, so fewer slots only means fewer warps busy at the very end
+		const size_t per_copy = (size_t)2 * (p->num_jk > 0 ? p->num_jk : 1) * p->n_r * p->n_2 * 32 + (size_t)p->n_r * p->n_2 * 8;
+		const char *cap_env = getenv("MIA_ACC_CAP_MB");
+		const size_t cap = (size_t)(cap_env && *cap_env ? atoll(cap_env) : 4096) << 20;
+		size_t fit = cap / (per_copy ? per_copy : 1);
+		if (fit < 64) fit = 64;
+		if ((size_t)cfg.n_partials > fit) cfg.n_partials = (int)fit;
+	}
 	cfg.max_tasks = (int)((nS / (32 / cfg.hsplit) + (int64_t)nc * nc + 1) * MAX_SPLIT);
 	(void)nD;
 	return true;
@@ -1573,7 +1584,7 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &gc, const GridDi
 	a.A = A;
 	a.nz = cfg.nz;
 	a.n_side = cfg.n_side;
-	a.n_workers = cfg.n_ctas * TW;
+	a.n_workers = cfg.n_partials;  // worker slots = accumulator copies
 	a.shard_index = shard.index;
 	a.shard_count = shard.count;
 	a.max_tasks = cfg.max_tasks;
