@@ -327,6 +327,9 @@ int mia_paircount(const mia_params *params, const mia_sample *D, const mia_sampl
 	// same catalogue on both sides (auto-correlation): every unordered pair is visited once (mia_tiled_rppi2s.cuh)
 	const bool alias = (D->pos == S->pos && D->weight == S->weight && D->jk == S->jk && nD == nS);
 	pl.tiled.sym = (pl.kernel == MIA_KERNEL_TILED && pl.tiled.sym_ok && alias && pl.cand_bytes == (int)sizeof(CandSW)) ? 1 : 0;
+	if (pl.tiled.sym && params->geometry == MIA_GEOM_RMU &&
+		rmu_sym_chunk(D->weight == nullptr, pl.tiled.w_r * params->n_2) == 0)
+		pl.tiled.sym = 0;  // weighted records + slots would leave one CTA per SM: the ordered kernel is faster
 	if (pl.tiled.sym) pl.tiled.sym = rppi2s_cand_bytes(D->weight == nullptr);  // bytes per candidate record (48 / 64)
 	DevParams P;
 	fill_dev_params(params, pl, P);

@@ -89,6 +89,19 @@ struct ColInfo {
 	double umin, umax, vmin, vmax;
 };
 
+// Candidate of the symmetric (auto-correlation) kernels: position (+ weight) as in Cand, plus what the REVERSE pair needs: its
+// normalised axis direction (u, v order) and w * e.  48 bytes with unit weights, 64 with weights; both are multiples of 16
+// (bulk copies).  u, v, l lead the record like in Cand.
+struct __align__(16) CandSU {
+	double u, v, l, we;
+	double a0, a1;
+};
+struct __align__(16) CandSW {
+	double u, v, l, we;
+	double a0, a1;
+	double w, pad;
+};
+
 struct TiledConfig {
 	int geom;        // MIA_GEOM_*
 	int w_r;         // (r, mu_r): r bins per accumulation window
@@ -131,6 +144,7 @@ struct TiledArgs {
 	int nz, n_side, n_workers, shard_index, shard_count, max_tasks;
 	int w_r, ratio, hsplit, n_lr;  // (r, mu_r) kernel (ratio, n_lr: also the row-streaming (r_p, Pi) kernel)
 	const double *vlo, *vhi;       // row-streaming (r_p, Pi) kernel: envelopes of the v coordinates per column index cv
+	int ch_sym;                    // symmetric (r, mu_r) variant: candidates per staged chunk
 	int *flags;
 };
 
@@ -138,6 +152,9 @@ struct TiledArgs {
 inline bool rmu_supported(const mia_params *p, int &w_r);
 inline size_t tiled_rmu_smem_bytes(bool unit_w, bool sig);
 inline int launch_rmu(const TiledArgs &a, bool unit_w, bool los2, bool sig, int n_ctas, size_t smem, cudaStream_t st);
+inline int launch_rmu_sym(const TiledArgs &a, bool unit_w, bool los2, int n_ctas, size_t smem, cudaStream_t st);
+inline size_t tiled_rmu_sym_smem_bytes(bool unit_w, int ns, int ch);
+inline int rmu_sym_chunk(bool unit_w, int ns);
 inline bool plan_rmu_grid(const mia_params *p, int n_side, TiledConfig &cfg, int &nc, int &nz, int &k);
 // defined in mia_tiled_rppi2.cuh
 struct TiledWorkspace;
@@ -153,7 +170,7 @@ inline bool rppi2s_supported(int ncu, int k, int ratio);
 inline size_t tiled_rppi2s_smem_bytes(bool unit_w);
 inline int launch_rppi2s(const TiledArgs &a, bool unit_w, int n_ctas, size_t smem, cudaStream_t st);
 inline int rmu_fill_tasks(const TiledArgs &a, const int64_t *prim_cell_start, const int64_t *cell_start, const int32_t *task_off,
-						  int ncol_s, int nzs, int k, int split, int32_t *task_col, int64_t *task_first, int32_t *task_n,
+						  int ncol_s, int nzs, int k, int split, int sym, int32_t *task_col, int64_t *task_first, int32_t *task_n,
 						  int32_t *task_slab, unsigned long long *task_cost, int32_t *n_tasks, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1529,7 +1546,7 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &gc, const GridDi
 										w.task_first, w.task_n, w.task_slab, w.task_cost, w.n_tasks, st);
 		if (rc) return rc;
 	} else if (cfg.geom == MIA_GEOM_RMU) {
-		const int rc = rmu_fill_tasks(a, prim_cell_start, G.cell_start, w.task_off, (int)ncol, nzs, P.ku, split, w.task_col, w.task_first,
+		const int rc = rmu_fill_tasks(a, prim_cell_start, G.cell_start, w.task_off, (int)ncol, nzs, P.ku, split, cfg.sym, w.task_col, w.task_first,
 									  w.task_n, w.task_slab, w.task_cost, w.n_tasks, st);
 		if (rc) return rc;
 	} else {
@@ -1548,7 +1565,8 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &gc, const GridDi
 	const bool rmu = cfg.geom == MIA_GEOM_RMU;
 	const bool sig = cfg.sig != 0;
 	if (sig && !rmu && !cfg.v2) return MIA_ERR_UNSUPPORTED;  // (plan_tiled never selects the cell-by-cell kernel for such calls)
-	const size_t smem = rmu ? tiled_rmu_smem_bytes(unit_w, sig)
+	a.ch_sym = (rmu && cfg.sym) ? rmu_sym_chunk(unit_w, cfg.w_r * P.n_2) : 0;
+	const size_t smem = rmu ? (cfg.sym ? tiled_rmu_sym_smem_bytes(unit_w, cfg.w_r * P.n_2, a.ch_sym) : tiled_rmu_smem_bytes(unit_w, sig))
 							: (cfg.sym ? tiled_rppi2s_smem_bytes(unit_w)
 									   : (cfg.v2 ? tiled_rppi2_smem_bytes(unit_w, sig) : tiled_smem_bytes(unit_w)));
 	if (rmu || cfg.v2) {
@@ -1591,7 +1609,8 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &gc, const GridDi
 	a.flags = flags;
 	if (ev_before) MIA_CUDA_CHECK(cudaEventRecord(ev_before, st));
 	if (rmu) {
-		const int rc = launch_rmu(a, unit_w, P.los == 2, sig, cfg.n_ctas, smem, st);
+		const int rc = cfg.sym ? launch_rmu_sym(a, unit_w, P.los == 2, cfg.n_ctas, smem, st)
+							   : launch_rmu(a, unit_w, P.los == 2, sig, cfg.n_ctas, smem, st);
 		if (rc) return rc;
 	} else if (cfg.sym) {
 		const int rc = launch_rppi2s(a, unit_w, cfg.n_ctas, smem, st);

@@ -56,6 +56,26 @@ inline size_t tiled_rmu_smem_bytes(bool unit_w, bool sig) {
 	return fixed + per_slot * NS_RMU;
 }
 
+// Symmetric (auto-correlation) variant: 48 / 64-byte candidate records (CandSU / CandSW, mia_tiled_rppi2s.cuh), a second
+// double2 per slot for the reverse pairs, and only the `ns` slots the configuration uses.
+#ifndef MIA_CH_RMU_S
+#define MIA_CH_RMU_S 64
+#endif
+constexpr int CH_RMU_S = MIA_CH_RMU_S;  // largest chunk; smaller ones are used when many slots are needed
+constexpr size_t RMU_SYM_SMEM_MAX = 115000;  // two CTAs per SM
+inline size_t tiled_rmu_sym_smem_bytes(bool unit_w, int ns, int ch) {
+	const size_t rec = unit_w ? 48 : 64;
+	const size_t fixed = rec * TW * STAGES * (size_t)ch + sizeof(int) * TW * MAX_NEIGH_RMU + 256 + 768;
+	const size_t per_slot = (size_t)TP * (16 + 16 + 4 + (unit_w ? 0 : 8));
+	return fixed + per_slot * (size_t)ns;
+}
+// candidates per staged chunk of the symmetric variant such that two CTAs fit an SM (0: does not fit)
+inline int rmu_sym_chunk(bool unit_w, int ns) {
+	for (int ch = CH_RMU_S; ch >= 16; ch -= 8)
+		if (tiled_rmu_sym_smem_bytes(unit_w, ns, ch) <= RMU_SYM_SMEM_MAX) return ch;
+	return 0;
+}
+
 // Can the tiled (r, mu_r) kernel take this configuration?  (Declined configurations go to the general kernel.)
 inline bool rmu_supported(const mia_params *p, int &w_r) {
 	const int n = p->n_2;
@@ -129,18 +149,24 @@ inline bool plan_rmu_grid(const mia_params *p, int n_side, TiledConfig &cfg, int
 	nz = nc * lmul;
 	cfg.hsplit = hs;
 	cfg.n_lr = (n_side > 1 && nz % n_side == 0) ? n_side : 1;
+	// symmetric auto-correlation variant: the streamed columns (own u rows and k rows ahead) must be unambiguously ahead under
+	// the periodic wrap, one candidate per warp step, and two CTAs must fit an SM (only the slots in use are allocated)
+	cfg.sym_ok = (2 * (k + cfg.ratio) < nc && hs == 1 &&
+				  rmu_sym_chunk(true, cfg.w_r * p->n_2) > 0 && env_int("MIA_RMU_SYM", 1) != 0) ? 1 : 0;
+	// (with weights the records and slots are larger: decided again at call time, mia_api.cu)
 	return true;
 }
 
 // Neighbour enumeration shared by the task-cost kernel and the pair kernel.  Offsets (iu, iv) run over a
 // (2k + ratio)^2 window (or the whole grid when that wraps); returns the candidate column or -1.
 __device__ __forceinline__ int rmu_neighbour(int o, int su0, int sv0, int ratio, int ncu, int ncv, int k, int periodic,
-											 double cs, double reach) {
+											 double cs, double reach, int sym = 0) {
 	const bool all_u = 2 * k + ratio >= ncu, all_v = 2 * k + ratio >= ncv;
 	const int wu = all_u ? ncu : 2 * k + ratio, wv = all_v ? ncv : 2 * k + ratio;
 	if (o >= wu * wv) return -1;
 	const int iu = o / wv, iv = o - iu * wv;
 	const int ou = iu - k, ov = iv - k;  // offsets from the first candidate column of the shape column
+	if (sym && ou < 0) return -1;        // symmetric kernel: own u rows and the rows AHEAD only (half-space rule on d_u)
 	int nu = all_u ? iu : ratio * su0 + ou, nv = all_v ? iv : ratio * sv0 + ov;
 	if (nu < 0) {
 		if (!periodic) return -1;
@@ -172,7 +198,7 @@ __device__ __forceinline__ int rmu_n_offsets(int ratio, int ncu, int ncv, int k)
 // One warp task = up to spt consecutive shape galaxies of one shape column; cost = shapes x candidates in reach.
 __global__ void k_fill_tasks_rmu(const int64_t *__restrict__ prim_cell_start, const int64_t *__restrict__ cell_start,
 								 const int32_t *__restrict__ task_off, int ncu, int ncv, int nz, int ratio, int nzs, int spt,
-								 int split, int k, int periodic, double cs, double reach, int32_t *__restrict__ task_col,
+								 int split, int k, int periodic, int sym, double cs, double reach, int32_t *__restrict__ task_col,
 								 int64_t *__restrict__ task_first, int32_t *__restrict__ task_n,
 								 int32_t *__restrict__ task_slab, unsigned long long *__restrict__ task_cost,
 								 int32_t *__restrict__ n_tasks) {
@@ -187,7 +213,7 @@ __global__ void k_fill_tasks_rmu(const int64_t *__restrict__ prim_cell_start, co
 	const int n_off = rmu_n_offsets(ratio, ncu, ncv, k);
 	unsigned long long W = 0;
 	for (int o = 0; o < n_off; o++) {
-		const int nc_ = rmu_neighbour(o, su0, sv0, ratio, ncu, ncv, k, periodic, cs, reach);
+		const int nc_ = rmu_neighbour(o, su0, sv0, ratio, ncu, ncv, k, periodic, cs, reach, sym);
 		if (nc_ >= 0) W += (unsigned long long)(cell_start[(int64_t)(nc_ + 1) * nz] - cell_start[(int64_t)nc_ * nz]);
 	}
 	int t = task_off[c];
@@ -205,12 +231,12 @@ __global__ void k_fill_tasks_rmu(const int64_t *__restrict__ prim_cell_start, co
 }
 
 inline int rmu_fill_tasks(const TiledArgs &a, const int64_t *prim_cell_start, const int64_t *cell_start, const int32_t *task_off,
-						  int ncol_s, int nzs, int k, int split, int32_t *task_col, int64_t *task_first, int32_t *task_n,
+						  int ncol_s, int nzs, int k, int split, int sym, int32_t *task_col, int64_t *task_first, int32_t *task_n,
 						  int32_t *task_slab, unsigned long long *task_cost, int32_t *n_tasks, cudaStream_t st) {
 	const DevParams &P = a.P;
 	const double cs = P.L / P.ncu, reach = sqrt(P.r2_thr[P.n_r]) * (1.0 + 1e-6);
 	k_fill_tasks_rmu<<<(unsigned)((ncol_s + 127) / 128), 128, 0, st>>>(prim_cell_start, cell_start, task_off, P.ncu, P.ncv, P.ncl,
-																	   a.ratio, nzs, 32 / a.hsplit, split, k, P.periodic, cs, reach, task_col,
+																	   a.ratio, nzs, 32 / a.hsplit, split, k, P.periodic, sym, cs, reach, task_col,
 																	   task_first, task_n, task_slab, task_cost, n_tasks);
 	return (int)cudaGetLastError();
 }
@@ -218,14 +244,14 @@ inline int rmu_fill_tasks(const TiledArgs &a, const int64_t *prim_cell_start, co
 // Neighbour candidate columns of a shape column, ordered by jackknife (u, v) region so that candidate labels change
 // rarely.  Writes the list to nlist (per-warp shared scratch) and returns its length.
 __device__ __noinline__ int build_neighbour_list_rmu(int *nlist, int2 *scratch, int scol, int ratio, int ncu, int ncv, int k,
-													 int periodic, int n_side, double cs, double reach) {
+													 int periodic, int n_side, double cs, double reach, int sym) {
 	const int lane = threadIdx.x & 31;
 	const int ncv_s = ncv / ratio;
 	const int su0 = scol / ncv_s, sv0 = scol % ncv_s;
 	const int n_off = rmu_n_offsets(ratio, ncu, ncv, k), n_keys = n_side * n_side;
 	__syncwarp();
 	for (int o = lane; o < n_off; o += 32) {  // scratch = this warp's (idle) staging buffers
-		const int c_ = rmu_neighbour(o, su0, sv0, ratio, ncu, ncv, k, periodic, cs, reach);
+		const int c_ = rmu_neighbour(o, su0, sv0, ratio, ncu, ncv, k, periodic, cs, reach, sym);
 		int key = -1;
 		if (c_ >= 0) {
 			const int nu = c_ / ncv, nv = c_ - nu * ncv;
@@ -261,6 +287,7 @@ __device__ __forceinline__ float ord2f(unsigned o) {
 // "suspect" decisions bit for bit.
 struct RmuApprox {
 	double gp, gc;  // cos 2phi, sin 2phi
+	double inv2;    // 2 / r_p^2
 	int idx;        // mu bin, clamped to [0, n_mu - 1]
 	bool susp;      // too close to a mu edge, or |cos| ~ 1
 };
@@ -295,6 +322,7 @@ __device__ __forceinline__ RmuApprox rmu_approx(double du, double dv, double dz,
 	const double inv2 = __hiloint2double(__double2hiint(z) + 0x00100000, __double2loint(z));  // 2 / r_p^2
 	r.gp = fma(cr * cr, inv2, -1.0);
 	r.gc = (cr * fabs(sr)) * inv2;
+	r.inv2 = inv2;
 	r.susp = susp_mu || (r.gp >= 1.0 - 1e-11);
 	return r;
 }
@@ -504,6 +532,252 @@ __device__ __noinline__ unsigned flush_slots_rmu(const FlushCtx &fc, PrivAcc acc
 	return binned;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// SYMMETRIC variant (auto-correlations; see mia_tiled_rppi2s.cuh for the idea): every unordered pair is visited once, by the
+// galaxy that sees the other one ahead along u (wrapped d_u < 0); the separation, r^2, the range tests, the r bin, the
+// reciprocals and mu are shared, the reverse pair has mu -> -mu (mirrored mu bin: the SAME private slot, second double2) and
+// its own projected shape (the candidate record carries its axis and w * e).  Pairs near a mu edge or with |cos| ~ 1 in
+// either ordering, and exact ties d_u == 0, go to an exact path that adds straight into the slot's accumulator copy.
+// ------------------------------------------------------------------------------------------------------------------
+template <bool UNITW>
+struct RmuRec {
+	typedef CandSW type;
+};
+template <>
+struct RmuRec<true> {
+	typedef CandSU type;
+};
+
+struct RmuPairS {
+	RmuApprox ap;      // forward e+ / ex, mu bin, suspicion flag
+	double gpr, gcr;   // reverse e+ / ex (unweighted)
+	unsigned bad;      // some ordering needs the exact path
+};
+__device__ __forceinline__ RmuPairS rmu_pair_sym(double du, double dv, double dz, double rp2, double s, double a0, double a1,
+												 double b0, double b1, double hn, double tbias, int n_mu) {
+	RmuPairS r;
+	r.ap = rmu_approx(du, dv, dz, rp2, s, a0, a1, hn, tbias, n_mu);
+	const double crr = fma(du, b0, __dmul_rn(dv, b1));   // reverse: separation -sep, cos = -crr / r_p
+	const double srr = fma(du, b1, -__dmul_rn(dv, b0));
+	r.gpr = fma(crr * crr, r.ap.inv2, -1.0);
+	r.gcr = -((crr * fabs(srr)) * r.ap.inv2);
+	r.bad = (unsigned)r.ap.susp | (unsigned)(r.gpr >= 1.0 - 1e-11);
+	return r;
+}
+
+template <bool UNITW, bool LOS2, int VAR>
+__device__ __forceinline__ bool pair_loop_rmu_sym(uint32_t cb, int n, double L, double halfL, double pu, double pv, double pl,
+												  double a0, double a1, double su, double sv, double sl, double w_lo, double w_hi,
+												  double w_thr, double w_cut, double hn, double tbias, int n_mu, const PrivAcc &acc,
+												  uint32_t ar_off) {
+	constexpr uint32_t REC = (uint32_t)sizeof(typename RmuRec<UNITW>::type);
+	auto wrap = [&](double d) {
+		const double c = __hiloint2double(__double2hiint(L) | (__double2hiint(d) & 0x80000000), __double2loint(L));
+		return (fabs(d) > halfL) ? __dsub_rn(d, c) : d;
+	};
+	unsigned lane_susp = 0u;
+	double cu, cv, cl, we, b0, b1, cw = 1.0, pad_;
+	lds_v2(cu, cv, cb);
+	lds_v2(cl, we, cb + 16);
+	lds_v2(b0, b1, cb + 32);
+	if (!UNITW) lds_v2(cw, pad_, cb + 48);
+	uint32_t na = cb + REC;
+	MIA_UNROLL_PRAGMA(MIA_UNROLL_RMU)
+	for (int j = 0; j < n; j++) {
+		double nu, nv, nl, nwe, nb0, nb1, nw = 1.0;
+		lds_v2(nu, nv, na);
+		lds_v2(nl, nwe, na + 16);
+		lds_v2(nb0, nb1, na + 32);
+		if (!UNITW) lds_v2(nw, pad_, na + 48);
+		na += REC;
+		double du = __dsub_rn(pu, cu), dv = __dsub_rn(pv, cv), dz = __dsub_rn(pl, cl);  // shape minus position, :418
+		if (VAR == 2) {
+			du = wrap(du);
+			dv = wrap(dv);
+			dz = wrap(dz);
+		} else if (VAR == 1) {
+			du = __dadd_rn(du, su);
+			dv = __dadd_rn(dv, sv);
+			dz = __dadd_rn(dz, sl);
+		}
+		const double uu = __dmul_rn(du, du), vv = __dmul_rn(dv, dv), ll = __dmul_rn(dz, dz);
+		const double rp2 = __dadd_rn(uu, vv);
+		const double s = LOS2 ? __dadd_rn(rp2, ll) : __dadd_rn(__dadd_rn(uu, ll), vv);
+		const unsigned inr = (s >= w_lo) & (s < w_hi) & (rp2 > w_cut);
+		const RmuPairS pr = rmu_pair_sym(du, dv, dz, rp2, s, a0, a1, b0, b1, hn, tbias, n_mu);
+		const int slot = pr.ap.idx + ((s >= w_thr) ? n_mu : 0);
+		const uint32_t so = (uint32_t)slot * (uint32_t)TP;
+		double f0, f1, r0, r1, sw = 0.0;
+		lds_v2(f0, f1, acc.a2 + so * 16u);
+		lds_v2(r0, r1, acc.a2 + so * 16u + ar_off);
+		const unsigned c0 = lds_u32(acc.ac + so * 4u);
+		if (!UNITW) sw = lds_f64(acc.aw + so * 8u);
+		const int dh = __double2hiint(du);
+		const unsigned neg = (unsigned)(dh < 0);
+		const unsigned tie = (unsigned)((((unsigned)dh << 1) | (unsigned)__double2loint(du)) == 0u);
+		lane_susp |= inr & ((neg & pr.bad) | tie);
+		const bool ok = (inr & neg & (pr.bad ^ 1u)) != 0u;
+		double gp = pr.ap.gp, gc = pr.ap.gc;
+		if (!UNITW) {
+			gp *= cw;
+			gc *= cw;
+			sts_f64_if(ok, acc.aw + so * 8u, sw + cw);
+		}
+		sts_v2_if(ok, acc.a2 + so * 16u, f0 + gp, f1 + gc);
+		sts_v2_if(ok, acc.a2 + so * 16u + ar_off, fma(pr.gpr, we, r0), fma(pr.gcr, we, r1));
+		sts_u32_if(ok, acc.ac + so * 4u, c0 + 1u);
+		cu = nu;
+		cv = nv;
+		cl = nl;
+		we = nwe;
+		b0 = nb0;
+		b1 = nb1;
+		cw = nw;
+	}
+	return lane_susp != 0u;
+}
+
+// rows A[jk_shape] (+ B[jk_pos] when the position galaxy lies in another region) += one (count, sum w, sum e+, sum ex);
+// loads before stores
+__device__ __forceinline__ void add_rows_fc(const FlushCtx &fc, size_t bin, int jk_shape, int jk_pos, unsigned long long cnt, double dw,
+											double sp, double sc) {
+	const size_t ia = (size_t)jk_shape * fc.nb + bin;
+	const bool has_b = fc.num_jk > 0 && jk_pos != jk_shape;
+	const size_t ib = has_b ? (size_t)(fc.J + jk_pos) * fc.nb + bin : ia;
+	const unsigned long long c_a = fc.pcnt[ia], c_b = fc.pcnt[ib];
+	const double d_a = fc.pddw[ia], p_a = fc.psp[ia], x_a = fc.psc[ia], d_b = fc.pddw[ib], p_b = fc.psp[ib];
+	fc.pcnt[ia] = c_a + cnt;
+	fc.pddw[ia] = d_a + dw;
+	fc.psp[ia] = p_a + sp;
+	fc.psc[ia] = x_a + sc;
+	if (has_b) {
+		fc.pcnt[ib] = c_b + cnt;
+		fc.pddw[ib] = d_b + dw;
+		fc.psp[ib] = p_b + sp;
+	}
+}
+
+// Rare path of the symmetric variant: the pairs the fast loop left out, one lane at a time, both orderings evaluated exactly
+// as the reference does (mu = Pi / sqrt(r^2), cos, NaN rule: measure_m_box_jk.py:431-438), added to the slot's copy.
+template <bool UNITW, bool LOS2>
+__device__ __noinline__ void slow_pairs_rmu_sym(bool lane_susp, uint32_t cb, int n, int periodic, double L, double halfL,
+												double pu, double pv, double pl, double a0, double a1, double pe, double pw, int jkS,
+												int jkD, const RmuWindow rw, double w_hi, double hn, double tbias, int n_mu,
+												const double *thr2, const FlushCtx fc, unsigned long long &nan_pairs,
+												unsigned long long &binned) {
+	constexpr uint32_t REC = (uint32_t)sizeof(typename RmuRec<UNITW>::type);
+	const int lane = threadIdx.x & 31;
+	auto sep = [&](double s_, double c_) {  // measure_m_box_jk.py:418-421
+		double d = __dsub_rn(s_, c_);
+		if (periodic) {
+			if (d > halfL) d = __dsub_rn(d, L);
+			if (d < -halfL) d = __dadd_rn(d, L);
+		}
+		return d;
+	};
+	for (unsigned m = __ballot_sync(0xffffffffu, lane_susp); m; m &= m - 1u) {
+		if (lane == __ffs(m) - 1) {
+			for (int j = 0; j < n; j++) {
+				double cu, cv, cl, we, b0, b1, cw = 1.0, pad_;
+				const uint32_t ca = cb + (uint32_t)j * REC;
+				lds_v2(cu, cv, ca);
+				lds_v2(cl, we, ca + 16);
+				lds_v2(b0, b1, ca + 32);
+				if (!UNITW) lds_v2(cw, pad_, ca + 48);
+				const double du = sep(pu, cu), dv = sep(pv, cv), dz = sep(pl, cl);
+				const double uu = __dmul_rn(du, du), vv = __dmul_rn(dv, dv), ll = __dmul_rn(dz, dz);
+				const double rp2 = __dadd_rn(uu, vv);
+				const double s = LOS2 ? __dadd_rn(rp2, ll) : __dadd_rn(__dadd_rn(uu, ll), vv);
+				if (!((s >= rw.lo) && (s < w_hi) && (rp2 > rw.cut))) continue;
+				// this galaxy takes the pair iff the other one is ahead: (d_u, d_v, d_z) lexicographically negative
+				if (!(du < 0.0 || (du == 0.0 && (dv < 0.0 || (dv == 0.0 && dz < 0.0))))) continue;
+				const RmuPairS pr = rmu_pair_sym(du, dv, dz, rp2, s, a0, a1, b0, b1, hn, tbias, n_mu);
+				if (!(du == 0.0 || pr.bad)) continue;  // the fast loop accumulated this pair
+				const double r = __dsqrt_rn(s), rp = __dsqrt_rn(rp2);
+				const int rbin = rw.ra + ((s >= rw.thr) ? 1 : 0);
+				const double ww = pw * cw;
+				for (int dir = 0; dir < 2; dir++) {
+					const double mu = __ddiv_rn(dir ? -dz : dz, r);  // :431; the reverse pair has sep_ji = -sep_ij exactly
+					int idx = 0;
+					for (int k = 1; k < n_mu; k++) idx += (mu >= thr2[k]) ? 1 : 0;
+					const double x0 = dir ? -du : du, x1 = dir ? -dv : dv;
+					const double c = dir ? __dadd_rn(__dmul_rn(__ddiv_rn(x0, rp), b0), __dmul_rn(__ddiv_rn(x1, rp), b1))
+										 : __dadd_rn(__dmul_rn(__ddiv_rn(x0, rp), a0), __dmul_rn(__ddiv_rn(x1, rp), a1));
+					double gp = 0.0, gc = 0.0;
+					if (fabs(c) <= 1.0) shape_projection(c, gp, gc);
+					else nan_pairs++;
+					const double amp = dir ? pw * we : pe * cw;  // w_D w_S e_S
+					add_rows_fc(fc, (size_t)rbin * fc.n_2 + idx, dir ? jkD : jkS, dir ? jkS : jkD, 1ull, ww, gp * amp, gc * amp);
+					binned++;
+				}
+			}
+		}
+		__syncwarp();
+	}
+}
+
+// Flush of the symmetric variant: as flush_slots_rmu, then -- after a warp barrier, because forward and reverse bins of
+// different lanes coincide -- the reverse sums go to the mirrored mu bin of rows A[label of the chunk] / B[label of the lane].
+template <bool UNITW>
+__device__ __noinline__ unsigned flush_slots_rmu_sym(const FlushCtx &fc, PrivAcc acc, uint32_t ar_off, int jkS, bool dead, double pe,
+													 double pw, int ra, int rb, int n_mu, int ns, int jkD) {
+	const int lane = threadIdx.x & 31;
+	unsigned binned = 0;
+	unsigned todo = __ballot_sync(0xffffffffu, !dead);
+	while (todo) {
+		const int leader = __ffs(todo) - 1;
+		const int k = __shfl_sync(0xffffffffu, jkS, leader);
+		const unsigned grp = __ballot_sync(0xffffffffu, jkS == k) & todo;
+		const bool in = (grp >> lane) & 1u;
+		unsigned tot_cnt = 0;
+		double tf_p = 0.0, tf_c = 0.0, tr_p = 0.0, tr_c = 0.0, tot_dw = 0.0;
+#pragma unroll 1
+		for (int sl = 0; sl < ns; sl++) {
+			const uint32_t so = (uint32_t)sl * TP;
+			const unsigned c = in ? lds_u32(acc.ac + so * 4u) : 0u;
+			const unsigned csum = __reduce_add_sync(0xffffffffu, c);
+			if (csum == 0u) continue;
+			double v0 = 0.0, v1 = 0.0, u0 = 0.0, u1 = 0.0;
+			if (in) {
+				lds_v2(v0, v1, acc.a2 + so * 16u);
+				lds_v2(u0, u1, acc.a2 + so * 16u + ar_off);
+			}
+			const double xf = warp_sum(v0 * pe), yf = warp_sum(v1 * pe);
+			const double xr = warp_sum(u0 * pw), yr = warp_sum(u1 * pw);
+			const double zs = UNITW ? (double)csum : warp_sum(in ? lds_f64(acc.aw + so * 8u) * pw : 0.0);
+			if (lane == sl) {
+				tot_cnt = csum;
+				tf_p = xf;
+				tf_c = yf;
+				tr_p = xr;
+				tr_c = yr;
+				tot_dw = zs;
+			}
+		}
+		const int roff = lane / n_mu, b2 = lane - roff * n_mu;
+		const int rbin = ra + roff;
+		const bool mine = lane < ns && tot_cnt;
+		if (mine && rbin > rb) atomicExch(&fc.flags[1], 1);
+		const bool go = mine && rbin <= rb;
+		if (go) add_rows_fc(fc, (size_t)rbin * fc.n_2 + b2, k, jkD, tot_cnt, tot_dw, tf_p, tf_c);
+		__syncwarp();
+		if (go) {
+			add_rows_fc(fc, (size_t)rbin * fc.n_2 + (n_mu - 1 - b2), jkD, k, tot_cnt, tot_dw, tr_p, tr_c);
+			binned += 2u * tot_cnt;
+		}
+		__syncwarp();
+		todo &= ~grp;
+	}
+#pragma unroll 1
+	for (int sl = 0; sl < ns; sl++) {
+		sts_v2(acc.a2 + (uint32_t)sl * TP * 16u, 0.0, 0.0);
+		sts_v2(acc.a2 + (uint32_t)sl * TP * 16u + ar_off, 0.0, 0.0);
+		if (!UNITW) sts_f64(acc.aw + (uint32_t)sl * TP * 8u, 0.0);
+		sts_u32(acc.ac + (uint32_t)sl * TP * 4u, 0u);
+	}
+	return binned;
+}
+
 __device__ __forceinline__ double warp_min_f64(double x) {
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) x = fmin(x, __shfl_xor_sync(0xffffffffu, x, o));
@@ -524,9 +798,10 @@ struct RmuCtx {
 	// per (task, window)
 	double L, halfL, lo, hi, thr, cut, hn, tbias;
 	int n_mu, ns, ra, rb, periodic, hlog, half;
-	uint32_t a2, aw, ac, av, ring_u32, hstep;
-	const Cand *cand;
-	Cand *ring;
+	uint32_t a2, aw, ac, av, ar_off, ring_u32, hstep;
+	int ch;  // symmetric variant: candidates per staged chunk
+	const unsigned char *cand;
+	unsigned char *ring;
 	uint64_t *full;
 	const double *thr2;
 	FlushCtx fc;
@@ -543,7 +818,7 @@ __device__ __forceinline__ double code_shift(int code, double L) { return code =
 // Consume one round: lane e (bit e of mask) holds a column descriptor = up to two contiguous candidate ranges [sA, eA),
 // [sB, eB) with ONE jackknife label `lab` and warp-constant image codes.  Ranges are cut into chunks of <= CH_RMU,
 // streamed through the warp's double buffer (bulk copy of chunk k+1 in flight while chunk k is processed).
-template <bool UNITW, bool LOS2, bool SIG>
+template <bool UNITW, bool LOS2, bool SIG, bool SYM>
 __device__ __noinline__ void process_round(RmuCtx *cx, int sA, int eA, int sB, int eB, int lab, int codes, unsigned mask) {
 	const int lane = threadIdx.x & 31;
 	const double L = cx->L, halfL = cx->halfL, pu = cx->pu, pv = cx->pv, pl = cx->pl, a0 = cx->a0, a1 = cx->a1;
@@ -561,20 +836,26 @@ __device__ __noinline__ void process_round(RmuCtx *cx, int sA, int eA, int sB, i
 	acc.aw = cx->aw;
 	acc.ac = cx->ac;
 	acc.av = cx->av;
-	const uint32_t ring_u32 = cx->ring_u32, hstep = cx->hstep;
-	const Cand *cand = cx->cand;
-	Cand *ring = cx->ring;
+	constexpr uint32_t REC = SYM ? (uint32_t)sizeof(typename RmuRec<UNITW>::type) : (uint32_t)sizeof(Cand);
+	const int CHR = SYM ? cx->ch : CH_RMU;  // candidates per staged chunk
+	const uint32_t ring_u32 = cx->ring_u32, hstep = cx->hstep, ar_off = cx->ar_off;
+	const unsigned char *cand = cx->cand;
+	unsigned char *ring = cx->ring;
 	uint64_t *full = cx->full;
 	uint32_t phase0 = cx->phase0, phase1 = cx->phase1;
 	int st_issue = cx->st_issue, cur_label = cx->cur_label;
-	unsigned long long tested = 0, nan_pairs = 0;
+	unsigned long long tested = 0, nan_pairs = 0, tested_extra = 0;  // tested_extra: ordered pairs binned by the exact path
 	unsigned binned = 0;
 
 	int pend_n = 0, pend_st = 0, pend_label = -1, pend_codes = 0;
 	auto consume = [&]() {
 		if (pend_label != cur_label) {  // candidates of another jackknife region: flush the private slots
-			if (cur_label >= 0)
-				binned += flush_slots_rmu<UNITW, SIG>(cx->fc, acc, cx->jk, dead, cx->pe, cx->pw, rw.ra, cx->rb, n_mu, cx->ns, cur_label);
+			if (cur_label >= 0) {
+				if (SYM)
+					binned += flush_slots_rmu_sym<UNITW>(cx->fc, acc, ar_off, cx->jk, dead, cx->pe, cx->pw, rw.ra, cx->rb, n_mu, cx->ns, cur_label);
+				else
+					binned += flush_slots_rmu<UNITW, SIG>(cx->fc, acc, cx->jk, dead, cx->pe, cx->pw, rw.ra, cx->rb, n_mu, cx->ns, cur_label);
+			}
 			cur_label = pend_label;
 		}
 		const int cu_ = pend_codes & 3, cv_ = (pend_codes >> 2) & 3, cl_ = (pend_codes >> 4) & 3;
@@ -587,8 +868,27 @@ __device__ __noinline__ void process_round(RmuCtx *cx, int sA, int eA, int sB, i
 		}
 		const int n_mine = (pend_n - half + (1 << hlog) - 1) >> hlog;  // candidates half, half + hsplit, ... of the chunk
 		if (!dead) tested += (unsigned long long)n_mine;
-		const uint32_t cb = ring_u32 + (uint32_t)pend_st * (uint32_t)(CH_RMU * sizeof(Cand)) + (uint32_t)half * (uint32_t)sizeof(Cand);
+		const uint32_t cb = ring_u32 + (uint32_t)pend_st * (uint32_t)(CHR * REC) + (uint32_t)half * REC;
 		bool susp;
+		if (SYM) {  // (hsplit == 1: half = 0, n_mine = pend_n)
+			if (cu_ == 3 || cv_ == 3 || cl_ == 3)
+				susp = pair_loop_rmu_sym<UNITW, LOS2, 2>(cb, n_mine, L, halfL, pu, pv, pl, a0, a1, 0.0, 0.0, 0.0, rw.lo, hi_lane, rw.thr, rw.cut,
+														 hn, tbias, n_mu, acc, ar_off);
+			else if (pend_codes & 63)
+				susp = pair_loop_rmu_sym<UNITW, LOS2, 1>(cb, n_mine, L, halfL, pu, pv, pl, a0, a1, code_shift(cu_, L), code_shift(cv_, L),
+														 code_shift(cl_, L), rw.lo, hi_lane, rw.thr, rw.cut, hn, tbias, n_mu, acc, ar_off);
+			else
+				susp = pair_loop_rmu_sym<UNITW, LOS2, 0>(cb, n_mine, L, halfL, pu, pv, pl, a0, a1, 0.0, 0.0, 0.0, rw.lo, hi_lane, rw.thr, rw.cut,
+														 hn, tbias, n_mu, acc, ar_off);
+			if (__any_sync(0xffffffffu, susp)) {
+				unsigned long long b_ = 0ull;
+				slow_pairs_rmu_sym<UNITW, LOS2>(susp, cb, n_mine, cx->periodic, L, halfL, pu, pv, pl, a0, a1, cx->pe, cx->pw, cx->jk,
+												cur_label, rw, rw.hi, hn, tbias, n_mu, cx->thr2, cx->fc, nan_pairs, b_);
+				tested_extra += b_;
+			}
+			__syncwarp();
+			return;
+		}
 		if (cu_ == 3 || cv_ == 3 || cl_ == 3)
 			susp = pair_loop_rmu<UNITW, LOS2, 2, SIG>(cb, n_mine, hstep, L, halfL, pu, pv, pl, a0, a1, 0.0, 0.0, 0.0, rw.lo, hi_lane, rw.thr,
 												 rw.cut, hn, tbias, n_mu, acc);
@@ -617,12 +917,12 @@ __device__ __noinline__ void process_round(RmuCtx *cx, int sA, int eA, int sB, i
 			const int en = piece ? d_eB : d_eA;
 			const int pc = (d_codes & 15) | (((d_codes >> (4 + 2 * piece)) & 3) << 4);
 			while (s < en) {
-				const int rest = en - s, nch = (rest + CH_RMU - 1) / CH_RMU;  // equal chunks (66 -> 33 + 33, not 64 + 2)
+				const int rest = en - s, nch = (rest + CHR - 1) / CHR;  // equal chunks (66 -> 33 + 33, not 64 + 2)
 				const int n = (rest + nch - 1) / nch;
 				if (lane == 0) {
-					const uint32_t bytes = (uint32_t)n * (uint32_t)sizeof(Cand);
+					const uint32_t bytes = (uint32_t)n * REC;
 					mbar_expect_tx(&full[st_issue], bytes);
-					bulk_load(ring + (size_t)st_issue * CH_RMU, cand + s, bytes, &full[st_issue]);
+					bulk_load(ring + (size_t)st_issue * CHR * REC, cand + (size_t)s * REC, bytes, &full[st_issue]);
 				}
 				if (pend_n > 0) consume();
 				pend_n = n;
@@ -640,12 +940,12 @@ __device__ __noinline__ void process_round(RmuCtx *cx, int sA, int eA, int sB, i
 	cx->st_issue = st_issue;
 	cx->cur_label = cur_label;
 	cx->tested += tested;
-	cx->binned += binned;
+	cx->binned += binned + tested_extra;
 	cx->nan_pairs += nan_pairs;
 }
 
-template <bool UNITW, bool LOS2, bool SIG>
-__global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
+template <bool UNITW, bool LOS2, bool SIG, bool SYM>
+__global__ void __launch_bounds__(TP, SYM ? 2 : 3) k_tiled_rmu(const TiledArgs a) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	const DevParams &P = a.P;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -660,26 +960,33 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 	const int sidx = lane & (spt - 1);
 
 	// ---- shared memory carve-up ------------------------------------------------------------------------------------
-	Cand *ring = reinterpret_cast<Cand *>(smem);  // [warp][stage][CH_RMU]
-	int *nlist_all = reinterpret_cast<int *>(smem + sizeof(Cand) * TW * STAGES * CH_RMU);
+	constexpr uint32_t REC = SYM ? (uint32_t)sizeof(typename RmuRec<UNITW>::type) : (uint32_t)sizeof(Cand);
+	const int CHR = SYM ? a.ch_sym : CH_RMU;
+	const int ns_alloc = SYM ? ns : NS_RMU;  // slots carved out of shared memory
+	unsigned char *ring = smem;  // [warp][stage][CHR] candidate records
+	int *nlist_all = reinterpret_cast<int *>(smem + (size_t)REC * TW * STAGES * CHR);
 	uint64_t *full = reinterpret_cast<uint64_t *>(nlist_all + TW * MAX_NEIGH_RMU);  // [warp][stage]
 	double *thr2_s = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(full) + 256);
 	unsigned char *accbase = reinterpret_cast<unsigned char *>(thr2_s) + 768;
 	const uint32_t acc_u32 = smem_u32(accbase);
-	Cand *my_ring = ring + (size_t)warp * STAGES * CH_RMU;
+	unsigned char *my_ring = ring + (size_t)warp * STAGES * CHR * REC;
 	int *nlist = nlist_all + warp * MAX_NEIGH_RMU;
 
 	RmuCtx cx;
+	// layout: a2 [slot][thread] 16 B | (SYM) reverse double2 | (weights) aw 8 B | (SIG) av 8 B | ac 4 B
+	const uint32_t f_bytes = SYM ? 32u : 16u;
 	cx.a2 = acc_u32 + (uint32_t)tid * 16u;
-	cx.aw = acc_u32 + (uint32_t)NS_RMU * TP * 16u + (uint32_t)tid * 8u;
-	cx.av = acc_u32 + (uint32_t)NS_RMU * TP * (UNITW ? 16u : 24u) + (uint32_t)tid * 8u;
-	cx.ac = acc_u32 + (uint32_t)NS_RMU * TP * ((UNITW ? 16u : 24u) + (SIG ? 8u : 0u)) + (uint32_t)tid * 4u;
+	cx.ar_off = (uint32_t)ns_alloc * TP * 16u;
+	cx.aw = acc_u32 + (uint32_t)ns_alloc * TP * f_bytes + (uint32_t)tid * 8u;
+	cx.av = acc_u32 + (uint32_t)ns_alloc * TP * (f_bytes + (UNITW ? 0u : 8u)) + (uint32_t)tid * 8u;
+	cx.ac = acc_u32 + (uint32_t)ns_alloc * TP * (f_bytes + (UNITW ? 0u : 8u) + (SIG ? 8u : 0u)) + (uint32_t)tid * 4u;
 	cx.ring_u32 = smem_u32(my_ring);
 	cx.ring = my_ring;
 	cx.full = full + warp * STAGES;
-	cx.cand = a.cand;
+	cx.cand = reinterpret_cast<const unsigned char *>(a.cand);
 	cx.thr2 = thr2_s;
-	cx.hstep = (uint32_t)hsplit * (uint32_t)sizeof(Cand);
+	cx.hstep = (uint32_t)hsplit * REC;
+	cx.ch = CHR;
 	cx.hlog = hsplit == 4 ? 2 : (hsplit == 2 ? 1 : 0);
 	cx.half = lane / spt;
 	cx.L = L;
@@ -702,8 +1009,9 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 	}
 	for (int e = tid; e <= P.n_2; e += blockDim.x) thr2_s[e] = P.thr2[e];
 #pragma unroll 1
-	for (int s = 0; s < NS_RMU; s++) {
+	for (int s = 0; s < ns_alloc; s++) {
 		sts_v2(cx.a2 + (uint32_t)s * TP * 16u, 0.0, 0.0);
+		if (SYM) sts_v2(cx.a2 + (uint32_t)s * TP * 16u + cx.ar_off, 0.0, 0.0);
 		if (!UNITW) sts_f64(cx.aw + (uint32_t)s * TP * 8u, 0.0);
 		if (SIG) sts_f64(cx.av + (uint32_t)s * TP * 8u, 0.0);
 		sts_u32(cx.ac + (uint32_t)s * TP * 4u, 0u);
@@ -806,7 +1114,7 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 		cx.jk = p.jk;
 		cx.dead = dead ? 1 : 0;
 		int nn = build_neighbour_list_rmu(nlist, reinterpret_cast<int2 *>(my_ring), col, a.ratio, P.ncu, P.ncv, P.ku, periodic,
-										  a.n_side, cs, reach);
+										  a.n_side, cs, reach, SYM ? 1 : 0);
 		// when tasks are scarce (small catalogues, many GPUs) a task covers one of `nparts` consecutive parts of the list
 		int noff = 0;
 		{
@@ -962,7 +1270,7 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 						if (r_eA > r_sA || r_eB > r_sB) r_lab = a.colreg[(long long)r_c * n_lr + g_r];
 					}
 					const unsigned m_simple = __ballot_sync(0xffffffffu, r_lab >= 0);
-					if (m_simple) process_round<UNITW, LOS2, SIG>(&cx, r_sA, r_eA, r_sB, r_eB, r_lab, r_codes, m_simple);
+					if (m_simple) process_round<UNITW, LOS2, SIG, SYM>(&cx, r_sA, r_eA, r_sB, r_eB, r_lab, r_codes, m_simple);
 					// ---- column-regions holding several labels (cells cut by a jackknife face: unaligned grids only) ------------
 					unsigned m_cplx = __ballot_sync(0xffffffffu, r_lab == -1);
 					while (m_cplx) {
@@ -986,7 +1294,7 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 									c_lab = (c_nlab == 1) ? cinf->label : -2;
 								}
 								const unsigned m1 = __ballot_sync(0xffffffffu, c_nlab == 1);
-								if (m1) process_round<UNITW, LOS2, SIG>(&cx, c_s, c_e, 0, 0, c_lab, pc, m1);
+								if (m1) process_round<UNITW, LOS2, SIG, SYM>(&cx, c_s, c_e, 0, 0, c_lab, pc, m1);
 								unsigned mm = __ballot_sync(0xffffffffu, c_nlab > 1);
 								while (mm) {  // a cell with several labels: one label run at a time
 									const int f = __ffs(mm) - 1;
@@ -997,7 +1305,7 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 										const int lb = a.cand_jk[pos];
 										int qq = pos + 1;
 										while (qq < end && a.cand_jk[qq] == lb) qq++;
-										process_round<UNITW, LOS2, SIG>(&cx, pos, qq, 0, 0, lb, pc, 1u);  // lane 0 carries the run
+										process_round<UNITW, LOS2, SIG, SYM>(&cx, pos, qq, 0, 0, lb, pc, 1u);  // lane 0 carries the run
 										pos = qq;
 									}
 								}
@@ -1013,7 +1321,10 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 				acc.aw = cx.aw;
 				acc.ac = cx.ac;
 				acc.av = cx.av;
-				cx.binned += flush_slots_rmu<UNITW, SIG>(cx.fc, acc, p.jk, dead, cx.pe, p.w, ra, rb, n_mu, ns, cx.cur_label);
+				if (SYM)
+					cx.binned += flush_slots_rmu_sym<UNITW>(cx.fc, acc, cx.ar_off, p.jk, dead, cx.pe, p.w, ra, rb, n_mu, ns, cx.cur_label);
+				else
+					cx.binned += flush_slots_rmu<UNITW, SIG>(cx.fc, acc, p.jk, dead, cx.pe, p.w, ra, rb, n_mu, ns, cx.cur_label);
 				cx.cur_label = -1;
 			}
 		}
@@ -1034,11 +1345,19 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rmu(const TiledArgs a) {
 	}
 }
 
-template <bool UNITW, bool LOS2, bool SIG>
+template <bool UNITW, bool LOS2, bool SIG, bool SYM = false>
 inline int launch_rmu_variant(const TiledArgs &a, int n_ctas, size_t smem, cudaStream_t st) {
-	MIA_CUDA_CHECK(cudaFuncSetAttribute(k_tiled_rmu<UNITW, LOS2, SIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	k_tiled_rmu<UNITW, LOS2, SIG><<<n_ctas, TP, smem, st>>>(a);
+	MIA_CUDA_CHECK(cudaFuncSetAttribute(k_tiled_rmu<UNITW, LOS2, SIG, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	k_tiled_rmu<UNITW, LOS2, SIG, SYM><<<n_ctas, TP, smem, st>>>(a);
 	return (int)cudaGetLastError();
+}
+
+inline int launch_rmu_sym(const TiledArgs &a, bool unit_w, bool los2, int n_ctas, size_t smem, cudaStream_t st) {
+	if (unit_w)
+		return los2 ? launch_rmu_variant<true, true, false, true>(a, n_ctas, smem, st)
+					: launch_rmu_variant<true, false, false, true>(a, n_ctas, smem, st);
+	return los2 ? launch_rmu_variant<false, true, false, true>(a, n_ctas, smem, st)
+				: launch_rmu_variant<false, false, false, true>(a, n_ctas, smem, st);
 }
 
 template <bool SIG>

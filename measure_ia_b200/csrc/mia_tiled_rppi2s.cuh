@@ -42,17 +42,7 @@ namespace mia {
 constexpr int WRS = MIA_S_WR;    // r bins per accumulation window (the same for both variants: it fixes the grouping of the sums)
 constexpr int NSLOT_S = 2 * WRS; // private slots per thread: (r bin of the window) x (Pi slot of the forward pair)
 
-// Candidate of the symmetric kernel: position (+ weight) as in Cand, plus what the REVERSE pair needs: its normalised axis
-// direction (u, v order) and w * e.  48 bytes with unit weights, 64 with weights; both are multiples of 16 (bulk copies).
-struct __align__(16) CandSU {
-	double u, v, l, we;
-	double a0, a1;
-};
-struct __align__(16) CandSW {
-	double u, v, l, we;
-	double a0, a1;
-	double w, pad;
-};
+// (candidate records CandSU / CandSW: mia_tiled.cuh)
 template <bool UNITW>
 struct CandRec {
 	typedef CandSW type;
