@@ -240,28 +240,52 @@ class Workload:
 		}
 		return res
 
-	def parity_vs_general(self, out):
-		"""The timed (tiled) result against the general kernel (one thread per shape galaxy, the reference's operation
-		sequence incl. divisions, square roots and its NaN rule) on the SAME full workload: pair counts and jackknife pair
-		counts must be bit-identical, fp64 sums within 1e-10 (same tolerance as tests/test_gpu_parity.py::_assert_same_sums:
-		1e-10 relative, plus 1e-11 of the largest bin, plus eps x the largest pair count -- the rounding noise of summing
-		that many terms of magnitude <= 1 in two different orders; the general kernel adds with atomics in no fixed order)."""
+	def parity_vs_general(self, out, repeat_general=True):
+		"""The timed (tiled) result on the SAME full workload against
+		(a) the general kernel (one thread per shape galaxy, the reference's operation sequence incl. divisions, square roots
+		    and its NaN rule): pair counts and jackknife pair counts must be bit-identical; fp64 sums within 1e-10 relative
+		    + 1e-11 of the largest bin + the general kernel's OWN run-to-run noise (it adds with atomics in no fixed order:
+		    two runs of it differ by ~6e-11 of the largest S x D bin at 3e10 pairs, measured and reported here);
+		(b) when the timed kernel is the symmetric one, the ORDERED tiled kernel -- an independent pair loop that evaluates
+		    every ordered pair on its own, also with fixed-order sums: agreement to ~1e-13 of the largest bin."""
 		torch = self.torch
-		ref = self.step(kernel="general")
 		names = ("dd_count", "dd_w", "spd", "scd", "dd_jk_count", "dd_jk_w", "spd_jk")
+
+		def rel(a, b):  # largest |a - b| over the largest |a|, worst array
+			w = 0.0
+			for i in (1, 2, 3, 5, 6):
+				if a[i].numel():
+					w = max(w, float(((a[i] - b[i]).abs().max() / a[i].abs().max().clamp_min(1e-300)).item()))
+			return w
+
+		ref = self.step(kernel="general")
 		exact = bool(torch.equal(out[0], ref[0]) and torch.equal(out[4], ref[4]))
-		worst, worst_rel = 0.0, 0.0
-		floor = 1e-15 * float(ref[0].max().item())
+		noise = [0.0] * 8
+		if repeat_general:
+			ref2 = self.step(kernel="general")
+			exact = exact and bool(torch.equal(ref2[0], ref[0]))
+			noise = [float((ref[i].double() - ref2[i].double()).abs().max().item()) if ref[i].numel() else 0.0 for i in range(7)]
+			noise_rel = rel(ref, ref2)
+			del ref2
+		worst = 0.0
 		for i in (1, 2, 3, 5, 6):
 			a, b = ref[i], out[i]
 			if a.numel():
-				tol = 1e-10 * a.abs() + 1e-11 * a.abs().max() + floor
+				tol = 1e-10 * a.abs() + 1e-11 * a.abs().max() + 2.0 * noise[i]
 				worst = max(worst, float(((a - b).abs() / tol).max().item()))
-				worst_rel = max(worst_rel, float(((a - b).abs().max() / a.abs().max()).item()))
-		return {"against": "general kernel (reference-exact arithmetic, measure_w_box_jk.py:401-461) on the full workload",
-				"dd_and_dd_jk_bit_exact": exact, "sums_within_1e-10": bool(worst <= 1.0), "worst_err_over_tol": worst, "worst_abs_err_over_largest_bin": worst_rel,
-				"nan_rule_pairs": int(out[7][2].item()), "nan_rule_pairs_general": int(ref[7][2].item()),
-				"compared": list(names)}
+		res = {"against": "general kernel (reference-exact arithmetic, measure_w_box_jk.py:401-461) on the full workload",
+			   "dd_and_dd_jk_bit_exact": exact, "sums_within_1e-10": bool(worst <= 1.0), "worst_err_over_tol": worst,
+			   "timed_vs_general_rel_to_largest_bin": rel(ref, out),
+			   "general_run_to_run_rel_to_largest_bin": noise_rel if repeat_general else None,
+			   "nan_rule_pairs": int(out[7][2].item()), "nan_rule_pairs_general": int(ref[7][2].item()),
+			   "compared": list(names)}
+		del ref
+		if int(out[7][4].item()) == self.ops.KERNEL_TILED_SYM:
+			ordered = self.step(kernel="tiled_ordered")
+			res["symmetric_vs_ordered_kernel"] = {
+				"dd_and_dd_jk_bit_exact": bool(torch.equal(out[0], ordered[0]) and torch.equal(out[4], ordered[4])),
+				"sums_rel_to_largest_bin": rel(ordered, out)}
+		return res
 
 
 def run_cfg5(dev, rank, world, barrier, kernel):
@@ -490,7 +514,7 @@ def main():
 					rec["roofline"] = roofline(r, Ws.kind, world, peak, peak_clocks, Ws.N, name)
 					rec["roofline"].pop("note", None)
 				if not args.no_parity and (name != "cfg4" or world >= 8):  # (1e7 galaxies: the general kernel needs 8 GPUs)
-					rec["parity_check"] = Ws.parity_vs_general(r["out"])
+					rec["parity_check"] = Ws.parity_vs_general(r["out"], repeat_general=(name != "cfg4"))
 				sec[name] = rec
 				del Ws, r
 				torch.cuda.empty_cache()
