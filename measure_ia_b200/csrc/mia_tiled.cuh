@@ -71,6 +71,9 @@ constexpr int W_R = MIA_W_R;     // r bins per accumulation window
 constexpr int NSLOT = 2 * W_R;   // private histogram slots per thread
 constexpr int MAX_SPLIT = 8;     // a warp task may be cut into up to 8 line-of-sight parts when tasks are scarce
 constexpr int SLOTS_PER_SM = 6;  // CTAs launched per SM; fixed, so that results do not depend on occupancy
+#ifndef MIA_SLOT_MULT
+#define MIA_SLOT_MULT 0  // 0: by catalogue size
+#endif
 
 struct LutEntry {
 	double thr;  // threshold inside this entry's range of s (or +inf)
@@ -176,6 +179,11 @@ inline int rmu_fill_tasks(const TiledArgs &a, const int64_t *prim_cell_start, co
 // ------------------------------------------------------------------------------------------------------------------
 // planning (host)
 // ------------------------------------------------------------------------------------------------------------------
+inline int env_int(const char *name, int dflt) {
+	const char *v = getenv(name);
+	return (v && *v) ? atoi(v) : dflt;
+}
+
 inline int hi_word(double x) {
 	long long b;
 	memcpy(&b, &x, 8);
@@ -285,13 +293,19 @@ inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g,
 		const char *ev = getenv("MIA_RPPI_V2");
 		int v2 = ev ? atoi(ev) : MIA_RPPI_V2;
 		int div2 = 0;
+		bool thin_auto = false;
 		if (cfg.sig && v2 == 0) v2 = 1;
 		const bool must_rows = cfg.sig;  // only the row-streaming kernel has the variance variant
 		if (v2 == 1) {
 			const double rho = (double)nD / (L * L * L);
 			auto piece = [&](int d) { return rho * (reach / d) * (1.6 * reach) * (L / nz); };  // candidates per streamed range
-			if (nz > 16) v2 = 0;
-			else if (piece(10) >= 100.0) div2 = 10;
+			// thin slabs (more than 16): the ordered rows kernel loses to the cell-by-cell kernel (196 vs 171 ms, cfg2 with 8 x 20
+			// bins), the SYMMETRIC rows kernel wins (153 ms) -- so rows are planned when the two samples have the same size (an
+			// auto-correlation, as far as the plan can know: the workspace layout must not depend on pointer identity) and the
+			// grid admits the half-space rule (checked below)
+			thin_auto = nz > 16 && nz <= 32 && nD == nS && env_int("MIA_SYM", 1) != 0 && p->kernel != MIA_KERNEL_TILED_ORDERED;
+			if (nz > 16 && !thin_auto) v2 = 0;
+			else if (piece(10) >= (thin_auto ? 40.0 : 100.0)) div2 = 10;
 			else if (piece(6) >= 15.0) div2 = 6;
 			else v2 = 0;
 			if (v2 == 0 && must_rows) {
@@ -300,10 +314,20 @@ inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g,
 			}
 		}
 		if (v2) {  // row-streaming kernel: finer columns, coarser shape columns
+			const int nc_cells = nc;
 			cfg.w_r = div2;  // (r_p, Pi): carries the chosen cells per r_max to plan_rppi2_grid (0 = default)
 			if (!plan_rppi2_grid(p, n_side, cfg, nc, nz, k)) return false;
 			cfg.sym_ok = rppi2s_supported(nc, k, cfg.ratio) ? 1 : 0;
-		} else {
+			if (thin_auto && !cfg.sym_ok && !must_rows) {  // no symmetric kernel after all: back to the cell-by-cell plan
+				v2 = 0;
+				cfg.v2 = 0;
+				cfg.ratio = 1;
+				cfg.n_lr = 1;
+				cfg.w_r = 0;
+				nc = nc_cells;
+			}
+		}
+		if (!v2) {
 			const double cs = L / nc;
 			k = (int)ceil(reach / cs);
 			if (k < 1) k = 1;
@@ -327,7 +351,15 @@ inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g,
 	}
 	cfg.num_sms = sms;
 	cfg.n_ctas = sms * SLOTS_PER_SM;
-	cfg.n_partials = cfg.n_ctas * TW;
+	// worker slots (= accumulator copies) per SM: more slots = a shorter tail behind the last slot, more copies to zero and
+	// reduce.  The cell-by-cell kernel assigns slots statically to its launched warps; the others hand them out dynamically.
+	// Measured (profiles/r02_tuning.md, cfg2): 1x / 2x / 4x slots = 110.6 / 109.2 / 103.3 ms; small catalogues keep 1x (zeroing and
+	// reducing 2 GB of copies costs 0.5 ms).
+	{
+		const int auto_mult = nS >= 500000 ? 4 : (nS >= 200000 ? 2 : 1);
+		const int mult = env_int("MIA_SLOT_MULT", MIA_SLOT_MULT > 0 ? MIA_SLOT_MULT : auto_mult);
+		cfg.n_partials = cfg.n_ctas * TW * ((cfg.v2 || p->geometry == MIA_GEOM_RMU) ? (mult < 1 ? 1 : mult) : 1);
+	}
 	{
 		// one accumulator copy per worker slot: [2 * regions][bins] x 32 bytes.  Cap the total (default 4 GiB, MIA_ACC_CAP_MB)
 		// by using fewer slots -- many jackknife regions x many bins would otherwise ask for tens of GB; slots are handed out
@@ -340,7 +372,6 @@ inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g,
 		if ((size_t)cfg.n_partials > fit) cfg.n_partials = (int)fit;
 	}
 	cfg.max_tasks = (int)((nS / (32 / cfg.hsplit) + (int64_t)nc * nc + 1) * MAX_SPLIT);
-	(void)nD;
 	return true;
 }
 

@@ -94,10 +94,6 @@ inline bool rmu_supported(const mia_params *p, int &w_r) {
 	return true;
 }
 
-inline int env_int(const char *name, int dflt) {
-	const char *v = getenv(name);
-	return (v && *v) ? atoi(v) : dflt;
-}
 
 // Grid of the (r, mu_r) kernel: cubic candidate cells of about r_max / DIV, aligned with the jackknife sub-boxes (a cell
 // then carries one label) and with the coarser shape columns.
