@@ -221,7 +221,7 @@ __global__ void k_fill_tasks_rmu(const int64_t *__restrict__ prim_cell_start, co
 			task_n[t] = n;
 			task_slab[2 * t] = part;
 			task_slab[2 * t + 1] = split;
-			task_cost[t] = (unsigned long long)n * W / (unsigned long long)split + 1ull;
+			task_cost[t] = (unsigned long long)(spt / 2 + n / 2) * W / (unsigned long long)split + 1ull;  // (see k_fill_tasks_rppi2)
 		}
 	}
 }

@@ -157,7 +157,9 @@ __global__ void k_fill_tasks_rppi2(const int64_t *__restrict__ prim_cell_start, 
 			task_n[t] = n;
 			task_slab[2 * t] = (int)((long long)nz * part / split);
 			task_slab[2 * t + 1] = (int)((long long)nz * (part + 1) / split);
-			task_cost[t] = (unsigned long long)n * W / (unsigned long long)split + 1ull;
+			// the loop is branch-free over the 32 lanes: a task with few shapes costs almost what a full one does (only its
+			// streamed ranges shrink a little), so the cost is mostly the candidates in reach, not shapes x candidates
+			task_cost[t] = (unsigned long long)(16 + n / 2) * W / (unsigned long long)split + 1ull;
 		}
 	}
 }
