@@ -672,8 +672,15 @@ def combine_across_ranks(dd_count, dd_w, spd, scd, jk_count, jk_w, spd_jk, stats
 	flat = torch.empty(world * packed.numel(), dtype=torch.int64, device=packed.device)
 	dist.all_gather_into_tensor(flat, packed)
 	gathered = flat.view(world, packed.numel())
-	ints = gathered[:, :ints.numel()].sum(dim=0)
 	n0, n1 = dd_count.numel(), jk_count.numel()
+	# every rank must have built the SAME task table and slot map (same kernel, cells, warp tasks): ranks with different SM
+	# counts or MIA_* tuning variables would silently drop or double-count tasks
+	per_rank_stats = gathered[:, n0 + n1:n0 + n1 + stats.numel()]
+	if not bool((per_rank_stats[:, 4:7] == per_rank_stats[0:1, 4:7]).all()):
+		raise RuntimeError("measure_ia_b200: ranks disagree on the kernel / cell grid / task table "
+						   f"(per-rank [kernel, cells, tasks]: {per_rank_stats[:, 4:7].tolist()}); all ranks need the same GPU "
+						   "model and the same MIA_* environment")
+	ints = gathered[:, :ints.numel()].sum(dim=0)
 	dd_count = ints[:n0].view_as(dd_count)
 	jk_count = ints[n0:n0 + n1].view_as(jk_count)
 	stats_sum = ints[n0 + n1:].view_as(stats)
@@ -689,7 +696,6 @@ def combine_across_ranks(dd_count, dd_w, spd, scd, jk_count, jk_w, spd_jk, stats
 		outs.append(total[o:o + t.numel()].view_as(t))
 		o += t.numel()
 	stats_out = stats_sum.clone()
-	stats_out[4] = stats[4]  # kernel id is not additive
-	stats_out[5] = stats[5]
+	stats_out[4:7] = stats[4:7]  # kernel id, cells and the size of the (global) task table are not additive
 	res = (dd_count, outs[0], outs[1], outs[2], jk_count, outs[3], outs[4], stats_out)
 	return res + (outs[5],) if var is not None else res

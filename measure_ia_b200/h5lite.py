@@ -15,7 +15,8 @@ the two golden files under the reference's ``tests/data/processed/TNG300`` conta
 * object-header continuation blocks are followed when reading
 
 Chunked / compressed datasets, attributes, links other than hard links and big-endian types are not supported and
-raise ``NotImplementedError`` when encountered.
+raise ``NotImplementedError`` when encountered.  Attributes are skipped on reading; a file that holds any can be read but
+not rewritten (every flush re-serialises the whole file, which would drop them): ``flush`` raises instead.
 
 The file is parsed fully on open and re-serialised on ``close()`` when it was modified (the reference's files are a
 few hundred small float64 arrays, well under a few MB), which gives h5py's ``'a'`` semantics: existing content is
@@ -78,10 +79,12 @@ class Dataset:
 		return np.array(out) if isinstance(out, np.ndarray) else out
 
 	def __setitem__(self, sel, value):
-		self._data[sel] = value
 		node = self
 		while node.parent is not None:
 			node = node.parent
+		if getattr(node, "mode", "a") == "r":  # (a cached tree may be shared with a later writable handle)
+			raise OSError("Unable to write to dataset (file opened read-only)")
+		self._data[sel] = value
 		node._dirty = True
 
 	def __array__(self, dtype=None, copy=None):
@@ -262,7 +265,10 @@ class File(Group):
 						child.parent = self
 				else:
 					with open(self.filename, "rb") as fh:
-						_Reader(fh.read()).read_into(self)
+						reader = _Reader(fh.read())
+						reader.read_into(self)
+						if reader.unsupported:
+							self._shared["lossy"] = ", ".join(sorted(reader.unsupported))
 				self._shared["dirty"] = False
 			else:
 				self._shared["dirty"] = True  # a new (possibly empty) file must still be written
@@ -277,10 +283,19 @@ class File(Group):
 
 	def flush(self):
 		if self._shared["dirty"] and (self.mode != "r" or self._shared["open"] > 1):
+			if self._shared.get("lossy"):
+				# every flush re-serialises the whole file: content h5lite does not model would silently disappear
+				raise NotImplementedError(f"{self.filename} holds {self._shared['lossy']}, which h5lite cannot preserve when "
+										  "rewriting the file; write to a new file (or install h5py)")
 			blob = _Writer().serialise(self)
 			tmp = self.filename + ".h5lite.tmp"
 			with open(tmp, "wb") as fh:
 				fh.write(blob)
+			if os.path.exists(self.filename):  # keep the permission bits of the file being replaced
+				try:
+					os.chmod(tmp, os.stat(self.filename).st_mode & 0o7777)
+				except OSError:
+					pass
 			os.replace(tmp, self.filename)
 			self._shared["dirty"] = False
 			_RECENT.pop(self._shared["key"], None)
@@ -316,6 +331,7 @@ class File(Group):
 class _Reader:
 	def __init__(self, buf):
 		self.b = buf
+		self.unsupported = set()  # content that is skipped on reading and therefore lost when the file is rewritten
 		if buf[:8] != _SIG:
 			raise OSError("not an HDF5 file (bad signature)")
 		ver = buf[8]
@@ -349,6 +365,8 @@ class _Reader:
 			while p + 8 <= end and len(msgs) < nmsg:
 				mtype, msize, mflags = struct.unpack_from("<HHB", b, p)
 				body = p + 8
+				if mtype in (0x000C, 0x0015):
+					self.unsupported.add("attributes")
 				if mtype == 0x0010:  # continuation
 					caddr, clen = struct.unpack_from("<QQ", b, body)
 					blocks.append((caddr, clen))

@@ -60,6 +60,16 @@ def load_library():
 		if not os.path.exists(LIB_PATH):
 			raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
 							   "(there is no CPU fallback for the pair-count operator)")
+		from . import build
+		if build._stale():
+			# built from other sources than the ones in the tree (same ABI number, different kernels): rebuild, or refuse
+			import shutil
+			import warnings
+			if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+				warnings.warn("libmia_b200.so does not match the sources in the tree: rebuilding")
+				build.build_library()
+			else:
+				raise RuntimeError("libmia_b200.so does not match the sources in the tree and nvcc is not available to rebuild")
 		lib = ctypes.CDLL(LIB_PATH)
 		lib.mia_strerror.restype = ctypes.c_char_p
 		lib.mia_strerror.argtypes = [ctypes.c_int]

@@ -18,22 +18,22 @@ def _free_port():
 		return s.getsockname()[1]
 
 
-def _partials(rank, n_r=5, n_2=4, num_jk=8):
+def _partials(rank, n_r=5, n_2=4, num_jk=8, tasks_skew=0):
 	g = torch.Generator().manual_seed(100 + rank)
 	dd_count = torch.randint(0, 1000, (n_r, n_2), generator=g, dtype=torch.int64)
 	jk_count = torch.randint(0, 100, (num_jk, n_r, n_2), generator=g, dtype=torch.int64)
 	f = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64) * 1e3  # noqa: E731
-	stats = torch.tensor([10 + rank, 20 + rank, rank, 0, 2, 77, 5 + rank, 9], dtype=torch.int64)
+	stats = torch.tensor([10 + rank, 20 + rank, rank, 0, 2, 77, 5 + tasks_skew * rank, 9], dtype=torch.int64)
 	return dd_count, f(n_r, n_2), f(n_r, n_2), f(n_r, n_2), jk_count, f(num_jk, n_r, n_2), f(num_jk, n_r, n_2), stats
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, tasks_skew=0):
 	os.environ["MASTER_ADDR"] = "127.0.0.1"
 	os.environ["MASTER_PORT"] = str(port)
 	dist.init_process_group("gloo", rank=rank, world_size=world)
 	try:
 		from measure_ia_b200.box import combine_across_ranks
-		res = combine_across_ranks(*_partials(rank))
+		res = combine_across_ranks(*_partials(rank, tasks_skew=tasks_skew))
 		torch.save([t.clone() for t in res], os.path.join(out_dir, f"rank{rank}.pt"))
 	finally:
 		dist.destroy_process_group()
@@ -52,7 +52,13 @@ def test_combine_across_two_ranks(tmp_path):
 	# statistics: additive entries are summed, the kernel id / cell count are kept
 	for r in range(world):
 		s = got[r][7]
-		assert s[0] == 21 and s[1] == 41 and s[6] == 11 and s[4] == 2 and s[5] == 77
+		assert s[0] == 21 and s[1] == 41 and s[6] == 5 and s[4] == 2 and s[5] == 77
+
+
+def test_ranks_with_different_task_tables_fail_loudly(tmp_path):
+	"""Ranks that built different task tables (different SM counts / MIA_* variables) would drop or double-count tasks."""
+	with pytest.raises(Exception, match="ranks disagree"):
+		mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), 1), nprocs=2, join=True)
 
 
 def test_shard_slices_cover_the_sample():
