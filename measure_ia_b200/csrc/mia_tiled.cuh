@@ -1559,7 +1559,9 @@ inline int tiled_launch(const TiledConfig &cfg, const GridDims &gc, const GridDi
 	const double tasks_est = (double)nS / (double)spt + 0.5 * (double)ncol;
 	// (measured, profiles/r01_tuning.md: finer tasks help the (r_p, Pi) kernel's tail, the (r, mu_r) kernel pays more per task)
 	const char *tpw_env = getenv("MIA_TASKS_PER_WARP");
-	const double tasks_per_warp = tpw_env ? atof(tpw_env) : (cfg.geom == MIA_GEOM_RMU ? 8.0 : MIA_TASKS_PER_WARP);
+	// (cell-by-cell kernel: static slots, finer tasks shorten its tail; the others hand out slots dynamically and reuse per-task
+	// set-up across slabs, so they prefer long tasks: cfg2 96.7 ms at 8 against 98.3 at 32)
+	const double tasks_per_warp = tpw_env ? atof(tpw_env) : ((cfg.geom == MIA_GEOM_RMU || cfg.v2) ? 8.0 : MIA_TASKS_PER_WARP);
 	const double want = tasks_per_warp * (double)cfg.n_ctas * TW * (double)shard.count;
 	int split = (int)ceil(want / (tasks_est > 1.0 ? tasks_est : 1.0));
 	split = split < 1 ? 1 : (split > MAX_SPLIT ? MAX_SPLIT : split);

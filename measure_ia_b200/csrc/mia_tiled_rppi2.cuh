@@ -443,6 +443,10 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rppi2(const TiledArgs a) {
 		const int su0 = col / ncv_s;
 
 		const int slab0 = a.task_slab[2 * task], slab1 = a.task_slab[2 * task + 1];
+		// per-row v ranges of the two top windows, valid while the same lanes are alive (see the round set-up below)
+		float c_vmin0 = 0.f, c_vmax0 = 0.f, c_vmin1 = 0.f, c_vmax1 = 0.f;
+		int c_code0 = 0, c_code1 = 0;
+		unsigned c_alive0 = 0u, c_alive1 = 0u;
 		for (int s = slab0; s < slab1; s++) {
 			const double zlo = a.slab_lo[s], zhi = a.slab_hi[s];
 			if (!(zlo <= zhi)) continue;  // empty slab (uniform branch)
@@ -501,22 +505,44 @@ __global__ void __launch_bounds__(TP, 3) k_tiled_rppi2(const TiledArgs a) {
 							else if (cu >= ncu) cu = periodic ? cu - ncu : -1;
 						}
 						const long long row = (long long)cu * nz + s;
-						ColInfo ri;
-						ri.umin = ri.vmin = INFINITY;
-						ri.umax = ri.vmax = -INFINITY;
-						if (cu >= 0) ri = a.colinfo[row];
-						const int cu_code = axis_code(bu0, bu1, ri.umin, ri.umax);
-						// v cells within sqrt(r_hi^2 - d_u^2) of some alive shape of the warp (single precision, rounded outwards)
+						// v cells within sqrt(r_hi^2 - d_u^2) of some alive shape of the warp (single precision, rounded outwards), from
+						// the GEOMETRIC bounds of the row (cell edges): the range depends on the window and on which lanes are alive,
+						// not on the slab or the v region, so it is computed once per (task, window) and reused
 						float vmin_f = INFINITY, vmax_f = -INFINITY;
-						for (unsigned mm = alive; mm; mm &= mm - 1u) {
-							const int i = __ffs(mm) - 1;
-							const double xu = __shfl_sync(0xffffffffu, p.u, i), xv = __shfl_sync(0xffffffffu, p.v, i);
-							const double gu = gap(xu, ri.umin, ri.umax, cu_code);
-							const double g2 = gu * gu * (1.0 - 1e-9);
-							if (g2 < win_hi) {
-								const double dv = (double)(__fsqrt_ru(__double2float_ru(win_hi - g2)) * 1.000001f) + eps_v;
-								vmin_f = fminf(vmin_f, __double2float_rd(xv - dv));
-								vmax_f = fmaxf(vmax_f, __double2float_ru(xv + dv));
+						int cu_code = 0;
+						const bool cacheable = (q < 2) && (rbase == 0);
+						const unsigned c_al = q == 0 ? c_alive0 : c_alive1;
+						if (cacheable && c_al == alive) {
+							vmin_f = q == 0 ? c_vmin0 : c_vmin1;
+							vmax_f = q == 0 ? c_vmax0 : c_vmax1;
+							cu_code = q == 0 ? c_code0 : c_code1;
+						} else {
+							const double rlo = cu >= 0 ? (double)cu / P.inv_cu - eps_v : INFINITY;
+							const double rhi = cu >= 0 ? (double)(cu + 1) / P.inv_cu + eps_v : -INFINITY;
+							cu_code = axis_code(bu0, bu1, rlo, rhi);
+							for (unsigned mm = alive; mm; mm &= mm - 1u) {
+								const int i = __ffs(mm) - 1;
+								const double xu = __shfl_sync(0xffffffffu, p.u, i), xv = __shfl_sync(0xffffffffu, p.v, i);
+								const double gu = gap(xu, rlo, rhi, cu_code);
+								const double g2 = gu * gu * (1.0 - 1e-9);
+								if (g2 < win_hi) {
+									const double dv = (double)(__fsqrt_ru(__double2float_ru(win_hi - g2)) * 1.000001f) + eps_v;
+									vmin_f = fminf(vmin_f, __double2float_rd(xv - dv));
+									vmax_f = fmaxf(vmax_f, __double2float_ru(xv + dv));
+								}
+							}
+							if (cacheable) {
+								if (q == 0) {
+									c_vmin0 = vmin_f;
+									c_vmax0 = vmax_f;
+									c_code0 = cu_code;
+									c_alive0 = alive;
+								} else {
+									c_vmin1 = vmin_f;
+									c_vmax1 = vmax_f;
+									c_code1 = cu_code;
+									c_alive1 = alive;
+								}
 							}
 						}
 						int r_sA = 0, r_eA = 0, r_sB = 0, r_eB = 0, r_lab = -2, r_codes = 0, r_clA = 0, r_clB = 0;
