@@ -59,7 +59,7 @@ inline size_t tiled_rppi2s_smem_bytes(bool unit_w) {
 	const size_t ring = unit_w ? sizeof(CandSU) * CandRec<true>::CH : sizeof(CandSW) * CandRec<false>::CH;
 	const size_t fixed = ring * TW * STAGES + 256 + 768;
 	const size_t per_slot = (size_t)TP * (16 + 16 + 4 + (unit_w ? 0 : 8));
-	return fixed + per_slot * NSLOT_S;
+	return fixed + per_slot * NSLOT_S + (size_t)TP * 16;  // + per-thread flush factors {w e, w}
 }
 
 // Can the symmetric kernel take this grid?  The rows a warp streams (its own `ratio` rows and k rows ahead) must be
@@ -108,6 +108,7 @@ struct RWindowS {
 constexpr uint32_t AR_OFF = (uint32_t)NSLOT_S * TP * 16u;
 struct PrivAccS {
 	uint32_t af, ac, aw;
+	uint32_t fac;  // [thread] double2 {w e, w} of the thread's galaxy: the factors the flush applies to the lanes' sums
 };
 
 // Loop variants
@@ -414,39 +415,48 @@ __device__ __noinline__ void slow_pairs_sym(bool lane_susp, uint32_t cb, int n, 
 template <bool UNITW>
 __device__ __noinline__ unsigned flush_slots_sym(const FlushCtxS &fc, PrivAccS acc, unsigned long long key, bool dead, double pe,
 												 double pw, int ra, int rb, int jkD) {
+	static_assert(3 * NSLOT_S <= 32, "one lane per (slot, {forward, reverse, count}) column");
 	const int lane = threadIdx.x & 31;
+	// Column sums instead of butterflies: lane L < NS sums the forward double2 of slot L over the lanes of the group, lane NS + L
+	// the reverse double2, lane 2 NS + L the pair count (and the sum of w_D): 32 serial steps for ALL slots at once, each lane
+	// starting at its own lane index (rotated, so that the shared-memory banks are spread) -- a fixed order, about a third of the
+	// instructions of five butterfly reductions per slot.  All lanes run the same instruction stream (unused loads are harmless).
+	const int role = lane / NSLOT_S, sl = lane - role * NSLOT_S;
+	const uint32_t col2 = (acc.af - (uint32_t)lane * 16u) + (uint32_t)sl * TP * 16u + (role == 1 ? AR_OFF : 0u);
+	const uint32_t colc = (acc.ac - (uint32_t)lane * 4u) + (uint32_t)sl * TP * 4u;
+	const uint32_t colw = (acc.aw - (uint32_t)lane * 8u) + (uint32_t)sl * TP * 8u;
+	const uint32_t fac0 = acc.fac - (uint32_t)lane * 16u;
+	(void)pe;
+	(void)pw;
+	__syncwarp();  // the other lanes' private slots are read below: their stores must be visible
 	unsigned binned = 0;
 	unsigned todo = __ballot_sync(0xffffffffu, !dead);
 	while (todo) {
 		const int leader = __ffs(todo) - 1;
 		const unsigned long long k = __shfl_sync(0xffffffffu, key, leader);
 		const unsigned grp = __ballot_sync(0xffffffffu, key == k) & todo;
-		const bool in = (grp >> lane) & 1u;
-		unsigned tot_cnt = 0;
-		double tf_p = 0.0, tf_c = 0.0, tr_p = 0.0, tr_c = 0.0, tot_dw = 0.0;
-#pragma unroll 1
-		for (int sl = 0; sl < NSLOT_S; sl++) {
-			const uint32_t so = (uint32_t)sl * TP;
-			const unsigned c = in ? lds_u32(acc.ac + so * 4u) : 0u;
-			const unsigned csum = __reduce_add_sync(0xffffffffu, c);
-			if (csum == 0u) continue;
-			double v0 = 0.0, v1 = 0.0, u0 = 0.0, u1 = 0.0;
-			if (in) {
-				lds_v2(v0, v1, acc.af + so * 16u);
-				lds_v2(u0, u1, acc.af + so * 16u + AR_OFF);
-			}
-			const double xf = warp_sum(v0 * pe), yf = warp_sum(v1 * pe);
-			const double xr = warp_sum(u0 * pw), yr = warp_sum(u1 * pw);
-			const double zs = UNITW ? (double)csum : warp_sum(in ? lds_f64(acc.aw + so * 8u) * pw : 0.0);
-			if (lane == sl) {
-				tot_cnt = csum;
-				tf_p = xf;
-				tf_c = yf;
-				tr_p = xr;
-				tr_c = yr;
-				tot_dw = zs;
-			}
+		double x = 0.0, y = 0.0, dw = 0.0;
+		unsigned cnt = 0u;
+#pragma unroll 4
+		for (int t = 0; t < 32; t++) {
+			const int j = (t + lane) & 31;
+			const bool in = (grp >> j) & 1u;
+			double v0, v1, fe, fw;
+			lds_v2(v0, v1, col2 + (uint32_t)j * 16u);
+			lds_v2(fe, fw, fac0 + (uint32_t)j * 16u);
+			const unsigned c = lds_u32(colc + (uint32_t)j * 4u);
+			const double f = in ? (role == 0 ? fe : fw) : 0.0;
+			x = fma(v0, f, x);
+			y = fma(v1, f, y);
+			cnt += in ? c : 0u;
+			if (!UNITW) dw = fma(lds_f64(colw + (uint32_t)j * 8u), in ? fw : 0.0, dw);
 		}
+		// slot L's totals meet in lane L
+		const int srcr = (lane + NSLOT_S) & 31, srcc = (lane + 2 * NSLOT_S) & 31;
+		const double tf_p = x, tf_c = y;
+		const double tr_p = __shfl_sync(0xffffffffu, x, srcr), tr_c = __shfl_sync(0xffffffffu, y, srcr);
+		const unsigned tot_cnt = __shfl_sync(0xffffffffu, cnt, srcc);
+		const double tot_dw = UNITW ? (double)tot_cnt : __shfl_sync(0xffffffffu, dw, srcc);
 		const int kjk = (int)(k >> 32);
 		const int kfb0 = (int)((k >> 24) & 0xffu) - 1, kfb1 = (int)((k >> 16) & 0xffu) - 1;
 		const int krb0 = (int)((k >> 8) & 0xffu) - 1, krb1 = (int)(k & 0xffu) - 1;
@@ -465,11 +475,11 @@ __device__ __noinline__ unsigned flush_slots_sym(const FlushCtxS &fc, PrivAccS a
 		todo &= ~grp;
 	}
 #pragma unroll
-	for (int sl = 0; sl < NSLOT_S; sl++) {
-		sts_v2(acc.af + (uint32_t)sl * TP * 16u, 0.0, 0.0);
-		sts_v2(acc.af + (uint32_t)sl * TP * 16u + AR_OFF, 0.0, 0.0);
-		if (!UNITW) sts_f64(acc.aw + (uint32_t)sl * TP * 8u, 0.0);
-		sts_u32(acc.ac + (uint32_t)sl * TP * 4u, 0u);
+	for (int s_ = 0; s_ < NSLOT_S; s_++) {
+		sts_v2(acc.af + (uint32_t)s_ * TP * 16u, 0.0, 0.0);
+		sts_v2(acc.af + (uint32_t)s_ * TP * 16u + AR_OFF, 0.0, 0.0);
+		if (!UNITW) sts_f64(acc.aw + (uint32_t)s_ * TP * 8u, 0.0);
+		sts_u32(acc.ac + (uint32_t)s_ * TP * 4u, 0u);
 	}
 	return binned;
 }
@@ -624,6 +634,7 @@ __global__ void __launch_bounds__(TP, MIA_S_MIN_CTAS) k_tiled_rppi2s(const Tiled
 	cx.acc.af = acc_u32 + (uint32_t)tid * 16u;
 	cx.acc.aw = acc_u32 + (uint32_t)NSLOT_S * TP * 32u + (uint32_t)tid * 8u;
 	cx.acc.ac = acc_u32 + (uint32_t)NSLOT_S * TP * (UNITW ? 32u : 40u) + (uint32_t)tid * 4u;
+	cx.acc.fac = acc_u32 + (uint32_t)NSLOT_S * TP * (UNITW ? 36u : 44u) + (uint32_t)tid * 16u;
 	cx.ring_u32 = smem_u32(my_ring);
 	cx.ring = reinterpret_cast<unsigned char *>(my_ring);
 	cx.full = full + warp * STAGES;
@@ -745,6 +756,8 @@ __global__ void __launch_bounds__(TP, MIA_S_MIN_CTAS) k_tiled_rppi2s(const Tiled
 		cx.a1 = p.a1;
 		cx.pe = p.w * p.e;
 		cx.pw = p.w;
+		sts_v2(cx.acc.fac, cx.pe, cx.pw);  // the flush reads the other lanes' factors from shared memory
+		__syncwarp();
 		cx.jkS = p.jk;
 		const int su0 = col / ncv_s;
 
