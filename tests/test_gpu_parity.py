@@ -122,6 +122,8 @@ def _host_call(torch, oracle, data, geom, num_jk, boxsize, n_r, n_2, kernel=0, s
 	from measure_ia_b200 import MeasureIABox, ops
 	box = MeasureIABox(data, None, boxsize=boxsize, num_bins_r=n_r, num_bins_pi=n_2)
 	pos, pos_s, axis, e, w, w_s, same = box._prepare(None, "distortion")
+	if pos is pos_s and np.array_equal(w, w_s):
+		w_s = w  # the C ABI recognises an auto-correlation by pointer identity of pos / weight / jk (include/mia_b200.h)
 	L = round(num_jk ** (1 / 3)) if num_jk else 0
 	jk = box._jackknife_labels(pos, L).astype(np.int32) if num_jk else None
 	r2_thr, thr2, rp2_cut, _ = box._thresholds_for(geom, None)
@@ -156,12 +158,18 @@ def test_c_abi_host_entry(torch_cuda, oracle, geom):
 		np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-11 * np.abs(b).max())
 
 
-def test_shards_sum_to_whole(torch_cuda, oracle):
-	"""Multi-GPU partitioning property on one GPU: the shards of the shape sample add up to the unsharded result."""
+@pytest.mark.parametrize("geom,plan", [("rppi", "default"), ("rppi", "rows"), ("rmu", "default")])
+def test_shards_sum_to_whole(torch_cuda, oracle, monkeypatch, geom, plan):
+	"""Multi-GPU partitioning property on one GPU: the shards of the shape sample add up to the unsharded result (default
+	plan: cell-by-cell kernel, static slots; rows: the symmetric kernel, interleaved slots handed out dynamically)."""
 	from measure_ia_b200.synthetic import uniform_box
+	if plan == "rows":
+		monkeypatch.setenv("MIA_RPPI_V2", "2")
 	data = uniform_box(30000, 205.0, seed=9)
-	whole, _ = _host_call(torch_cuda, oracle, data, "rppi", 27, 205.0, 10, 8)
-	parts = [_host_call(torch_cuda, oracle, data, "rppi", 27, 205.0, 10, 8, shard=(i, 3))[0] for i in range(3)]
+	whole, _ = _host_call(torch_cuda, oracle, data, geom, 27, 205.0, 10, 8)
+	if plan == "rows" or geom == "rmu":
+		assert int(whole["stats"][4]) == 4  # the symmetric kernels (same arrays on both sides through the host entry point)
+	parts = [_host_call(torch_cuda, oracle, data, geom, 27, 205.0, 10, 8, shard=(i, 3))[0] for i in range(3)]
 	assert np.array_equal(sum(p["dd_count"] for p in parts), whole["dd_count"])
 	assert np.array_equal(sum(p["dd_jk_count"] for p in parts), whole["dd_jk_count"])
 	np.testing.assert_allclose(sum(p["spd"] for p in parts), whole["spd"], rtol=1e-10, atol=1e-9)
@@ -320,6 +328,9 @@ _CROSS_CASES = [
 	(20, 50.0, 16, 27, 6, 10, dict(gen="lattice", los=0, separation_limits=(2.5, 20.0))),
 	(12, 30.0, 15, 27, 4, 6, dict(gen="lattice", los=1, n_random=150, separation_limits=(2.5, 12.5), pi_max=7.5)),
 	(20000, 100.0, 12, 8, 10, 8, dict(gen="aligned_pairs")),
+	# 11^3 regions on a grid that cannot be aligned with them: rows whose region holds several labels take the cell-by-cell
+	# path of the (symmetric) rows kernels, and the accumulator workspace cap (fewer worker slots) applies
+	(5000, 60.0, 21, 1331, 6, 6, {}),
 ]
 
 
