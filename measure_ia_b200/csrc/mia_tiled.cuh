@@ -304,10 +304,27 @@ inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g,
 			// auto-correlation, as far as the plan can know: the workspace layout must not depend on pointer identity) and the
 			// grid admits the half-space rule (checked below)
 			thin_auto = nz > 16 && nz <= 32 && nD == nS && env_int("MIA_SYM", 1) != 0 && p->kernel != MIA_KERNEL_TILED_ORDERED;
+			// cells per r_max: the finest of 26 / 22 / 18 / 14 / 10 that still leaves ~110 candidates per streamed range (measured,
+			// profiles/r02_tuning.md: cfg2 95.9 / 93.2 / 94.9 ms at 10 / 14 / 18; cfg4 3650 / 3419 / 3323 / 3247 / 3230 / 3250 ms at
+			// 10 / 14 / 18 / 22 / 26 / 30): finer cells cull better and fill the 32 lanes of a round with rows
 			if (nz > 16 && !thin_auto) v2 = 0;
-			else if (piece(10) >= (thin_auto ? 40.0 : 100.0)) div2 = 10;
-			else if (piece(6) >= 15.0) div2 = 6;
-			else v2 = 0;
+			else if (thin_auto) {
+				if (piece(10) >= 40.0) div2 = 10;
+				else if (piece(6) >= 15.0) div2 = 6;
+				else v2 = 0;
+			} else {
+				for (int d : {26, 22, 18, 14}) {
+					if (piece(d) >= 110.0) {
+						div2 = d;
+						break;
+					}
+				}
+				if (!div2) {
+					if (piece(10) >= 100.0) div2 = 10;
+					else if (piece(6) >= 15.0) div2 = 6;
+					else v2 = 0;
+				}
+			}
 			if (v2 == 0 && must_rows) {
 				v2 = 2;
 				div2 = 6;
