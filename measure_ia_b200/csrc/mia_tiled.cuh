@@ -314,6 +314,9 @@ inline bool plan_tiled(const mia_params *p, int64_t nD, int64_t nS, GridDims &g,
 				else v2 = 0;
 			} else {
 				for (int d : {26, 22, 18, 14}) {
+					// (the ordered kernel streams 2k + 2 rows: beyond 14 they no longer fit one round of 32 lanes; it measured
+					// 114.4 / 113.4 / 118.5 ms at 10 / 14 / 18 on cfg2, so different sample sizes -- surely a cross-correlation -- stop at 14)
+					if (d > 14 && nD != nS) continue;
 					if (piece(d) >= 110.0) {
 						div2 = d;
 						break;
