@@ -514,7 +514,7 @@ def main():
 					rec["roofline"] = roofline(r, Ws.kind, world, peak, peak_clocks, Ws.N, name)
 					rec["roofline"].pop("note", None)
 				if not args.no_parity and (name != "cfg4" or world >= 8):  # (1e7 galaxies: the general kernel needs 8 GPUs)
-					rec["parity_check"] = Ws.parity_vs_general(r["out"], repeat_general=(name != "cfg4"))
+					rec["parity_check"] = Ws.parity_vs_general(r["out"])  # (cfg4: 2 x 25 s of the sharded general kernel)
 				sec[name] = rec
 				del Ws, r
 				torch.cuda.empty_cache()
