@@ -243,6 +243,19 @@ def test_workspace_planning_runs_without_a_gpu(monkeypatch):
 		assert ws("rppi", 1000000, kernel="tiled") > 0
 	assert ws("rmu", 100000, n_2=40) > 0
 	assert ws("rmu", 100000, n_2=40, kernel="tiled") == 0
+	# planning knobs that change the workspace: the symmetric kernels' 64-byte candidate records (equal sample sizes only),
+	# the accumulator cap, finer worker slots for large catalogues
+	monkeypatch.delenv("MIA_RPPI_V2")
+	full = ws("rppi", 1000000)
+	assert ws("rppi", 1000000, kernel="tiled_ordered") < full  # 32-byte candidates, no symmetric path
+	monkeypatch.setenv("MIA_SLOT_MULT", "1")
+	one = ws("rppi", 1000000)
+	assert one < full and full - one > 1.0e9  # 4x the accumulator copies by default at 1e6 shapes (1.96 GB vs 0.49 GB)
+	monkeypatch.delenv("MIA_SLOT_MULT")
+	monkeypatch.setenv("MIA_ACC_CAP_MB", "256")
+	assert ws("rppi", 1000000) < one
+	monkeypatch.delenv("MIA_ACC_CAP_MB")
+	assert ws("rppi", 1000000, num_jk=1000) < 6.0e9  # 2000 rows x 80 bins x 32 B per copy: capped at 4 GiB of copies
 
 
 def test_h5lite_reuses_the_tree_it_wrote_last(tmp_path):
