@@ -326,7 +326,21 @@ def run_cfg5(dev, rank, world, barrier, kernel):
 				box.create_full_cov_matrix_projections(corr, names, num_box=27)
 		barrier()
 		wall = time.perf_counter() - t0
+	# the same work through the batched call: one catalogue preparation and one file handle for the three
+	# projections, the covariance combination included
+	try:
+		barrier()
+		t0 = time.perf_counter()
+		box.measure_xi_projections(names, "both", num_jk=27, temp_file_path=tmp + "/", masks=dict(masks), statistics="w")
+		barrier()
+		bw = time.perf_counter() - t0
+		bp = sum(int(r["count"].sum()) for r in box.last_results.values())
+		batched = {"wall_s": bw, "value": bp / bw, "pairs_equal": bp == pairs, "t_catalogue_s": box.last_stats["t_catalogue"],
+				   "t_write_s": box.last_stats["t_write"], "api": "measure_xi_projections(names, statistics='w')"}
+	except Exception as exc:  # noqa: BLE001
+		batched = {"error": f"{type(exc).__name__}: {exc}"}
 	return {"value": pairs / wall, "unit": "pairs/s", "wall_s": wall, "pairs": pairs, "pair_kernel_ms_rank0": kernel_ms,
+			"batched": batched,
 			"config": {"n_position": n_p, "n_shape": n_s, "masks": "70 % / 60 % kept", "weights": "U(0.5, 1.5)", "boxsize": L,
 					   "num_jk": 27, "bins": [10, 8], "datasets": names,
 					   "steps": "3 x measure_xi_w(host numpy dict) + create_full_cov_matrix_projections(w_g_plus, w_gg)"},

@@ -357,12 +357,27 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 			self._thresholds[key] = (r2_thr, thr2, calib.rp_cut_threshold(rp_cut), clean)
 		return self._thresholds[key]
 
+	def _device(self):
+		"""The CUDA device of this object's operator calls; raises when there is none (no CPU fallback)."""
+		import torch
+		if not torch.cuda.is_available():
+			raise RuntimeError("measure_ia_b200 needs a CUDA device: the pair-count operator has no CPU fallback")
+		return torch.device(self.device) if self.device is not None else torch.device("cuda", torch.cuda.current_device())
+
 	# ---- input preparation on the device (same semantics as _prepare / _jackknife_labels / _responsivity) ---------------
 	def _prepare_device(self, masks, ellipticity, L_subboxes, dev):
 		"""Upload the raw catalogue once and do the whole preparation with fp64 torch ops on the GPU: mask selection,
 		axis normalisation, e(q), jackknife labels (strict-inequality rule, label 0 on faces), responsivities and the
 		per-region counts.  At 1e6-1e7 galaxies the numpy versions cost as much as the pair kernel itself
-		(SURVEY.md 8(f)-1); sqrt and division are IEEE-exact on the device, so axis / e / labels are bit-identical."""
+		(SURVEY.md 8(f)-1); sqrt and division are IEEE-exact on the device, so axis / e / labels are bit-identical.
+
+		Two halves: `_prepare_catalogue` (everything that does not depend on the projection: positions, weights, masks,
+		labels, per-region counts) and `_prepare_shapes` (the projected shape inputs: axis, e, responsivities);
+		`measure_xi_projections` runs the first half once for all its projections."""
+		C = self._prepare_catalogue(masks, L_subboxes, dev)
+		return self._prepare_shapes(C, self.data["Axis_Direction"], self.data["q"], masks, ellipticity)
+
+	def _prepare_catalogue(self, masks, L_subboxes, dev):
 		import torch
 		d = self.data
 		f64 = torch.float64
@@ -374,7 +389,6 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 		same_w = d["weight"] is d["weight_shape_sample"]
 		pos = up(d["Position"])
 		pos_s = pos if same_pos else up(d["Position_shape_sample"])
-		axis_v, q = up(d["Axis_Direction"]), up(d["q"])
 		w = up(d["weight"])
 		w_s = w if same_w else up(d["weight_shape_sample"])
 		if masks is not None:
@@ -390,7 +404,6 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 				masks["weight_shape_sample"] = m
 			mk = lambda k: torch.from_numpy(np.ascontiguousarray(masks[k], dtype=bool)).to(dev)  # noqa: E731
 			pos, pos_s = pos[mk("Position")], pos_s[mk("Position_shape_sample")]
-			axis_v, q = axis_v[mk("Axis_Direction")], q[mk("q")]
 			w, w_s = w[mk("weight")], w_s[mk("weight_shape_sample")]
 		# auto-correlation?  Decided by VALUE on the device (the constructor injects two separate unit-weight arrays, and a
 		# user may pass equal copies): the operator then receives the same tensors on both sides, which lets the library
@@ -399,21 +412,8 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 					and (pos is pos_s or torch.equal(pos, pos_s)) and (w is w_s or torch.equal(w, w_s)))
 		if same:
 			pos_s, w_s = pos, w
-		if axis_v.dim() != 2 or axis_v.shape[1] < 2 or pos.dim() != 2 or pos.shape[1] != 3 or pos_s.shape[1:] != pos.shape[1:]:
+		if pos.dim() != 2 or pos.shape[1] != 3 or pos_s.dim() != 2 or pos_s.shape[1:] != pos.shape[1:]:
 			raise ValueError("Position / Position_shape_sample must be (N, 3) and Axis_Direction (N_s, >= 2) arrays")
-		# row norm over ALL columns, summed left to right like np.sum(axis_v ** 2, axis=1) (measure_w_box_jk.py:326); the
-		# pair loop reads the first two normalised components (calculate_dot_product_arrays iterates over the columns of
-		# the 2-D projected separation, measure_IA_base.py:186-205)
-		sq = axis_v[:, 0] * axis_v[:, 0]
-		for c in range(1, axis_v.shape[1]):
-			sq = sq + axis_v[:, c] * axis_v[:, c]
-		axis = (axis_v / torch.sqrt(sq)[:, None])[:, :2].contiguous()
-		if ellipticity == "distortion":
-			e = (1 - q * q) / (1 + q * q)
-		elif ellipticity == "ellipticity":
-			e = (1 - q) / (1 + q)
-		else:
-			raise ValueError("Invalid value for ellipticity. Choose 'distortion' or 'ellipticity'.")
 		num_box = L_subboxes ** 3 if L_subboxes else 0
 
 		def labels(p):
@@ -429,14 +429,51 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 				lab = lab * n + ic
 			return torch.where(inside, lab, torch.zeros_like(lab)).to(torch.int32)
 
-		jk_p = jk_s = None
-		t = w_s * (1 - e * e / 2.0)
-		R = float((t.sum() / w_s.sum()).item()) if t.numel() else float("nan")
-		R_jk = n_p_k = n_s_k = None
+		jk_p = jk_s = n_p_k = n_s_k = None
 		if num_box:
 			jk_p = labels(pos)
 			jk_s = jk_p if same else labels(pos_s)
-			js = jk_s.to(torch.int64)
+			n_p_k = pos.shape[0] - torch.bincount(jk_p.to(torch.int64), minlength=num_box).cpu().numpy()
+			n_s_k = pos_s.shape[0] - torch.bincount(jk_s.to(torch.int64), minlength=num_box).cpu().numpy()
+		unit_p = bool((w == 1.0).all().item())
+		unit_s = unit_p if same else bool((w_s == 1.0).all().item())
+		return dict(pos=pos.contiguous(), pos_s=pos_s.contiguous(), w=None if unit_p else w.contiguous(),
+					w_s=None if unit_s else w_s.contiguous(), w_s_full=w_s, jk_p=jk_p, jk_s=jk_s, same=same, n_p_k=n_p_k,
+					n_s_k=n_s_k, Np=int(pos.shape[0]), Ns=int(pos_s.shape[0]), num_box=num_box, dev=dev)
+
+	def _prepare_shapes(self, C, axis_direction, q_ratio, masks, ellipticity):
+		"""The projection-dependent half of the preparation: normalised axis, e(q), R and the per-region R_jk."""
+		import torch
+		dev, f64 = C["dev"], torch.float64
+
+		def up(a):
+			return torch.from_numpy(np.ascontiguousarray(a)).to(dev).to(f64)
+
+		axis_v, q = up(axis_direction), up(q_ratio)
+		if masks is not None:
+			mk = lambda k: torch.from_numpy(np.ascontiguousarray(masks[k], dtype=bool)).to(dev)  # noqa: E731
+			axis_v, q = axis_v[mk("Axis_Direction")], q[mk("q")]
+		if axis_v.dim() != 2 or axis_v.shape[1] < 2:
+			raise ValueError("Position / Position_shape_sample must be (N, 3) and Axis_Direction (N_s, >= 2) arrays")
+		# row norm over ALL columns, summed left to right like np.sum(axis_v ** 2, axis=1) (measure_w_box_jk.py:326); the
+		# pair loop reads the first two normalised components (calculate_dot_product_arrays iterates over the columns of
+		# the 2-D projected separation, measure_IA_base.py:186-205)
+		sq = axis_v[:, 0] * axis_v[:, 0]
+		for c in range(1, axis_v.shape[1]):
+			sq = sq + axis_v[:, c] * axis_v[:, c]
+		axis = (axis_v / torch.sqrt(sq)[:, None])[:, :2].contiguous()
+		if ellipticity == "distortion":
+			e = (1 - q * q) / (1 + q * q)
+		elif ellipticity == "ellipticity":
+			e = (1 - q) / (1 + q)
+		else:
+			raise ValueError("Invalid value for ellipticity. Choose 'distortion' or 'ellipticity'.")
+		w_s, num_box = C["w_s_full"], C["num_box"]
+		t = w_s * (1 - e * e / 2.0)
+		R = float((t.sum() / w_s.sum()).item()) if t.numel() else float("nan")
+		R_jk = None
+		if num_box:
+			js = C["jk_s"].to(torch.int64)
 			# per realisation: the same ratio over the shapes NOT in region k (measure_w_box_jk.py:463-466).  Masked
 			# torch.sum calls (fixed reduction tree) instead of index_add_/bincount-with-weights, whose atomics would make
 			# the last bit of R_jk vary from run to run
@@ -452,16 +489,14 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 			num, den = torch.cat(num), torch.cat(den)
 			with np.errstate(invalid="ignore", divide="ignore"):
 				R_jk = num.cpu().numpy() / den.cpu().numpy()
-			n_p_k = pos.shape[0] - torch.bincount(jk_p.to(torch.int64), minlength=num_box).cpu().numpy()
-			n_s_k = pos_s.shape[0] - torch.bincount(js, minlength=num_box).cpu().numpy()
-		unit_p = bool((w == 1.0).all().item())
-		unit_s = unit_p if same else bool((w_s == 1.0).all().item())
-		return dict(pos=pos.contiguous(), pos_s=pos_s.contiguous(), axis=axis, e=e.contiguous(),
-					w=None if unit_p else w.contiguous(), w_s=None if unit_s else w_s.contiguous(), jk_p=jk_p, jk_s=jk_s,
-					same=same, R=R, R_jk=R_jk, n_p_k=n_p_k, n_s_k=n_s_k, Np=int(pos.shape[0]), Ns=int(pos_s.shape[0]))
+		P = dict(C)
+		P.update(axis=axis, e=e.contiguous(), R=R, R_jk=R_jk)
+		return P
 
 	# ---- the pair loop: ONE operator call replaces the reference's twelve variants -----------------------------------------
-	def _pair_sums(self, geom, masks, L_subboxes, ellipticity, rp_cut=None, variance=False):
+	def _pair_sums(self, geom, masks, L_subboxes, ellipticity, rp_cut=None, variance=False, prepared=None, los=None):
+		"""`prepared` / `los`: inputs already on the device (`_prepare_shapes`) and the line of sight to use instead of
+		``data["LOS"]`` -- the batched projections call."""
 		import torch
 
 		from . import ops
@@ -469,12 +504,10 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 		t0 = time.perf_counter()
 		if ellipticity not in ("distortion", "ellipticity"):
 			raise ValueError("Invalid value for ellipticity. Choose 'distortion' or 'ellipticity'.")
-		if not torch.cuda.is_available():
-			raise RuntimeError("measure_ia_b200 needs a CUDA device: the pair-count operator has no CPU fallback")
-		dev = torch.device(self.device) if self.device is not None else torch.device("cuda", torch.cuda.current_device())
+		dev = self._device()
 		num_box = L_subboxes ** 3 if L_subboxes else 0
 		r2_thr, thr2, rp2_cut, clean = self._thresholds_for(geom, rp_cut)
-		P = self._prepare_device(masks, ellipticity, L_subboxes, dev)
+		P = prepared if prepared is not None else self._prepare_device(masks, ellipticity, L_subboxes, dev)
 		torch.cuda.synchronize(dev)
 		t1 = time.perf_counter()
 
@@ -484,7 +517,8 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 		kernel = ops.KERNEL_NAMES[self.kernel]
 		out = torch.ops.measure_ia_b200.paircount(
 			P["pos"], P["w"], P["jk_p"], P["pos_s"], P["w_s"], P["jk_s"], P["axis"], P["e"], torch.from_numpy(r2_thr),
-			torch.from_numpy(thr2), ops.GEOM_RPPI if geom == "rppi" else ops.GEOM_RMU, int(self.data["LOS"]),
+			torch.from_numpy(thr2), ops.GEOM_RPPI if geom == "rppi" else ops.GEOM_RMU,
+			int(self.data["LOS"] if los is None else los),
 			bool(self.periodicity), num_box, float(self.boxsize), float(self.r_bins[-1]), float(rp2_cut), kernel, rank, world,
 			bool(variance))
 		dd_count, dd_w, spd, scd, jk_count, jk_w, spd_jk, stats, var = out
@@ -505,7 +539,9 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 		return res
 
 	# ---- results -> the reference's HDF5 layout (measure_w_box_jk.py:498-539, measure_w_box.py:387-407) ------------------
-	def _write_xi(self, geom, res, dataset_name, num_box, jk_group_name, corr_type, return_output=False):
+	def _write_xi(self, geom, res, dataset_name, num_box, jk_group_name, corr_type, return_output=False, handle=None):
+		"""`handle`: an output file the caller already has open (the batched projections call writes all its datasets
+		through one handle); otherwise the file is opened and closed here."""
 		R = res["R"]
 		DD = res["DD"]
 		SpD = res["SpD_raw"] / (2 * R)
@@ -535,7 +571,7 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 			if return_output:
 				return xi_gp, xi_gg, sep, mid2, SpD, DD, RR
 			X = dataset_name
-			f = open_file(self.output_file_name, "a")
+			f = handle if handle is not None else open_file(self.output_file_name, "a")
 			try:
 				snap = self.snap_group
 				g = create_group_hdf5(f, f"{snap}/{top}/xi_g_plus/")
@@ -610,7 +646,8 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 						write_dataset_hdf5(out, f"{X}_jackknife_{num_box}", data=std)
 						write_dataset_hdf5(out, f"{X}_jackknife_cov_{num_box}", data=cov)
 			finally:
-				f.close()
+				if handle is None:
+					f.close()
 
 	# ---- public API ---------------------------------------------------------------------------------------------------------
 	def _measure(self, geom, dataset_name, corr_type, num_jk, temp_file_path, masks, ellipticity, rp_cut=None):
@@ -651,6 +688,86 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 		``rp_cut`` is accepted and, exactly as in the reference, NOT forwarded to the pair loop (measure_IA.py:218-259
 		never passes it on), so it has no effect through this entry point."""
 		self._measure("rmu", dataset_name, corr_type, num_jk, temp_file_path, masks, ellipticity, rp_cut=None)
+
+	def measure_xi_projections(self, dataset_names=("LOS_x", "LOS_y", "LOS_z"), corr_type="both", num_jk=0,
+							   temp_file_path=None, masks=None, statistics=("w", "multipoles"), projections=None,
+							   ellipticity='distortion', full_covariance=True):
+		r"""Several projections of ONE box in one call (not a method of the reference).
+
+		The reference's workflow for the covariance of three projections (measure_jackknife.py:573-648 reads the datasets
+		``LOS_x`` / ``LOS_y`` / ``LOS_z``) is three ``MeasureIABox`` runs per statistic, each of which re-reads, re-masks and
+		re-labels the same positions.  Here the projection-independent half of the preparation (upload, mask selection,
+		weights, jackknife labels, per-region counts; `_prepare_catalogue`) runs ONCE, each (projection, statistic) is one
+		operator call on the resident catalogue, everything is written through one file handle, and -- for three
+		projections with ``num_jk > 0`` and ``full_covariance`` -- ``create_full_cov_matrix_projections`` follows for every
+		integrated statistic.  Each stored dataset is what the separate ``measure_xi_w`` / ``measure_xi_multipoles`` calls
+		with ``data["LOS"]`` (and the projection's shapes) set accordingly would have stored.
+
+		projections : one dict per dataset name; ``"LOS"`` (default: 0, 1, 2, ...) and optionally ``"Axis_Direction"`` and
+			``"q"`` -- the PROJECTED shapes of that line of sight, which in the reference's catalogues differ per projection;
+			missing keys fall back to ``self.data``.
+		statistics : any of ``"w"`` ((r_p, Pi) grid, ``measure_xi_w``) and ``"multipoles"`` ((r, mu_r), ``measure_xi_multipoles``).
+		"""
+		dataset_names = list(dataset_names)
+		if projections is None:
+			projections = [{"LOS": i} for i in range(len(dataset_names))]
+		projections = [dict(p) for p in projections]
+		if len(projections) != len(dataset_names):
+			raise ValueError("one entry of `projections` per dataset name")
+		for p in projections:
+			if p.get("LOS", None) not in (0, 1, 2):
+				raise ValueError("every projection needs LOS in (0, 1, 2)")
+		statistics = [statistics] if isinstance(statistics, str) else list(statistics)
+		for st in statistics:
+			if st not in ("w", "multipoles"):
+				raise KeyError("Unknown statistic. Choose from [w, multipoles]")
+		L = 0
+		if num_jk > 0:
+			L, exact = integer_cube_root(num_jk)
+			if not exact:
+				raise ValueError(
+					f"Use x^3 as input for num_jk, with x as an int. {float(int(num_jk ** (1. / 3)))},{num_jk ** (1. / 3)}")
+		if temp_file_path is None:
+			raise ValueError(
+				"Input temp_file_path for faster computation. Do not want to save data temporarily? Input file_path_tree=False.")
+		if corr_type not in ("both", "g+", "gg"):
+			raise KeyError("Unknown value for corr_type. Choose from [g+, gg, both]")
+		if ellipticity not in ("distortion", "ellipticity"):
+			raise ValueError("Invalid value for ellipticity. Choose 'distortion' or 'ellipticity'.")
+		want_var = isinstance(temp_file_path, (bool, int)) and temp_file_path == False and num_jk > 0  # noqa: E712
+		t0 = time.perf_counter()
+		C = self._prepare_catalogue(masks, L, self._device())
+		t_cat = time.perf_counter() - t0
+		results, stats, pending = {}, {}, []
+		for name, proj in zip(dataset_names, projections):
+			P = self._prepare_shapes(C, proj.get("Axis_Direction", self.data["Axis_Direction"]), proj.get("q", self.data["q"]),
+									 masks, ellipticity)
+			for st in statistics:
+				geom = "rppi" if st == "w" else "rmu"
+				res = self._pair_sums(geom, masks, L, ellipticity, None, variance=want_var, prepared=P, los=proj["LOS"])
+				results[(name, st)] = res
+				stats[(name, st)] = self.last_stats
+				pending.append((geom, res, name))
+		t1 = time.perf_counter()
+		is_writer = self.last_stats["rank"] == 0
+		if is_writer and self.output_file_name is not None:
+			f = open_file(self.output_file_name, "a")
+			try:
+				for geom, res, name in pending:
+					jk_group = f"{name}_jk{num_jk}" if num_jk > 0 else ""
+					self._write_xi(geom, res, name, num_jk if num_jk > 0 else 0, jk_group, corr_type, handle=f)
+				if full_covariance and num_jk > 0 and len(dataset_names) == 3:
+					kinds = {"both": ["g_plus", "gg"], "g+": ["g_plus"], "gg": ["gg"]}[corr_type]
+					for st in statistics:
+						for which in kinds:
+							self.create_full_cov_matrix_projections(("w_" if st == "w" else "multipoles_") + which, dataset_names,
+																	num_box=num_jk, _handle=f)
+			finally:
+				f.close()
+		self.last_results = results
+		self.last_result = pending[-1][1] if pending else None
+		self.last_stats = dict(self.last_stats) if pending else {}
+		self.last_stats.update(per_measurement=stats, t_catalogue=t_cat, t_pairs=t1 - t0, t_write=time.perf_counter() - t1)
 
 
 def combine_across_ranks(dd_count, dd_w, spd, scd, jk_count, jk_w, spd_jk, stats, var=None):

@@ -13,21 +13,23 @@ _VALID = ("w_g_plus", "multipoles_g_plus", "w_gg", "multipoles_gg")
 
 
 class JackknifeCombinationMixin:
-	def measure_covariance_multiple_datasets(self, corr_type, dataset_names, num_box=27, return_output=False):
+	def measure_covariance_multiple_datasets(self, corr_type, dataset_names, num_box=27, return_output=False, _handle=None):
 		"""Jackknife covariance of one dataset with itself or of two datasets with each other
-		(measure_jackknife.py:485-571): cov[:, i] = (n-1)/n sum_b (x_b - mean_x) (y_b[i] - mean_y[i])."""
+		(measure_jackknife.py:485-571): cov[:, i] = (n-1)/n sum_b (x_b - mean_x) (y_b[i] - mean_y[i]).
+		`_handle` (not in the reference): an output file the caller keeps open, used instead of opening / closing it here."""
 		if corr_type not in _VALID:
 			raise ValueError("corr_type must be 'w_g_plus', 'w_gg', 'multipoles_g_plus' or 'multipoles_gg'.")
 		if len(dataset_names) not in (1, 2):
 			raise KeyError("Too many datasets given, choose either 1 or 2")
-		f = open_file(self.output_file_name, "a")
+		f = _handle if _handle is not None else open_file(self.output_file_name, "a")
 		try:
 			reals = []
 			for name in dataset_names:
 				grp = f[f"{self.snap_group}/{corr_type}/{name}_jk{num_box}"]
 				reals.append(np.array([grp[f"{name}_{b}"][:] for b in range(num_box)]))
 		finally:
-			f.close()
+			if _handle is None:
+				f.close()
 		means = []
 		for x in reals:
 			m = np.zeros(self.num_bins_r)
@@ -49,19 +51,20 @@ class JackknifeCombinationMixin:
 			std = np.sqrt(std)
 		cov *= (num_box - 1) / num_box
 		if self.output_file_name is not None and not return_output:
-			f = open_file(self.output_file_name, "a")
+			f = _handle if _handle is not None else open_file(self.output_file_name, "a")
 			try:
 				grp = create_group_hdf5(f, f"{self.snap_group}/{corr_type}")
 				stem = dataset_names[0] if len(dataset_names) == 1 else dataset_names[0] + "_" + dataset_names[1]
 				write_dataset_hdf5(grp, f"{stem}_jackknife_cov_{num_box}", data=cov)
 				write_dataset_hdf5(grp, f"{stem}_jackknife_{num_box}", data=std)
 			finally:
-				f.close()
+				if _handle is None:
+					f.close()
 			return None
 		return cov, std
 
 	def create_full_cov_matrix_projections(self, corr_type, dataset_names=["LOS_x", "LOS_y", "LOS_z"], num_box=27,
-										   return_output=False):
+										   return_output=False, _handle=None):
 		"""Block covariance of three projections and of each pair of projections (measure_jackknife.py:573-648).
 
 		Kept quirk of the reference: the blocks it calls `cov_yz` / `cov_xz` are read from the datasets
@@ -69,8 +72,9 @@ class JackknifeCombinationMixin:
 		below use them exactly as the reference does, so the stored results are identical."""
 		n0, n1, n2 = dataset_names
 		for pair in ((n0, n1), (n0, n2), (n1, n2)):
-			self.measure_covariance_multiple_datasets(corr_type=corr_type, dataset_names=list(pair), num_box=num_box)
-		f = open_file(self.output_file_name, "a")
+			self.measure_covariance_multiple_datasets(corr_type=corr_type, dataset_names=list(pair), num_box=num_box,
+													  _handle=_handle)
+		f = _handle if _handle is not None else open_file(self.output_file_name, "a")
 		try:
 			grp = f[f"{self.snap_group}/{corr_type}"]
 			cov_xx = grp[f"{n0}_jackknife_cov_{num_box}"][:]
@@ -91,5 +95,6 @@ class JackknifeCombinationMixin:
 			write_dataset_hdf5(grp, f"{n0}_{n2}_combined_jackknife_cov_{num_box}", data=cov2xz)
 			write_dataset_hdf5(grp, f"{n1}_{n2}_combined_jackknife_cov_{num_box}", data=cov2yz)
 		finally:
-			f.close()
+			if _handle is None:
+				f.close()
 		return None

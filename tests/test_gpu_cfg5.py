@@ -81,3 +81,51 @@ def test_cfg5_cross_weights_masks_three_projections(tmp_path, oracle):
 	pu.assert_datasets_match(got, combined, exact_counts=False, label="cfg5 combined covariance: ")
 	cov3 = got[f"w_g_plus/LOS_x_LOS_y_LOS_z_combined_jackknife_cov_{NUM_JK}"]
 	assert cov3.shape == (30, 30)
+
+
+def test_batched_projections_equal_separate_calls(tmp_path):
+	"""``measure_xi_projections``: one catalogue preparation for three projections x two statistics, one file
+	handle, the three-projection covariance at the end -- the file must hold what the reference's workflow (one run per
+	projection and statistic with that projection's shapes, then ``create_full_cov_matrix_projections``) writes."""
+	import torch
+	if not torch.cuda.is_available():
+		pytest.skip("GPU tests need a CUDA device")
+	from measure_ia_b200 import MeasureIABox
+	from measure_ia_b200.synthetic import uniform_box
+	n_pos, n_shape = 60_000, 25_000
+	data = uniform_box(n_pos, L, seed=707, n_shape=n_shape, weights=True)
+	rng = np.random.default_rng(708)
+	proj = []
+	for los in range(3):  # projected shapes differ from one line of sight to the next
+		th = np.pi * rng.random(n_shape)
+		proj.append({"LOS": los, "Axis_Direction": np.stack([np.cos(th), np.sin(th)], 1) * rng.uniform(0.5, 2.0, n_shape)[:, None],
+					 "q": rng.uniform(0.2, 1.0, n_shape)})
+	masks = {"Position": rng.random(n_pos) < 0.7, "Position_shape_sample": rng.random(n_shape) < 0.6}
+	masks["Axis_Direction"] = masks["q"] = masks["weight_shape_sample"] = masks["Position_shape_sample"]
+	masks["weight"] = masks["Position"]
+	kw = dict(boxsize=L, num_bins_r=10, num_bins_pi=8)
+
+	sep = str(tmp_path / "separate.hdf5")
+	counts = {}
+	for name, p in zip(NAMES, proj):
+		d = dict(data)
+		d.update(p)
+		box = MeasureIABox(d, sep, **kw)
+		for kind, run in (("w", box.measure_xi_w), ("multipoles", box.measure_xi_multipoles)):
+			run(name, "both", num_jk=NUM_JK, temp_file_path=False, masks=dict(masks))
+			counts[(name, kind)] = (box.last_result["count"].copy(), box.last_result["count_jk"].copy())
+	for corr in ("w_g_plus", "w_gg", "multipoles_g_plus", "multipoles_gg"):
+		box.create_full_cov_matrix_projections(corr, NAMES, num_box=NUM_JK)
+
+	bat = str(tmp_path / "batched.hdf5")
+	d = dict(data)
+	d["LOS"] = 2  # not used: every projection names its own line of sight
+	box = MeasureIABox(d, bat, **kw)
+	box.measure_xi_projections(NAMES, "both", num_jk=NUM_JK, temp_file_path=False, masks=dict(masks), projections=proj)
+	assert set(box.last_results) == set(counts)
+	for key, (c, cjk) in counts.items():
+		assert np.array_equal(box.last_results[key]["count"], c) and np.array_equal(box.last_results[key]["count_jk"], cjk), key
+		assert box.last_stats["per_measurement"][key]["kernel"] == 2
+	got, want = _read_all(bat), _read_all(sep)
+	assert set(got) == set(want)
+	pu.assert_datasets_match(got, want, exact_counts=False, label="batched projections: ")

@@ -14,8 +14,9 @@ from measure_ia_b200 import MeasureIABox, SimInfo, h5lite
 from measure_ia_b200.box import integer_cube_root
 
 
-def oracle_pair_sums(oracle):
-	"""A stand-in for MeasureIABox._pair_sums that gets the five accumulators from the CPU oracle."""
+def oracle_pair_sums(oracle, n_threads=4):
+	"""A stand-in for MeasureIABox._pair_sums that gets the five accumulators from the CPU oracle (n_threads=1: sums in a
+	fixed order, bit-reproducible from call to call)."""
 	def _pair_sums(self, geom, masks, L_subboxes, ellipticity, rp_cut=None, variance=False):
 		pos, pos_s, axis, e, w, w_s, same = self._prepare(masks, ellipticity)
 		num_box = L_subboxes ** 3 if L_subboxes else 0
@@ -26,7 +27,7 @@ def oracle_pair_sums(oracle):
 		R, R_jk = self._responsivity(w_s, e, jk_s, num_box)
 		bins2 = self.pi_bins if geom == "rppi" else self.mu_r_bins
 		r = oracle.paircount(geom, pos, w, jk_p, pos_s, axis, e, w_s, jk_s, self.r_bins, (self.r_min, self.r_max), bins2,
-							 self.boxsize, self.periodicity, int(self.data["LOS"]), 1.0, num_box=num_box, n_threads=4)
+							 self.boxsize, self.periodicity, int(self.data["LOS"]), 1.0, num_box=num_box, n_threads=n_threads)
 		self.last_stats = dict(rank=0)
 		return dict(count=r["count"], DD=r["DD"], SpD_raw=r["SpD"], ScD_raw=r["ScD"], count_jk=None, DD_jk=r["DD_jk"],
 					SpD_jk=r["SpD_jk"], var_raw=r["var"] if variance else None, R=R, R_jk=R_jk, jk_p=jk_p, jk_s=jk_s,
