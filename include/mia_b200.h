@@ -44,7 +44,8 @@ enum {
 	MIA_ERR_WORKSPACE = -2, /* workspace too small: call mia_workspace_bytes */
 	MIA_ERR_RANGE = -3,     /* a coordinate is outside [0, boxsize) (the reference's KDTree raises here too) */
 	MIA_ERR_WINDOW = -4,    /* internal consistency check of the tiled kernel failed (a pair fell outside its window) */
-	MIA_ERR_UNSUPPORTED = -5
+	MIA_ERR_UNSUPPORTED = -5,
+	MIA_ERR_UNSORTED = -6   /* light-cone entry: a sample is not sorted by comoving distance (or holds a NaN distance) */
 };
 
 /* Binning and geometry.  Threshold tables are HOST pointers, copied during the call. */
@@ -131,6 +132,57 @@ int mia_paircount_host(const mia_params *params, const mia_sample *position_host
  * measure_w_box_jk.py:775-780; used after an all-gather so the fp64 sums do not depend on arrival order).
  * parts is [n_parts][n_values] row-major, out is [n_values]: out[i] = ((parts[0][i] + parts[1][i]) + ...). */
 int mia_combine_partials_f64(const double *parts, int32_t n_parts, int64_t n_values, double *out, void *stream);
+
+/* ---- light-cone brute pair loops (additive to ABI v3) ---------------------------------------------------
+ *
+ * Replaces the O(N_p N_s) loops over position galaxies of the reference's light-cone estimators:
+ *     src/measureia/measure_w_lightcone.py:137-183   _measure_xi_rp_pi_lightcone_brute     -> MIA_GEOM_RPPI, shapes = 1
+ *     src/measureia/measure_w_lightcone.py:307-334   _count_pairs_xi_rp_pi_lightcone_brute -> MIA_GEOM_RPPI, shapes = 0
+ *     src/measureia/measure_m_lightcone.py:142-191   _measure_xi_r_mur_lightcone_brute     -> MIA_GEOM_RMU,  shapes = 1
+ *     src/measureia/measure_m_lightcone.py:300-330   _count_pairs_xi_r_mur_lightcone_brute -> MIA_GEOM_RMU,  shapes = 0
+ * and, through num_patches, the leave-one-patch-out re-runs of measure_jackknife.py:116-170 in the same pass.
+ * The flat-sky separation of a pair is formed at the POSITION galaxy's distance (see mia_lightcone.cuh for the operation
+ * sequence); distances (pyccl in the reference) and the per-galaxy trigonometry are the caller's, so that they are the
+ * caller's numpy bit for bit. */
+typedef struct mia_lc_params {
+	int32_t abi_version; /* MIA_ABI_VERSION */
+	int32_t geometry;    /* MIA_GEOM_RPPI / MIA_GEOM_RMU */
+	int32_t n_r;
+	int32_t n_2;
+	int32_t num_patches; /* jackknife patches (labels 0..num_patches-1 come with the samples), 0 = none */
+	int32_t shapes;      /* 1: also sum w w e_+ and w w e_x (the `_measure_xi_*` loops); 0: pair counts only (`_count_pairs_*`) */
+	double proj_scale;   /* factor applied to the PROJECTED separation (dx, dy) only: h with over_h, else 1
+	                        (measure_w_lightcone.py:145-146; the distances themselves arrive already scaled, :131-133) */
+	double rp2_cut;      /* MIA_GEOM_RMU: a pair needs r_p^2 > rp2_cut (measure_m_lightcone.py:172) */
+	const double *r2_thr_host; /* as in mia_params */
+	const double *thr2_host;
+	float *timings_host; /* optional HOST pointer to 2 floats: [0] pair kernel ms, [1] whole call ms */
+} mia_lc_params;
+
+/* One light-cone catalogue, SORTED BY chi ASCENDING (MIA_ERR_UNSORTED otherwise).  All arrays have n entries. */
+typedef struct mia_lc_sample {
+	int64_t n;
+	const double *ra;     /* degrees */
+	const double *dec;    /* degrees */
+	const double *chi;    /* comoving radial distance of the redshift (times h with over_h) */
+	const double *cosdec; /* position sample: cos(dec / 180 * pi) as the caller computes it; NULL for the shape sample */
+	const double *weight; /* NULL = unit weights */
+	const double *e1;     /* shape sample with shapes = 1: e cos(2 phi_axis) */
+	const double *e2;     /*                               e sin(2 phi_axis) */
+	const int32_t *patch; /* jackknife patch label, NULL when num_patches == 0 */
+} mia_lc_sample;
+
+/* Results go to a mia_hist: dd_count / dd_w / spd / scd as for the box; dd_jk_count / dd_jk_w / spd_jk hold, per patch k,
+ * the sums over pairs with the position OR the shape galaxy in patch k (realisation k of the reference = total - [k]);
+ * stats[0] = separations computed, [1] = pairs binned, [4] = MIA_KERNEL_LIGHTCONE, [7] = kernels launched.  No workspace.
+ * `shard`: slice of the (sorted) position sample this call handles. */
+#define MIA_KERNEL_LIGHTCONE 5
+int mia_lightcone_paircount(const mia_lc_params *params, const mia_lc_sample *position, const mia_lc_sample *shape,
+							mia_shard shard, const mia_hist *out, void *stream);
+
+/* Same call with HOST buffers (allocates, copies, synchronises). */
+int mia_lightcone_paircount_host(const mia_lc_params *params, const mia_lc_sample *position_host,
+								 const mia_lc_sample *shape_host, mia_shard shard, const mia_hist *out_host, int device);
 
 #ifdef __cplusplus
 }

@@ -133,6 +133,17 @@ class MeasureIABase(SimInfo):
 			self._cap_grid = vol
 		return np.abs((n_pos - 1.0) * n_shape * self._cap_grid / volume)
 
+	def _thresholds_for(self, geom, rp_cut):
+		key = (geom, rp_cut)
+		if key not in self._thresholds:
+			_, r2_thr, clean = calib.r_thresholds(self.r_min, self.r_max, self.num_bins_r, self.r_bins)
+			if geom == "rppi":
+				thr2 = calib.pi_thresholds(self.pi_bins, self.num_bins_pi)
+			else:
+				thr2 = calib.mu_thresholds(self.mu_r_bins, self.num_bins_pi)
+			self._thresholds[key] = (r2_thr, thr2, calib.rp_cut_threshold(rp_cut), clean)
+		return self._thresholds[key]
+
 	# ---- jackknife regions ----------------------------------------------------------------------------------------------
 	def _jackknife_labels(self, positions, L_subboxes):
 		"""Label in [0, n^3) of the axis-aligned sub-box strictly containing each point; points on any sub-box face
@@ -345,17 +356,6 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 			for k in range(num_box):
 				R_jk[k] = np.delete(tk, k).sum() / np.delete(wk, k).sum()
 		return R, R_jk
-
-	def _thresholds_for(self, geom, rp_cut):
-		key = (geom, rp_cut)
-		if key not in self._thresholds:
-			_, r2_thr, clean = calib.r_thresholds(self.r_min, self.r_max, self.num_bins_r, self.r_bins)
-			if geom == "rppi":
-				thr2 = calib.pi_thresholds(self.pi_bins, self.num_bins_pi)
-			else:
-				thr2 = calib.mu_thresholds(self.mu_r_bins, self.num_bins_pi)
-			self._thresholds[key] = (r2_thr, thr2, calib.rp_cut_threshold(rp_cut), clean)
-		return self._thresholds[key]
 
 	def _device(self):
 		"""The CUDA device of this object's operator calls; raises when there is none (no CPU fallback)."""

@@ -1,0 +1,53 @@
+"""Comoving radial distances for the light-cone path (the reference calls ``pyccl.comoving_radial_distance``,
+measure_w_lightcone.py:128-130 with ``ccl.Cosmology(Omega_c=0.225, Omega_b=0.045, sigma8=0.8, h=0.7, n_s=1.0)`` as default).
+
+``pyccl`` (pinned ~=3.2 by the reference, uv.lock: 3.2.1) is absent from this image.  When it is importable and the caller
+passes one of its ``Cosmology`` objects it is used; otherwise distances come from the flat LCDM integral below (matter +
+cosmological constant, no radiation / neutrinos -- CCL's default adds those: a ~1e-4 relative difference at z < 1, so
+the DISTANCE conversion is not pinned against CCL; everything downstream of the distances is).
+Units: Mpc (not Mpc/h), like CCL.
+"""
+import numpy as np
+
+C_KM_S = 299792.458
+
+
+class Cosmology:
+	"""Minimal stand-in for ``pyccl.Cosmology``: keyword construction and ``cosmo["h"]`` item access."""
+
+	def __init__(self, Omega_c=0.225, Omega_b=0.045, sigma8=0.8, h=0.7, n_s=1.0, **extra):
+		self._p = dict(Omega_c=Omega_c, Omega_b=Omega_b, sigma8=sigma8, h=h, n_s=n_s, **extra)
+		self._p["Omega_m"] = Omega_c + Omega_b
+
+	def __getitem__(self, key):
+		return self._p[key]
+
+
+_GL_X, _GL_W = np.polynomial.legendre.leggauss(64)
+
+
+def flat_lcdm_distance(omega_m, h, a):
+	"""chi(a) = c / H0 int_0^z dz' / sqrt(Om (1 + z')^3 + 1 - Om), 64-point Gauss-Legendre per object (the integrand is
+	smooth: converged to rounding for z < 10)."""
+	a = np.asarray(a, dtype=np.float64)
+	z = 1.0 / a - 1.0
+	half = 0.5 * z
+	acc = np.zeros_like(z)
+	for x, w in zip(_GL_X, _GL_W):
+		zz = half * (x + 1.0)
+		acc += w / np.sqrt(omega_m * (1.0 + zz) ** 3 + (1.0 - omega_m))
+	return C_KM_S / (100.0 * h) * half * acc
+
+
+def comoving_radial_distance(cosmology, a):
+	"""Same call signature as ``pyccl.comoving_radial_distance(cosmology, a)``."""
+	try:  # pragma: no cover - pyccl is absent from the build image
+		import pyccl
+		if isinstance(cosmology, pyccl.Cosmology):
+			return pyccl.comoving_radial_distance(cosmology, a)
+	except Exception:  # noqa: BLE001
+		pass
+	if callable(cosmology):  # a user-supplied chi(a)
+		return np.asarray(cosmology(np.asarray(a, dtype=np.float64)), dtype=np.float64)
+	om = cosmology["Omega_c"] + cosmology["Omega_b"]
+	return flat_lcdm_distance(om, cosmology["h"], a)

@@ -7,6 +7,7 @@
 #include "mia_common.cuh"
 #include "mia_general.cuh"
 #include "mia_grid.cuh"
+#include "mia_lightcone.cuh"
 #include "mia_tiled.cuh"
 #include "mia_tiled_rmu.cuh"
 #include "mia_tiled_rppi2.cuh"
@@ -17,6 +18,19 @@ using namespace mia;
 namespace {
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// CUDA events destroyed on every exit path
+struct CudaEvents {
+	cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+	int create(int n) {
+		for (int i = 0; i < n && i < 4; i++) MIA_CUDA_CHECK(cudaEventCreate(&e[i]));
+		return 0;
+	}
+	~CudaEvents() {
+		for (int i = 0; i < 4; i++)
+			if (e[i]) cudaEventDestroy(e[i]);
+	}
+};
 
 constexpr int RED_GROUPS = 32;  // groups of accumulator copies summed in parallel (stage 1 of the final reduction)
 
@@ -291,6 +305,7 @@ const char *mia_strerror(int code) {
 		case MIA_ERR_RANGE: return "a coordinate lies outside [0, boxsize)";
 		case MIA_ERR_WINDOW: return "tiled kernel: a pair fell outside its accumulation window (internal error)";
 		case MIA_ERR_UNSUPPORTED: return "configuration not supported by the requested kernel";
+		case MIA_ERR_UNSORTED: return "light-cone samples must be sorted by comoving distance (ascending, no NaN)";
 		default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
 	}
 }
@@ -600,6 +615,218 @@ int mia_combine_partials_f64(const double *parts, int32_t n_parts, int64_t n_val
 	k_combine<<<(unsigned)((n_values + 255) / 256), 256, 0, (cudaStream_t)stream>>>(parts, n_parts, n_values, out);
 	MIA_CUDA_CHECK(cudaGetLastError());
 	return MIA_OK;
+}
+
+// ---- light-cone brute pair loops (mia_lightcone.cuh) -------------------------------------------------------------------
+static int lc_validate(const mia_lc_params *p, const mia_lc_sample *D, const mia_lc_sample *S, const mia_hist *out) {
+	if (!p || p->abi_version != MIA_ABI_VERSION || !D || !S || !out) return MIA_ERR_ARG;
+	if (p->n_r < 1 || p->n_r > MIA_MAX_BINS || p->n_2 < 1 || p->n_2 > MIA_MAX_BINS || p->num_patches < 0) return MIA_ERR_ARG;
+	if (p->geometry != MIA_GEOM_RPPI && p->geometry != MIA_GEOM_RMU) return MIA_ERR_ARG;
+	if (!p->r2_thr_host || !p->thr2_host || !(p->proj_scale > 0.0)) return MIA_ERR_ARG;
+	if (D->n < 0 || S->n < 0 || D->n >= (1ll << 31) || S->n >= (1ll << 31)) return MIA_ERR_ARG;
+	if (D->n > 0 && (!D->ra || !D->dec || !D->chi || !D->cosdec)) return MIA_ERR_ARG;
+	if (S->n > 0 && (!S->ra || !S->dec || !S->chi)) return MIA_ERR_ARG;
+	if (p->shapes && S->n > 0 && (!S->e1 || !S->e2)) return MIA_ERR_ARG;
+	if (p->num_patches > 0 && ((D->n > 0 && !D->patch) || (S->n > 0 && !S->patch))) return MIA_ERR_ARG;
+	if (!out->dd_count || !out->dd_w || !out->spd || !out->scd || !out->stats) return MIA_ERR_ARG;
+	if (p->num_patches > 0 && (!out->dd_jk_count || !out->dd_jk_w || !out->spd_jk)) return MIA_ERR_ARG;
+	return MIA_OK;
+}
+
+int mia_lightcone_paircount(const mia_lc_params *p, const mia_lc_sample *D, const mia_lc_sample *S, mia_shard shard,
+							const mia_hist *out, void *stream) {
+	int rc = lc_validate(p, D, S, out);
+	if (rc != MIA_OK) return rc;
+	if (shard.count < 1 || shard.index < 0 || shard.index >= shard.count) return MIA_ERR_ARG;
+	cudaStream_t st = (cudaStream_t)stream;
+	const int nb = p->n_r * p->n_2;
+	const size_t K = (size_t)p->num_patches;
+	LcDev P;
+	memset(&P, 0, sizeof(P));
+	P.geom = p->geometry;
+	P.n_r = p->n_r;
+	P.n_2 = p->n_2;
+	P.num_patches = p->num_patches;
+	P.shapes = p->shapes ? 1 : 0;
+	P.proj_scale = p->proj_scale;
+	P.scaled = (p->proj_scale != 1.0) ? 1 : 0;
+	P.rp2_cut = p->rp2_cut;
+	for (int b = 0; b <= p->n_r; b++) P.r2_thr[b] = p->r2_thr_host[b];
+	for (int b = 0; b <= p->n_2; b++) P.thr2[b] = p->thr2_host[b];
+	if (p->geometry == MIA_GEOM_RPPI) {
+		P.win_lo = P.thr2[0];
+		P.win_hi = P.thr2[p->n_2];
+	} else {  // Pi^2 <= r^2 < r2_thr[n_r]
+		const double rmax = sqrt(P.r2_thr[p->n_r]) * (1.0 + 1e-12);
+		P.win_lo = -rmax;
+		P.win_hi = rmax;
+	}
+	CudaEvents ev;
+	const bool timed = p->timings_host != nullptr;
+	if (timed) {
+		rc = ev.create(4);
+		if (rc) return rc;
+		MIA_CUDA_CHECK(cudaEventRecord(ev.e[0], st));
+	}
+	MIA_CUDA_CHECK(cudaMemsetAsync(out->dd_count, 0, sizeof(int64_t) * nb, st));
+	MIA_CUDA_CHECK(cudaMemsetAsync(out->dd_w, 0, sizeof(double) * nb, st));
+	MIA_CUDA_CHECK(cudaMemsetAsync(out->spd, 0, sizeof(double) * nb, st));
+	MIA_CUDA_CHECK(cudaMemsetAsync(out->scd, 0, sizeof(double) * nb, st));
+	if (K) {
+		MIA_CUDA_CHECK(cudaMemsetAsync(out->dd_jk_count, 0, sizeof(int64_t) * K * nb, st));
+		MIA_CUDA_CHECK(cudaMemsetAsync(out->dd_jk_w, 0, sizeof(double) * K * nb, st));
+		MIA_CUDA_CHECK(cudaMemsetAsync(out->spd_jk, 0, sizeof(double) * K * nb, st));
+	}
+	MIA_CUDA_CHECK(cudaMemsetAsync(out->stats, 0, sizeof(uint64_t) * 8, st));
+	unsigned long long n_launch = 0;
+	int *flag = reinterpret_cast<int *>(out->stats + 3);  // sortedness flag (stats[3], zeroed above)
+	if (D->n > 0) {
+		k_lc_check_sorted<<<(unsigned)((D->n + 255) / 256), 256, 0, st>>>(D->chi, D->n, flag);
+		n_launch++;
+	}
+	if (S->n > 0) {
+		k_lc_check_sorted<<<(unsigned)((S->n + 255) / 256), 256, 0, st>>>(S->chi, S->n, flag);
+		n_launch++;
+	}
+	MIA_CUDA_CHECK(cudaGetLastError());
+	int h_flag = 0;
+	MIA_CUDA_CHECK(cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+	MIA_CUDA_CHECK(cudaStreamSynchronize(st));  // a wrong answer must never be returned silently
+	if (h_flag) return MIA_ERR_UNSORTED;
+
+	const int64_t p_begin = D->n * shard.index / shard.count, p_end = D->n * (shard.index + 1) / shard.count;
+	if (timed) MIA_CUDA_CHECK(cudaEventRecord(ev.e[1], st));
+	if (p_end > p_begin && S->n > 0) {
+		LcSampleDev Dd = {D->n, D->ra, D->dec, D->chi, D->cosdec, D->weight, nullptr, nullptr, D->patch};
+		LcSampleDev Sd = {S->n, S->ra, S->dec, S->chi, nullptr, S->weight, S->e1, S->e2, S->patch};
+		LcOut O = {(unsigned long long *)out->dd_count, out->dd_w, out->spd, out->scd, (unsigned long long *)out->dd_jk_count,
+				   out->dd_jk_w, out->spd_jk, (unsigned long long *)out->stats};
+		const unsigned gx = (unsigned)((p_end - p_begin + LC_TP - 1) / LC_TP);
+		int dev = 0, sms = 148;
+		if (cudaGetDevice(&dev) == cudaSuccess) {
+			int v = 0;
+			if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+		}
+		// segments of the chi window per position block: enough CTAs to fill the GPU a few times over
+		long long n_seg = (8ll * sms + gx - 1) / gx;
+		const long long max_tiles = (S->n + LC_TILE - 1) / LC_TILE;
+		if (n_seg > max_tiles) n_seg = max_tiles;
+		if (n_seg > 1024) n_seg = 1024;
+		if (n_seg < 1) n_seg = 1;
+		const size_t smem = lightcone_smem_bytes(nb);
+		const dim3 grid(gx, (unsigned)n_seg);
+#define LC_LAUNCH(G, SH)                                                                                                       \
+	do {                                                                                                                       \
+		MIA_CUDA_CHECK(cudaFuncSetAttribute(k_lightcone<G, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+		k_lightcone<G, SH><<<grid, LC_TP, smem, st>>>(P, Dd, Sd, p_begin, p_end, (int)n_seg, O);                               \
+	} while (0)
+		if (p->geometry == MIA_GEOM_RPPI) {
+			if (p->shapes) LC_LAUNCH(MIA_GEOM_RPPI, true);
+			else LC_LAUNCH(MIA_GEOM_RPPI, false);
+		} else {
+			if (p->shapes) LC_LAUNCH(MIA_GEOM_RMU, true);
+			else LC_LAUNCH(MIA_GEOM_RMU, false);
+		}
+#undef LC_LAUNCH
+		MIA_CUDA_CHECK(cudaGetLastError());
+		n_launch++;
+	}
+	if (timed) MIA_CUDA_CHECK(cudaEventRecord(ev.e[2], st));
+	const unsigned long long tail[2] = {(unsigned long long)MIA_KERNEL_LIGHTCONE, n_launch};
+	MIA_CUDA_CHECK(cudaMemcpyAsync(out->stats + 4, &tail[0], sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+	MIA_CUDA_CHECK(cudaMemcpyAsync(out->stats + 7, &tail[1], sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+	if (timed) MIA_CUDA_CHECK(cudaEventRecord(ev.e[3], st));
+	MIA_CUDA_CHECK(cudaStreamSynchronize(st));
+	if (timed) {
+		float a = 0.f, b = 0.f;
+		MIA_CUDA_CHECK(cudaEventElapsedTime(&a, ev.e[1], ev.e[2]));
+		MIA_CUDA_CHECK(cudaEventElapsedTime(&b, ev.e[0], ev.e[3]));
+		p->timings_host[0] = a;
+		p->timings_host[1] = b;
+	}
+	return MIA_OK;
+}
+
+int mia_lightcone_paircount_host(const mia_lc_params *p, const mia_lc_sample *Dh, const mia_lc_sample *Sh, mia_shard shard,
+								 const mia_hist *out_h, int device) {
+	int rc = lc_validate(p, Dh, Sh, out_h);
+	if (rc != MIA_OK) return rc;
+	MIA_CUDA_CHECK(cudaSetDevice(device));
+	const int nb = p->n_r * p->n_2;
+	const size_t K = (size_t)p->num_patches;
+	size_t o = 0;
+	auto take = [&](size_t bytes) {
+		size_t at = o;
+		o = align_up(o + bytes);
+		return at;
+	};
+	// inputs: up to 8 arrays per sample, then the outputs
+	const double *srcD[7] = {Dh->ra, Dh->dec, Dh->chi, Dh->cosdec, Dh->weight, nullptr, nullptr};
+	const double *srcS[7] = {Sh->ra, Sh->dec, Sh->chi, nullptr, Sh->weight, p->shapes ? Sh->e1 : nullptr, p->shapes ? Sh->e2 : nullptr};
+	size_t offD[7], offS[7];
+	for (int i = 0; i < 7; i++) offD[i] = take(srcD[i] ? sizeof(double) * Dh->n : 0);
+	for (int i = 0; i < 7; i++) offS[i] = take(srcS[i] ? sizeof(double) * Sh->n : 0);
+	const size_t o_pd = take(Dh->patch ? sizeof(int32_t) * Dh->n : 0), o_ps = take(Sh->patch ? sizeof(int32_t) * Sh->n : 0);
+	const size_t o_cnt = take(sizeof(int64_t) * nb), o_ddw = take(sizeof(double) * nb), o_sp = take(sizeof(double) * nb),
+				 o_sc = take(sizeof(double) * nb);
+	const size_t o_jcnt = take(sizeof(int64_t) * K * nb), o_jddw = take(sizeof(double) * K * nb), o_jsp = take(sizeof(double) * K * nb);
+	const size_t o_stats = take(sizeof(uint64_t) * 8);
+	unsigned char *d = nullptr;
+	MIA_CUDA_CHECK(cudaMalloc(&d, o + 256));
+	cudaStream_t st;
+	cudaError_t ce = cudaStreamCreate(&st);
+	if (ce != cudaSuccess) {
+		cudaFree(d);
+		return (int)ce;
+	}
+	auto h2d = [&](size_t off, const void *src, size_t bytes) {
+		if (src && bytes > 0 && rc == MIA_OK) {
+			cudaError_t e_ = cudaMemcpyAsync(d + off, src, bytes, cudaMemcpyHostToDevice, st);
+			if (e_ != cudaSuccess) rc = (int)e_;
+		}
+	};
+	for (int i = 0; i < 7; i++) h2d(offD[i], srcD[i], sizeof(double) * Dh->n);
+	for (int i = 0; i < 7; i++) h2d(offS[i], srcS[i], sizeof(double) * Sh->n);
+	h2d(o_pd, Dh->patch, sizeof(int32_t) * Dh->n);
+	h2d(o_ps, Sh->patch, sizeof(int32_t) * Sh->n);
+	if (rc == MIA_OK) {
+		auto dp = [&](const double *src, size_t off) { return src ? (const double *)(d + off) : (const double *)nullptr; };
+		mia_lc_sample Dd = {Dh->n, dp(srcD[0], offD[0]), dp(srcD[1], offD[1]), dp(srcD[2], offD[2]), dp(srcD[3], offD[3]),
+							dp(srcD[4], offD[4]), nullptr, nullptr, Dh->patch ? (const int32_t *)(d + o_pd) : nullptr};
+		mia_lc_sample Sd = {Sh->n, dp(srcS[0], offS[0]), dp(srcS[1], offS[1]), dp(srcS[2], offS[2]), nullptr,
+							dp(srcS[4], offS[4]), dp(srcS[5], offS[5]), dp(srcS[6], offS[6]),
+							Sh->patch ? (const int32_t *)(d + o_ps) : nullptr};
+		mia_hist od;
+		memset(&od, 0, sizeof(od));
+		od.dd_count = (int64_t *)(d + o_cnt);
+		od.dd_w = (double *)(d + o_ddw);
+		od.spd = (double *)(d + o_sp);
+		od.scd = (double *)(d + o_sc);
+		od.dd_jk_count = K ? (int64_t *)(d + o_jcnt) : nullptr;
+		od.dd_jk_w = K ? (double *)(d + o_jddw) : nullptr;
+		od.spd_jk = K ? (double *)(d + o_jsp) : nullptr;
+		od.stats = (uint64_t *)(d + o_stats);
+		rc = mia_lightcone_paircount(p, &Dd, &Sd, shard, &od, (void *)st);
+	}
+	auto d2h = [&](void *dst, size_t off, size_t bytes) {
+		if (dst && bytes > 0 && rc == MIA_OK) {
+			cudaError_t e_ = cudaMemcpyAsync(dst, d + off, bytes, cudaMemcpyDeviceToHost, st);
+			if (e_ != cudaSuccess) rc = (int)e_;
+		}
+	};
+	d2h(out_h->dd_count, o_cnt, sizeof(int64_t) * nb);
+	d2h(out_h->dd_w, o_ddw, sizeof(double) * nb);
+	d2h(out_h->spd, o_sp, sizeof(double) * nb);
+	d2h(out_h->scd, o_sc, sizeof(double) * nb);
+	d2h(out_h->dd_jk_count, o_jcnt, sizeof(int64_t) * K * nb);
+	d2h(out_h->dd_jk_w, o_jddw, sizeof(double) * K * nb);
+	d2h(out_h->spd_jk, o_jsp, sizeof(double) * K * nb);
+	d2h(out_h->stats, o_stats, sizeof(uint64_t) * 8);
+	cudaError_t se = cudaStreamSynchronize(st);
+	if (rc == MIA_OK && se != cudaSuccess) rc = (int)se;
+	cudaStreamDestroy(st);
+	cudaFree(d);
+	return rc;
 }
 
 }  // extern "C"

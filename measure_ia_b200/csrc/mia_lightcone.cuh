@@ -1,0 +1,232 @@
+// mia_lightcone.cuh -- brute pair loops of the LIGHT-CONE estimators for sm_100a.
+//
+// Reference: src/measureia/measure_w_lightcone.py:137-183 (_measure_xi_rp_pi_lightcone_brute), :307-334
+// (_count_pairs_xi_rp_pi_lightcone_brute), measure_m_lightcone.py:142-191 / :300-330 (the (r, mu_r) twins).  For every
+// POSITION galaxy n the reference forms, against the whole shape sample,
+//     Pi  = chi_s - chi_n
+//     dx  = ((ra_s - ra_n) / 180 * pi) * chi_n * cos(dec_n / 180 * pi),   dy = ((dec_s - dec_n) / 180 * pi) * chi_n
+//     (over_h: dx, dy *= h -- the projected pair only; the 3-D separation of the (r, mu_r) variant keeps the unscaled dx, dy)
+//     r_p = sqrt(dx^2 + dy^2),  r = sqrt((dx^2 + dy^2) + Pi^2),  mu_r = Pi / r
+//     e_+ = -e cos 2(phi_axis - phi_sep),  e_x = -e sin 2(phi_axis - phi_sep),  phi_sep = arctan2(dy / r_p, dx / r_p)
+// bins (r_p, Pi) or (r, mu_r) with the floor-log formula and accumulates w_n w_s {1, e_+, e_x}.  No neighbour search, no
+// periodic wrap: O(N_p N_s).
+//
+// Here: both samples arrive sorted by chi (the host mirror sorts; the library checks).  A CTA owns 128 consecutive position
+// galaxies (one per thread) and a segment of the shape sample's chi WINDOW that can reach them (Pi range of the binning,
+// or +-r_max): the only cull, exact because every pair inside the window is still tested with the reference's own
+// comparisons.  Shape galaxies are staged through shared memory in tiles.  Everything that decides a bin uses the
+// reference's IEEE operation sequence (__d*_rn, no contraction) against the calibrated thresholds,
+// so pair counts are bit-exact.  The shape projection needs no transcendental call per pair:
+//     cos 2 phi_sep = (dx^2 - dy^2) / r_p^2,  sin 2 phi_sep = 2 dx dy / r_p^2,
+//     e_+ = -(E1 cos 2phi_sep + E2 sin 2phi_sep),  e_x = -(E2 cos 2phi_sep - E1 sin 2phi_sep),
+// with E1 = e cos 2phi_axis, E2 = e sin 2phi_axis prepared per shape galaxy by the caller (numpy, the reference's own chain
+// theta -> axis -> phi_axis).  Sums go to a per-CTA shared-memory histogram (atomics; binned pairs are a small share of
+// the tested ones) and from there to the global result: exact to rounding, not bit-reproducible run to run (like the
+// general box kernel); counts are integers and always exact.
+//
+// Jackknife patches: T[k] = sum over pairs with the position OR the shape galaxy in patch k, so the reference's
+// realisation k (both samples without patch k, measure_jackknife.py:116-134) is total - T[k].
+#pragma once
+#include "mia_common.cuh"
+
+namespace mia {
+
+constexpr int LC_TP = 128;    // threads per CTA = position galaxies per CTA
+constexpr int LC_TILE = 128;  // shape galaxies per staged tile
+
+struct LcDev {
+	int geom, n_r, n_2, num_patches, shapes, scaled;
+	double proj_scale, rp2_cut;
+	double r2_thr[MIA_MAX_BINS + 1];
+	double thr2[MIA_MAX_BINS + 1];
+	double win_lo, win_hi;  // chi_s - chi_n outside [win_lo, win_hi] can never be binned
+};
+
+struct LcSampleDev {
+	int64_t n;
+	const double *ra, *dec, *chi, *cosdec, *w, *e1, *e2;
+	const int32_t *patch;
+};
+
+struct LcOut {
+	unsigned long long *cnt;  // [nb]
+	double *ddw, *sp, *sc;    // [nb]
+	unsigned long long *jcnt; // [num_patches][nb]
+	double *jddw, *jsp;       // [num_patches][nb]
+	unsigned long long *stats;
+};
+
+__global__ void k_lc_check_sorted(const double *__restrict__ chi, int64_t n, int *__restrict__ flag) {
+	const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+	if (i + 1 < n && !(chi[i] <= chi[i + 1])) atomicExch(flag, 1);  // also catches NaN
+	if (i < n && !(chi[i] == chi[i])) atomicExch(flag, 1);
+}
+
+template <int GEOM, bool SHAPES>
+__global__ void __launch_bounds__(LC_TP) k_lightcone(const LcDev P, const LcSampleDev D, const LcSampleDev S, int64_t p_begin,
+													 int64_t p_end, int n_seg, LcOut O) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int nb = P.n_r * P.n_2;
+	double *t_ra = reinterpret_cast<double *>(smem_raw);
+	double *t_dec = t_ra + LC_TILE, *t_chi = t_dec + LC_TILE, *t_w = t_chi + LC_TILE, *t_e1 = t_w + LC_TILE, *t_e2 = t_e1 + LC_TILE;
+	double *s_ddw = t_e2 + LC_TILE, *s_sp = s_ddw + nb, *s_sc = s_sp + nb;
+	unsigned int *s_cnt = reinterpret_cast<unsigned int *>(s_sc + nb);
+	int *t_patch = reinterpret_cast<int *>(s_cnt + nb);
+	__shared__ long long win[2];
+
+	for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+		s_ddw[b] = 0.0;
+		s_sp[b] = 0.0;
+		s_sc[b] = 0.0;
+		s_cnt[b] = 0u;
+	}
+	const int64_t blk0 = p_begin + (int64_t)blockIdx.x * LC_TP;
+	const int64_t blk1 = (blk0 + LC_TP < p_end) ? blk0 + LC_TP : p_end;
+	if (threadIdx.x == 0) {
+		// shape galaxies that can reach this block: chi_s in [chi(first) + win_lo, chi(last) + win_hi] (positions ascend in chi),
+		// widened by a relative slack so that the rounding of the subtraction can never exclude a pair the exact test accepts
+		const double c0 = D.chi[blk0], c1 = D.chi[blk1 - 1];
+		const double lo = c0 + P.win_lo - 1e-9 * (fabs(c0) + fabs(P.win_lo)) - 1e-300;
+		const double hi = c1 + P.win_hi + 1e-9 * (fabs(c1) + fabs(P.win_hi)) + 1e-300;
+		long long a = 0, b = S.n;
+		if (lo == lo && lo > -INFINITY) {
+			while (a < b) {  // first index with chi_s >= lo
+				const long long m = (a + b) >> 1;
+				if (S.chi[m] >= lo) b = m;
+				else a = m + 1;
+			}
+		}
+		win[0] = a;
+		a = win[0];
+		b = S.n;
+		if (hi == hi && hi < INFINITY) {
+			while (a < b) {  // first index with chi_s > hi
+				const long long m = (a + b) >> 1;
+				if (S.chi[m] > hi) b = m;
+				else a = m + 1;
+			}
+			win[1] = a;
+		} else {
+			win[1] = S.n;
+		}
+	}
+	__syncthreads();
+	const long long w0 = win[0], w1 = win[1];
+
+	const int64_t n = blk0 + threadIdx.x;
+	const bool active = n < blk1;
+	double ra_n = 0.0, dec_n = 0.0, chi_n = 0.0, cd_n = 0.0, w_n = 0.0;
+	int patch_n = 0;
+	if (active) {
+		ra_n = D.ra[n];
+		dec_n = D.dec[n];
+		chi_n = D.chi[n];
+		cd_n = D.cosdec[n];
+		w_n = D.w ? D.w[n] : 1.0;
+		patch_n = D.patch ? D.patch[n] : 0;
+	}
+	unsigned long long tested = 0, binned = 0;
+	const long long n_tiles = (w1 - w0 + LC_TILE - 1) / LC_TILE;
+	for (long long t = blockIdx.y; t < n_tiles; t += n_seg) {
+		const long long j0 = w0 + t * LC_TILE;
+		const int cnt = (int)((w1 - j0 < LC_TILE) ? (w1 - j0) : LC_TILE);
+		__syncthreads();  // the previous tile has been consumed
+		if ((int)threadIdx.x < cnt) {
+			const long long j = j0 + threadIdx.x;
+			t_ra[threadIdx.x] = S.ra[j];
+			t_dec[threadIdx.x] = S.dec[j];
+			t_chi[threadIdx.x] = S.chi[j];
+			t_w[threadIdx.x] = S.w ? S.w[j] : 1.0;
+			if (SHAPES) {
+				t_e1[threadIdx.x] = S.e1[j];
+				t_e2[threadIdx.x] = S.e2[j];
+			}
+			t_patch[threadIdx.x] = S.patch ? S.patch[j] : 0;
+		}
+		__syncthreads();
+		if (!active) continue;
+		tested += (unsigned long long)cnt;
+		for (int k = 0; k < cnt; k++) {
+			const double los = __dsub_rn(t_chi[k], chi_n);  // measure_w_lightcone.py:139
+			if (GEOM == MIA_GEOM_RPPI) {
+				if (!(los >= P.thr2[0] && los < P.thr2[P.n_2])) continue;  // :160-161
+			}
+			const double dra = __dmul_rn(__ddiv_rn(__dsub_rn(t_ra[k], ra_n), 180.0), 3.141592653589793);   // :140
+			const double ddec = __dmul_rn(__ddiv_rn(__dsub_rn(t_dec[k], dec_n), 180.0), 3.141592653589793);  // :141
+			const double dx = __dmul_rn(__dmul_rn(dra, chi_n), cd_n);                                       // :142
+			const double dy = __dmul_rn(ddec, chi_n);                                                         // :143
+			const double px = P.scaled ? __dmul_rn(dx, P.proj_scale) : dx, py = P.scaled ? __dmul_rn(dy, P.proj_scale) : dy;  // :145-146
+			const double rp2 = __dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py));  // :147
+			double s;
+			int bin2;
+			if (GEOM == MIA_GEOM_RPPI) {
+				s = rp2;
+				if (!(s >= P.r2_thr[0] && s < P.r2_thr[P.n_r])) continue;
+				bin2 = count_thresholds(los, P.thr2, P.n_2);
+			} else {
+				if (!(rp2 > P.rp2_cut)) continue;  // measure_m_lightcone.py:172
+				// the 3-D separation keeps the UNSCALED dx, dy (:150 builds it before `projected_sep *= h`)
+				s = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(los, los));  // :154
+				if (!(s >= P.r2_thr[0] && s < P.r2_thr[P.n_r])) continue;
+				const double mu = __ddiv_rn(los, __dsqrt_rn(s));  // :157
+				bin2 = count_thresholds(mu, P.thr2, P.n_2);
+			}
+			const int b = count_thresholds(s, P.r2_thr, P.n_r) * P.n_2 + bin2;
+			binned++;
+			const double ww = w_n * t_w[k];
+			double tp = 0.0, tc = 0.0;
+			if (SHAPES) {
+				// rp2 == 0 cannot be binned ((r_p, Pi): r_p >= r_min > 0; (r, mu_r): r_p^2 > rp2_cut >= 0), so the reference's
+				// NaN -> 0 rule (:153-154) never fires on a binned pair
+				const double inv = 1.0 / rp2;
+				const double c2 = (px * px - py * py) * inv, s2 = 2.0 * px * py * inv;
+				tp = -ww * (t_e1[k] * c2 + t_e2[k] * s2);
+				tc = -ww * (t_e2[k] * c2 - t_e1[k] * s2);
+			}
+			atomicAdd(&s_cnt[b], 1u);
+			atomicAdd(&s_ddw[b], ww);
+			if (SHAPES) {
+				atomicAdd(&s_sp[b], tp);
+				atomicAdd(&s_sc[b], tc);
+			}
+			if (P.num_patches > 0) {
+				const int ps = t_patch[k];
+				size_t row = (size_t)ps * nb + b;
+				atomicAdd(&O.jcnt[row], 1ull);
+				atomicAdd(&O.jddw[row], ww);
+				if (SHAPES) atomicAdd(&O.jsp[row], tp);
+				if (patch_n != ps) {
+					row = (size_t)patch_n * nb + b;
+					atomicAdd(&O.jcnt[row], 1ull);
+					atomicAdd(&O.jddw[row], ww);
+					if (SHAPES) atomicAdd(&O.jsp[row], tp);
+				}
+			}
+		}
+	}
+	__syncthreads();
+	for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+		if (s_cnt[b]) {
+			atomicAdd(&O.cnt[b], (unsigned long long)s_cnt[b]);
+			atomicAdd(&O.ddw[b], s_ddw[b]);
+			if (SHAPES) {
+				atomicAdd(&O.sp[b], s_sp[b]);
+				atomicAdd(&O.sc[b], s_sc[b]);
+			}
+		}
+	}
+	for (int o = 16; o > 0; o >>= 1) {
+		tested += __shfl_down_sync(0xffffffffu, tested, o);
+		binned += __shfl_down_sync(0xffffffffu, binned, o);
+	}
+	if ((threadIdx.x & 31) == 0) {
+		atomicAdd(&O.stats[0], tested);
+		atomicAdd(&O.stats[1], binned);
+	}
+}
+
+inline size_t lightcone_smem_bytes(int nb) {
+	return sizeof(double) * 6 * LC_TILE + (size_t)nb * (3 * sizeof(double) + sizeof(unsigned int)) + sizeof(int) * LC_TILE;
+}
+
+}  // namespace mia

@@ -1,0 +1,346 @@
+"""Host-side mirror of the reference's LIGHT-CONE API on top of the B200 brute pair-loop operator.
+
+``MeasureIALightcone`` keeps the constructor, the ``measure_xi_w`` / ``measure_xi_multipoles`` signatures, the data dictionaries
+(``RA``, ``DEC``, ``Redshift``, ``e1``, ``e2``, weights; randoms), the estimators and the HDF5 layout of the reference
+(``src/measureia/measure_IA.py:265-1058``, ``measure_w_lightcone.py``, ``measure_m_lightcone.py``,
+``measure_IA_base.py:670-742``).  The four O(N_p N_s) Python loops over position galaxies
+(``_measure_xi_rp_pi_lightcone_brute``, ``_count_pairs_xi_rp_pi_lightcone_brute`` and their (r, mu_r) twins) are ONE operator,
+``ops.lightcone_paircount`` (CUDA, sm_100a; no CPU fallback).
+
+Not built: the jackknife covariance of the light-cone estimators (``measure_cov`` / ``calc_errors``: k-means sky patches via
+``kmeans_radec`` and the leave-one-patch-out re-runs of measure_jackknife.py:59-483).  The operator already returns, per
+patch, the sums over pairs touching it (``num_patches``; realisation k = total - touch[k]); the host layout of the
+realisations is not mirrored, and asking for it raises ``NotImplementedError``.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import cosmo
+from .box import MeasureIABase
+from .io import create_group_hdf5, open_file, write_dataset_hdf5
+from .jackknife import JackknifeCombinationMixin
+
+
+class MeasureIALightcone(MeasureIABase, JackknifeCombinationMixin):
+	"""Drop-in for ``measureia.MeasureIALightcone`` (measure_IA.py:265-1058) without the jackknife covariance."""
+
+	def __init__(self, data, randoms_data, output_file_name, separation_limits=[0.1, 20.0], num_bins_r=8, num_bins_pi=20,
+				 pi_max=None, num_nodes=1):
+		super().__init__(data, output_file_name, False, None, separation_limits, num_bins_r, num_bins_pi, pi_max, None, False)
+		self.num_nodes = num_nodes  # accepted for compatibility
+		self.randoms_data = randoms_data
+		self.data_dir = None
+		self.num_samples = None
+		self.device = None
+		self.last_stats = None
+
+	# ---- the pair loop ---------------------------------------------------------------------------------------------------
+	def _device(self):
+		import torch
+		if not torch.cuda.is_available():
+			raise RuntimeError("measure_ia_b200 needs a CUDA device: the light-cone pair operator has no CPU fallback")
+		return torch.device(self.device) if self.device is not None else torch.device("cuda", torch.cuda.current_device())
+
+	def _select(self, masks, shapes):
+		"""The reference's input selection (measure_w_lightcone.py:80-112): arrays of ``self.data``, masked key by key; missing
+		weight masks become all-True masks stored in the caller's dict."""
+		d = self.data
+		keys = ["Redshift", "Redshift_shape_sample", "RA", "RA_shape_sample", "DEC", "DEC_shape_sample"] + (["e1", "e2"] if shapes else [])
+		if masks is None:
+			out = {k: d[k] for k in keys}
+			out["weight"], out["weight_shape_sample"] = d["weight"], d["weight_shape_sample"]
+			return out
+		out = {k: d[k][masks[k]] for k in keys}
+		if "weight" not in masks:
+			masks["weight"] = np.ones(self.Num_position, dtype=bool)
+		if "weight_shape_sample" not in masks:
+			masks["weight_shape_sample"] = np.ones(self.Num_shape, dtype=bool)
+		out["weight"] = d["weight"][masks["weight"]]
+		out["weight_shape_sample"] = d["weight_shape_sample"][masks["weight_shape_sample"]]
+		return out
+
+	def _pair_sums(self, geom, shapes, masks, over_h, cosmology, rp_cut=None, patches=None):
+		"""Per-galaxy preparation on the host with the reference's numpy expressions (distances, cos(dec), shape angles:
+		O(N)), then ONE operator call for the O(N_p N_s) loop.  Returns dict(count, DD, SpD, ScD[, touch_*])."""
+		import torch
+
+		from . import ops
+		t0 = time.perf_counter()
+		dev = self._device()
+		sel = self._select(masks, shapes)
+		if cosmology is None:  # measure_w_lightcone.py:123-126
+			cosmology = cosmo.Cosmology(Omega_c=0.225, Omega_b=0.045, sigma8=0.8, h=0.7, n_s=1.0)
+		h = cosmology["h"]
+		f = lambda a: np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
+		chi_p = f(cosmo.comoving_radial_distance(cosmology, 1 / (1 + f(sel["Redshift"]))))
+		chi_s = f(cosmo.comoving_radial_distance(cosmology, 1 / (1 + f(sel["Redshift_shape_sample"]))))
+		if over_h:  # :131-133
+			chi_p, chi_s = chi_p * h, chi_s * h
+		pos = dict(ra=f(sel["RA"]), dec=f(sel["DEC"]), chi=chi_p, cosdec=np.cos(f(sel["DEC"]) / 180 * np.pi), weight=f(sel["weight"]))
+		shp = dict(ra=f(sel["RA_shape_sample"]), dec=f(sel["DEC_shape_sample"]), chi=chi_s, weight=f(sel["weight_shape_sample"]))
+		if shapes:  # :135-140; e cos 2phi_axis and e sin 2phi_axis are what the device needs
+			e1, e2 = f(sel["e1"]), f(sel["e2"])
+			theta = 1. / 2 * np.arctan2(e2, e1)
+			axis = np.array([np.cos(theta), np.sin(theta)])
+			axis = axis / np.sqrt(np.sum(axis ** 2, axis=0))
+			e = np.sqrt(e1 ** 2 + e2 ** 2)
+			phi_axis = np.arctan2(axis[1], axis[0])
+			shp["e1"], shp["e2"] = e * np.cos(2 * phi_axis), e * np.sin(2 * phi_axis)
+		num_patches = 0
+		if patches is not None:
+			pp, ps = np.asarray(patches[0]), np.asarray(patches[1])
+			lo = int(min(pp.min(), ps.min())) if len(pp) and len(ps) else 0
+			num_patches = (int(max(pp.max(), ps.max())) - lo + 1) if len(pp) and len(ps) else 0
+			pos["patch"], shp["patch"] = (pp - lo).astype(np.int32), (ps - lo).astype(np.int32)
+		for k, n in (("position", len(pos["ra"])), ("shape", len(shp["ra"]))):
+			dd = pos if k == "position" else shp
+			if any(len(v) != n for v in dd.values()):
+				raise ValueError(f"light-cone {k} sample: arrays of different lengths")
+
+		def upload(d):  # sorted by chi: the operator's one requirement (it culls on the chi window)
+			order = np.argsort(d["chi"], kind="stable")
+			return {k: torch.from_numpy(np.ascontiguousarray(v[order])).to(dev) for k, v in d.items()}
+
+		r2_thr, thr2, rp2_cut, clean = self._thresholds_for("rppi" if geom == "rppi" else "rmu", rp_cut)
+		rank, world = 0, 1
+		if torch.distributed.is_available() and torch.distributed.is_initialized():
+			rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+		t1 = time.perf_counter()
+		out = ops.lightcone_paircount(upload(pos), upload(shp), torch.from_numpy(r2_thr), torch.from_numpy(thr2),
+									  ops.GEOM_RPPI if geom == "rppi" else ops.GEOM_RMU, bool(shapes), num_patches,
+									  float(h) if over_h else 1.0, float(rp2_cut), rank, world)
+		if world > 1:
+			from .box import combine_across_ranks
+			out = list(combine_across_ranks(out[0], out[1], out[2], out[3], out[4], out[5], out[6], out[7]))
+		torch.cuda.synchronize(dev)
+		t2 = time.perf_counter()
+		cnt, ddw, spd, scd, t_cnt, t_w, t_spd, stats = (t.cpu().numpy() for t in out)
+		self.last_stats = dict(tested=int(stats[0]), binned=int(stats[1]), kernel=int(stats[4]), launches=int(stats[7]),
+							   thresholds_clean=bool(clean), rank=rank, world=world, t_prep=t1 - t0, t_device=t2 - t1,
+							   kernel_ms=ops.LAST_LC_TIMINGS_MS[0])
+		res = dict(count=cnt, DD=ddw, SpD=spd, ScD=scd)
+		if num_patches:
+			res.update(touch_count=t_cnt, touch_DD=t_w, touch_SpD=t_spd)
+		self.last_result = res
+		return res
+
+	# ---- the reference's four loops, same names, same outputs ------------------------------------------------------------------
+	def _centres(self, geom):
+		sep = self.r_bins[:-1] + abs((self.r_bins[1:] - self.r_bins[:-1]) / 2.0)
+		b2 = self.pi_bins if geom == "rppi" else self.mu_r_bins
+		return sep, b2[:-1] + abs((b2[1:] - b2[:-1]) / 2.0)
+
+	def _measure_brute(self, geom, dataset_name, masks, return_output, print_num, over_h, cosmology, jk_group_name, rp_cut=None):
+		res = self._pair_sums(geom, True, masks, over_h, cosmology, rp_cut)
+		if print_num and self.verbose:
+			print(f"There are {len(self.data['RA_shape_sample'])} galaxies in the shape sample and {len(self.data['RA'])} galaxies in the position sample.")
+		DD, SpD, ScD = res["DD"].copy(), res["SpD"], res["ScD"]
+		DD[np.where(DD == 0)] = 1  # measure_w_lightcone.py:188
+		correlation = SpD / DD
+		sep, mid2 = self._centres(geom)
+		top = "w" if geom == "rppi" else "multipoles"
+		n1, n2 = ("_rp", "_pi") if geom == "rppi" else ("_r", "_mu_r")
+		if self.output_file_name is not None and not return_output:
+			if self.last_stats["rank"] == 0:
+				f = open_file(self.output_file_name, "a")
+				try:
+					g = create_group_hdf5(f, f"{self.snap_group}/{top}/xi_g_plus/{jk_group_name}")
+					write_dataset_hdf5(g, dataset_name, data=correlation)
+					write_dataset_hdf5(g, dataset_name + "_SplusD", data=SpD)
+					write_dataset_hdf5(g, dataset_name + n1, data=sep)
+					write_dataset_hdf5(g, dataset_name + n2, data=mid2)
+					g = create_group_hdf5(f, f"{self.snap_group}/{top}/xi_g_cross/{jk_group_name}")
+					write_dataset_hdf5(g, dataset_name + "_ScrossD", data=ScD)
+					write_dataset_hdf5(g, dataset_name + n1, data=sep)
+					write_dataset_hdf5(g, dataset_name + n2, data=mid2)
+					g = create_group_hdf5(f, f"{self.snap_group}/{top}/xi_gg/{jk_group_name}")
+					write_dataset_hdf5(g, dataset_name + "_DD", data=DD)
+					write_dataset_hdf5(g, dataset_name + n1, data=sep)
+					write_dataset_hdf5(g, dataset_name + n2, data=mid2)
+				finally:
+					f.close()
+			return None
+		return SpD, DD, sep, mid2
+
+	def _count_brute(self, geom, dataset_name, masks, return_output, print_num, over_h, cosmology, data_suffix, jk_group_name,
+					 rp_cut=None):
+		res = self._pair_sums(geom, False, masks, over_h, cosmology, rp_cut)
+		DD = res["DD"].copy()
+		DD[np.where(DD == 0)] = 1  # measure_w_lightcone.py:339
+		sep, mid2 = self._centres(geom)
+		top = "w" if geom == "rppi" else "multipoles"
+		n1, n2 = ("_rp", "_pi") if geom == "rppi" else ("_r", "_mu_r")
+		if self.output_file_name is not None and not return_output:
+			if self.last_stats["rank"] == 0:
+				f = open_file(self.output_file_name, "a")
+				try:
+					g = create_group_hdf5(f, f"{self.snap_group}/{top}/xi_gg/{jk_group_name}")
+					write_dataset_hdf5(g, dataset_name + data_suffix, data=DD)
+					write_dataset_hdf5(g, dataset_name + n1, data=sep)
+					write_dataset_hdf5(g, dataset_name + n2, data=mid2)
+				finally:
+					f.close()
+			return None
+		return DD, sep, mid2
+
+	def _measure_xi_rp_pi_lightcone_brute(self, dataset_name, masks=None, return_output=False, print_num=True, over_h=False,
+										  cosmology=None, jk_group_name=""):
+		"""measure_w_lightcone.py:45-214."""
+		return self._measure_brute("rppi", dataset_name, masks, return_output, print_num, over_h, cosmology, jk_group_name)
+
+	def _count_pairs_xi_rp_pi_lightcone_brute(self, dataset_name, masks=None, return_output=False, print_num=True, over_h=False,
+											  cosmology=None, data_suffix="_DD", jk_group_name=""):
+		"""measure_w_lightcone.py:216-343."""
+		return self._count_brute("rppi", dataset_name, masks, return_output, print_num, over_h, cosmology, data_suffix, jk_group_name)
+
+	def _measure_xi_r_mur_lightcone_brute(self, dataset_name, masks=None, return_output=False, print_num=True, over_h=True,
+										  cosmology=None, rp_cut=None, jk_group_name=""):
+		"""measure_m_lightcone.py:45-219."""
+		return self._measure_brute("rmu", dataset_name, masks, return_output, print_num, over_h, cosmology, jk_group_name, rp_cut)
+
+	def _count_pairs_xi_r_mur_lightcone_brute(self, dataset_name, masks=None, return_output=False, print_num=True, over_h=False,
+											  cosmology=None, rp_cut=None, data_suffix="_DD", jk_group_name=""):
+		"""measure_m_lightcone.py:221-363."""
+		return self._count_brute("rmu", dataset_name, masks, return_output, print_num, over_h, cosmology, data_suffix, jk_group_name,
+								 rp_cut)
+
+	# ---- estimators (measure_IA_base.py:670-742) -----------------------------------------------------------------------------
+	def _obs_estimator(self, corr_type, IA_estimator, dataset_name, dataset_name_randoms, num_samples, jk_group_name="",
+					   jk_group_name_randoms=""):
+		if IA_estimator not in ("clusters", "galaxies"):
+			raise ValueError("Unknown input for IA_estimator, choose from [clusters, galaxies].")
+		f = open_file(self.output_file_name, "a")
+		try:
+			which, top = corr_type
+			gp = which in ("g+", "both")
+			gg = which in ("gg", "both")
+			if gp:
+				group_gp = f[f"{self.snap_group}/{top}/xi_g_plus/{jk_group_name}"]
+				group_gp_r = f[f"{self.snap_group}/{top}/xi_g_plus/{jk_group_name_randoms}"]
+				SpD = group_gp[f"{dataset_name}_SplusD"][:]
+				SpR = group_gp_r[f"{dataset_name_randoms}_SplusD"][:]
+			group_gg = f[f"{self.snap_group}/{top}/xi_gg/{jk_group_name}"]
+			group_gg_r = f[f"{self.snap_group}/{top}/xi_gg/{jk_group_name_randoms}"]
+			DD = group_gg[f"{dataset_name}_DD"][:]
+			fD, fS = num_samples["D"] / num_samples["R_D"], num_samples["S"] / num_samples["R_S"]
+			read_SR = lambda: (group_gg[f"{dataset_name}_SR"][:] if which == "gg" else group_gg_r[f"{dataset_name_randoms}_DD"][:])  # noqa: E731
+			with np.errstate(divide="ignore", invalid="ignore"):
+				if IA_estimator == "clusters":
+					SR = read_SR()
+					SR *= fD
+					if gp:
+						SpR *= fD
+						write_dataset_hdf5(group_gp, dataset_name, SpD / DD - SpR / SR)
+					if gg:
+						RD = group_gg[f"{dataset_name}_RD"][:]
+						RR = group_gg[f"{dataset_name}_RR"][:]
+						RD *= fS
+						RR *= fS * fD
+						write_dataset_hdf5(group_gg, dataset_name, (DD - RD - SR) / RR - 1)
+				else:
+					RR = group_gg[f"{dataset_name}_RR"][:]
+					RR *= fS * fD
+					if gp:
+						SpR *= fD
+						write_dataset_hdf5(group_gp, dataset_name, (SpD - SpR) / RR)
+					if gg:
+						RD = group_gg[f"{dataset_name}_RD"][:]
+						SR = read_SR()
+						RD *= fS
+						SR *= fD
+						write_dataset_hdf5(group_gg, dataset_name, (DD - RD - SR) / RR + 1)
+		finally:
+			f.close()
+
+	# ---- public API -------------------------------------------------------------------------------------------------------------
+	def _prepare_randoms(self):
+		"""measure_IA.py:396-413: one random sample serves both roles; default unit weights."""
+		r = self.randoms_data
+		one = "RA_shape_sample" not in r
+		if one:
+			r["RA_shape_sample"], r["DEC_shape_sample"], r["Redshift_shape_sample"] = r["RA"], r["DEC"], r["Redshift"]
+		if "weight" not in r:
+			r["weight"] = np.ones(len(r["RA"]))
+		if "weight_shape_sample" not in r:
+			r["weight_shape_sample"] = r["weight"] if one else np.ones(len(r["RA_shape_sample"]))
+		return one
+
+	def _measure(self, top, IA_estimator, dataset_name, corr_type, want_cov, masks, masks_randoms, cosmology, over_h, rp_cut):
+		if IA_estimator not in ("clusters", "galaxies"):
+			raise KeyError("Unknown input for IA_estimator, choose from [clusters, galaxies].")
+		if corr_type not in ("both", "g+", "gg"):
+			raise KeyError("Unknown value for corr_type. Choose from [g+, gg, both]")
+		if want_cov:
+			raise NotImplementedError(
+				"measure_ia_b200: the jackknife covariance of the light-cone estimators is not built (pass measure_cov=False / "
+				"calc_errors=False); the operator's per-patch sums are available through _pair_sums(..., patches=(pos, shape))")
+		geom = "rppi" if top == "w" else "rmu"
+		kw = dict(over_h=over_h, cosmology=cosmology)
+		if geom == "rmu":
+			kw["rp_cut"] = rp_cut
+		measure = self._measure_xi_rp_pi_lightcone_brute if geom == "rppi" else self._measure_xi_r_mur_lightcone_brute
+		count = self._count_pairs_xi_rp_pi_lightcone_brute if geom == "rppi" else self._count_pairs_xi_r_mur_lightcone_brute
+		data = self.data  # restored at the end (measure_IA.py:392,687)
+		self._prepare_randoms()
+		self.data_dir = D = data
+		if "weight" not in D:
+			D["weight"] = np.ones(len(D["RA"]))
+		if "weight_shape_sample" not in D:
+			D["weight_shape_sample"] = np.ones(len(D["RA_shape_sample"]))
+		R = self.randoms_data
+		n = {}
+		n["D"] = len(D["RA"]) if masks is None else len(D["RA"][masks["RA"]])
+		n["S"] = len(D["RA_shape_sample"]) if masks is None else len(D["RA_shape_sample"][masks["RA_shape_sample"]])
+		n["R_D"] = len(R["RA"]) if masks_randoms is None else len(R["RA"][masks_randoms["RA"]])
+		n["R_S"] = len(R["RA_shape_sample"]) if masks_randoms is None else len(R["RA_shape_sample"][masks_randoms["RA_shape_sample"]])
+		self.num_samples = n
+
+		def combo(position, shape, shapes):
+			"""The reference's temporary data dictionaries (measure_IA.py:460-552): position sample from `position`,
+			shape sample from `shape`."""
+			d = {"Redshift": position["Redshift"], "Redshift_shape_sample": shape["Redshift_shape_sample"], "RA": position["RA"],
+				 "RA_shape_sample": shape["RA_shape_sample"], "DEC": position["DEC"], "DEC_shape_sample": shape["DEC_shape_sample"],
+				 "weight": position["weight"], "weight_shape_sample": shape["weight_shape_sample"]}
+			if shapes:
+				d["e1"], d["e2"] = shape["e1"], shape["e2"]
+			return d
+
+		try:
+			if corr_type in ("g+", "both"):
+				self.data = D  # S+D
+				measure(masks=masks, dataset_name=dataset_name, **kw)
+				self.data = combo(R, D, True)  # S+R
+				measure(masks=masks, dataset_name=f"{dataset_name}_randoms", **kw)
+			if corr_type == "gg":  # SD, SR (already there for 'both')
+				self.data = combo(D, D, False)
+				count(masks=masks, dataset_name=dataset_name, data_suffix="_DD", **kw)
+				self.data = combo(R, D, False)
+				count(masks=masks, dataset_name=dataset_name, data_suffix="_SR", **kw)
+			if corr_type in ("gg", "both"):  # RD
+				self.data = combo(D, R, False)
+				count(masks=masks, dataset_name=dataset_name, data_suffix="_RD", **kw)
+			if IA_estimator == "galaxies" or corr_type in ("gg", "both"):  # RR
+				self.data = combo(R, R, False)
+				count(masks=masks, dataset_name=dataset_name, data_suffix="_RR", **kw)
+			if self.last_stats["rank"] == 0:
+				self._obs_estimator([corr_type, top], IA_estimator, dataset_name, f"{dataset_name}_randoms", n)
+				if top == "w":
+					self._measure_w_g_i(corr_type=corr_type, dataset_name=dataset_name, return_output=False)
+				else:
+					self._measure_multipoles(corr_type=corr_type, dataset_name=dataset_name, return_output=False)
+		finally:
+			self.data = data
+
+	def measure_xi_w(self, IA_estimator, dataset_name, corr_type, jk_patches=None, num_jk=None, measure_cov=True, masks=None,
+					 masks_randoms=None, cosmology=None, over_h=False):
+		"""xi_gg, xi_g+ and w_gg, w_g+ for light-cone data (measure_IA.py:336-688)."""
+		self._measure("w", IA_estimator, dataset_name, corr_type, measure_cov, masks, masks_randoms, cosmology, over_h, None)
+
+	def measure_xi_multipoles(self, IA_estimator, dataset_name, corr_type, jk_patches=None, num_jk=None, calc_errors=True,
+							  masks=None, masks_randoms=None, cosmology=None, over_h=False, rp_cut=None):
+		"""Multipoles for light-cone data (measure_IA.py:690-1058)."""
+		self._measure("multipoles", IA_estimator, dataset_name, corr_type, calc_errors, masks, masks_randoms, cosmology, over_h,
+					  rp_cut)

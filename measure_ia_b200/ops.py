@@ -47,8 +47,22 @@ class MiaShard(ctypes.Structure):
 	_fields_ = [("index", ctypes.c_int32), ("count", ctypes.c_int32)]
 
 
+class MiaLcParams(ctypes.Structure):
+	_fields_ = [("abi_version", ctypes.c_int32), ("geometry", ctypes.c_int32), ("n_r", ctypes.c_int32), ("n_2", ctypes.c_int32),
+				("num_patches", ctypes.c_int32), ("shapes", ctypes.c_int32), ("proj_scale", ctypes.c_double),
+				("rp2_cut", ctypes.c_double), ("r2_thr_host", ctypes.c_void_p), ("thr2_host", ctypes.c_void_p),
+				("timings_host", ctypes.c_void_p)]
+
+
+class MiaLcSample(ctypes.Structure):
+	_fields_ = [("n", ctypes.c_int64), ("ra", ctypes.c_void_p), ("dec", ctypes.c_void_p), ("chi", ctypes.c_void_p),
+				("cosdec", ctypes.c_void_p), ("weight", ctypes.c_void_p), ("e1", ctypes.c_void_p), ("e2", ctypes.c_void_p),
+				("patch", ctypes.c_void_p)]
+
+
+KERNEL_LIGHTCONE = 5
 EXPORTS = ("mia_strerror", "mia_abi_version", "mia_workspace_bytes", "mia_paircount", "mia_paircount_host",
-		   "mia_combine_partials_f64")
+		   "mia_combine_partials_f64", "mia_lightcone_paircount", "mia_lightcone_paircount_host")
 
 _lib = None
 
@@ -86,6 +100,12 @@ def load_library():
 		lib.mia_combine_partials_f64.restype = ctypes.c_int
 		lib.mia_combine_partials_f64.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p,
 												 ctypes.c_void_p]
+		lib.mia_lightcone_paircount.restype = ctypes.c_int
+		lib.mia_lightcone_paircount.argtypes = [ctypes.POINTER(MiaLcParams), ctypes.POINTER(MiaLcSample),
+												ctypes.POINTER(MiaLcSample), MiaShard, ctypes.POINTER(MiaHist), ctypes.c_void_p]
+		lib.mia_lightcone_paircount_host.restype = ctypes.c_int
+		lib.mia_lightcone_paircount_host.argtypes = [ctypes.POINTER(MiaLcParams), ctypes.POINTER(MiaLcSample),
+													 ctypes.POINTER(MiaLcSample), MiaShard, ctypes.POINTER(MiaHist), ctypes.c_int]
 		if lib.mia_abi_version() != MIA_ABI_VERSION:
 			raise RuntimeError("libmia_b200.so ABI version mismatch; rebuild")
 		_lib = lib
@@ -201,3 +221,60 @@ def combine_partials(parts: torch.Tensor) -> torch.Tensor:
 		check(load_library().mia_combine_partials_f64(parts.data_ptr(), parts.shape[0], out.numel(), out.data_ptr(),
 													  torch.cuda.current_stream(parts.device).cuda_stream))
 	return out
+
+
+# ---- light-cone brute pair loops (include/mia_b200.h, mia_lightcone_paircount) -------------------------------------------
+LAST_LC_TIMINGS_MS = [0.0, 0.0]  # [pair kernel, whole call] of the last lightcone_paircount call
+_lc_timing_buf = (ctypes.c_float * 2)()
+
+
+def lightcone_paircount(position: dict, shape: dict, r2_thr: torch.Tensor, thr2: torch.Tensor, geometry: int, shapes: bool,
+						num_patches: int = 0, proj_scale: float = 1.0, rp2_cut: float = 0.0, shard_index: int = 0,
+						shard_count: int = 1) -> List[torch.Tensor]:
+	"""Pair sums of a light-cone position sample around a shape sample (reference loops: measure_w_lightcone.py:137-183,
+	:307-334, measure_m_lightcone.py:142-191, :300-330).
+
+	position: dict of 1-D float64 CUDA tensors ra, dec, chi, cosdec[, weight][, patch (int32)], SORTED by chi;
+	shape: ra, dec, chi[, weight][, e1, e2 (= e cos 2phi_axis, e sin 2phi_axis)][, patch].  No CPU implementation.
+	Returns [dd_count i64 (n_r,n_2), dd_w, spd, scd, touch_count i64 (num_patches,n_r,n_2), touch_w, touch_spd, stats i64 (8)].
+	"""
+	lib = load_library()
+	dev = position["chi"].device
+	n_r, n_2 = r2_thr.numel() - 1, thr2.numel() - 1
+	assert r2_thr.dtype == torch.float64 and thr2.dtype == torch.float64 and not r2_thr.is_cuda and not thr2.is_cuda
+	params = MiaLcParams(MIA_ABI_VERSION, geometry, n_r, n_2, num_patches, 1 if shapes else 0, float(proj_scale), float(rp2_cut),
+						 r2_thr.data_ptr(), thr2.data_ptr(), ctypes.addressof(_lc_timing_buf))
+	f64, i32, i64 = torch.float64, torch.int32, torch.int64
+
+	def sample(d, is_shape):
+		n = d["chi"].shape[0]
+		for k, t in d.items():
+			if t is not None:
+				_check_rows(k, t, n)
+		return MiaLcSample(n, _dev_ptr(d["ra"], f64, ()), _dev_ptr(d["dec"], f64, ()), _dev_ptr(d["chi"], f64, ()),
+						   None if is_shape else _dev_ptr(d["cosdec"], f64, ()), _dev_ptr(d.get("weight"), f64, ()),
+						   _dev_ptr(d.get("e1"), f64, ()) if is_shape else None, _dev_ptr(d.get("e2"), f64, ()) if is_shape else None,
+						   _dev_ptr(d.get("patch"), i32, ()))
+
+	D, S = sample(position, False), sample(shape, True)
+	with torch.cuda.device(dev):
+		dd_count = torch.empty((n_r, n_2), dtype=i64, device=dev)
+		dd_w, spd, scd = (torch.empty((n_r, n_2), dtype=f64, device=dev) for _ in range(3))
+		t_count = torch.empty((num_patches, n_r, n_2), dtype=i64, device=dev)
+		t_w, t_spd = (torch.empty((num_patches, n_r, n_2), dtype=f64, device=dev) for _ in range(2))
+		stats = torch.zeros(8, dtype=i64, device=dev)
+		H = MiaHist(dd_count.data_ptr(), dd_w.data_ptr(), spd.data_ptr(), scd.data_ptr(),
+					t_count.data_ptr() if num_patches else None, t_w.data_ptr() if num_patches else None,
+					t_spd.data_ptr() if num_patches else None, stats.data_ptr(), None)
+		stream = torch.cuda.current_stream(dev).cuda_stream
+		rc = lib.mia_lightcone_paircount(ctypes.byref(params), ctypes.byref(D), ctypes.byref(S),
+										 MiaShard(shard_index, shard_count), ctypes.byref(H), stream)
+	check(rc)
+	LAST_LC_TIMINGS_MS[:] = list(_lc_timing_buf)
+	return [dd_count, dd_w, spd, scd, t_count, t_w, t_spd, stats]
+
+
+def lightcone_paircount_host(params: MiaLcParams, D: MiaLcSample, S: MiaLcSample, H: MiaHist, shard=(0, 1), device=0):
+	"""``mia_lightcone_paircount_host``: host pointers in, host pointers out."""
+	check(load_library().mia_lightcone_paircount_host(ctypes.byref(params), ctypes.byref(D), ctypes.byref(S),
+													  MiaShard(shard[0], shard[1]), ctypes.byref(H), device))

@@ -54,3 +54,20 @@ def test_live_reference_masks_weights_cross(oracle):
 	masks = make_golden.make_masks(data, 7)
 	got, want = _both(oracle, data, "w", 100.0, num_jk=8, num_bins_r=5, num_bins_pi=6, masks=masks)
 	pu.assert_datasets_match(got, want, exact_counts=False, label="live masks: ")
+
+
+@pytest.mark.parametrize("kind,estimator,corr", [("w", "galaxies", "both"), ("multipoles", "clusters", "both"), ("w", "clusters", "gg")])
+def test_live_reference_lightcone(tmp_path, monkeypatch, kind, estimator, corr):
+	"""Light-cone brute loops: oracle/pylightcone.py + the product's host side against the live reference on a
+	catalogue that is NOT one of the committed fixtures (pyccl replaced by oracle/ref_shims/pyccl on both sides)."""
+	import make_golden_lightcone as mg
+	from measure_ia_b200.lightcone import MeasureIALightcone
+	from test_host_post import read_all
+	from test_lightcone_host import compare_with_fixture, oracle_lc_pair_sums, run_product
+	cat = dict(n=350, n_shape=280, n_rand=500, seed=901, weights=True)
+	call = dict(kind=kind, IA_estimator=estimator, corr_type=corr, over_h=(kind == "multipoles"))
+	want = mg.run_reference(cat, call)
+	monkeypatch.setattr(MeasureIALightcone, "_pair_sums", oracle_lc_pair_sums())
+	out = str(tmp_path / "lc.hdf5")
+	run_product(dict(catalogue=cat, call=call, binning=mg.BINNING), out)
+	compare_with_fixture(read_all(out), want, f"live light-cone {kind}/{estimator}/{corr}: ", False)
