@@ -347,6 +347,62 @@ def run_cfg5(dev, rank, world, barrier, kernel):
 			"kernel": box.last_stats["kernel"]}
 
 
+def run_lightcone(dev, rank, world, barrier, peak, cpu_leg):
+	"""the light-cone brute loop `_measure_xi_rp_pi_lightcone_brute` (measure_w_lightcone.py:45-214) through the
+	public class, host numpy inputs: 4e5 position x 4e5 shape galaxies on a 30 x 30 degree patch, 0.1 < z < 0.4, 10 x 8 bins,
+	|Pi| < 60.  The reference visits all N_p N_s pairs, so the like-for-like rate is RAW pairs per second (N_p N_s / time); the
+	kernel computes a separation only for pairs inside the chi window and the sky pre-filter."""
+	import numpy as np
+	from measure_ia_b200.lightcone import MeasureIALightcone
+
+	def catalogue(n, seed):
+		rng = np.random.default_rng(seed)
+		return {"RA": rng.uniform(0.0, 30.0, n), "DEC": rng.uniform(-15.0, 15.0, n), "Redshift": rng.uniform(0.1, 0.4, n),
+				"RA_shape_sample": rng.uniform(0.0, 30.0, n), "DEC_shape_sample": rng.uniform(-15.0, 15.0, n),
+				"Redshift_shape_sample": rng.uniform(0.1, 0.4, n), "e1": rng.normal(0, 0.2, n), "e2": rng.normal(0, 0.2, n)}
+
+	n = 400_000
+	obj = MeasureIALightcone(catalogue(n, 77), None, None, [0.1, 20.0], 10, 8, 60.0)
+	wall, kernel_ms = 0.0, 0.0
+	for _ in range(2):  # one warm-up, one timed
+		barrier()
+		t0 = time.perf_counter()
+		obj._measure_xi_rp_pi_lightcone_brute("All", return_output=True, print_num=False)
+		barrier()
+		wall, kernel_ms = time.perf_counter() - t0, obj.last_stats["kernel_ms"]
+	st, res = obj.last_stats, obj.last_result
+	binned = int(res["count"].sum())
+	rec = {"value": binned / wall, "unit": "pairs/s", "wall_s": wall, "pair_kernel_ms_rank0": kernel_ms, "pairs": binned,
+		   "separations_computed": st["tested"], "raw_pairs": n * n, "raw_pairs_per_s": n * n / wall,
+		   "config": {"n_position": n, "n_shape": n, "sky": "30 x 30 deg, 0.1 < z < 0.4", "bins": [10, 8], "pi_max": 60.0,
+					  "api": "MeasureIALightcone._measure_xi_rp_pi_lightcone_brute(host numpy dict, return_output=True)"}}
+	if peak:
+		rec["roofline"] = {"bound": "fp64-alu", "achieved": binned * 64 / (kernel_ms * 1e-3) / 1e12 if kernel_ms else None,
+						   "peak": peak, "unit": "TFLOP/s", "kernel_ms": kernel_ms,
+						   "note": "64 flop credited per BINNED pair as for the box; separations that end in a range reject "
+								   "(separations_computed - pairs) are uncredited work"}
+		if kernel_ms:
+			rec["roofline"]["frac"] = rec["roofline"]["achieved"] / peak
+	if cpu_leg:  # the numpy oracle (the reference's own vectorised-per-galaxy arithmetic) on a bounded subsample, one core
+		sys.path.insert(0, os.path.join(_REPO, "oracle"))
+		import pylightcone
+		m = 12000
+		sub = catalogue(m, 78)
+		t0 = time.perf_counter()
+		pos, h = pylightcone.sample(sub["RA"], sub["DEC"], sub["Redshift"])
+		shp, _ = pylightcone.sample(sub["RA_shape_sample"], sub["DEC_shape_sample"], sub["Redshift_shape_sample"], e1=sub["e1"], e2=sub["e2"])
+		want = pylightcone.pair_sums("rppi", pos, shp, 0.1, 20.0, obj.r_bins, obj.pi_bins, 10, 8)
+		dt = time.perf_counter() - t0
+		small = MeasureIALightcone(sub, None, None, [0.1, 20.0], 10, 8, 60.0)
+		small._measure_xi_rp_pi_lightcone_brute("All", return_output=True, print_num=False)
+		rec["cpu_baseline"] = {"raw_pairs_per_s": m * m / dt, "cores": 1, "kind": "port",
+							   "sample": f"{m} x {m} galaxies of the same generator in {dt:.1f} s (oracle/pylightcone.py, numpy)"}
+		rec["parity_check"] = {"against": "oracle/pylightcone.py on the CPU sample",
+							   "dd_bit_exact": bool(np.array_equal(small.last_result["count"], want["count"])),
+							   "pairs": int(want["count"].sum())}
+	return rec
+
+
 def fp64_peak(torch, dev):
 	"""Dependent-free DFMA rate of this GPU, measured live (MEASURED_PEAKS.json carries no FP64 figure), with the SM
 	clock sampled while the probe runs."""
@@ -542,6 +598,10 @@ def main():
 			sec["cfg5"] = run_cfg5(dev, rank, world, barrier, args.kernel)
 		except Exception as exc:  # noqa: BLE001
 			sec["cfg5"] = {"error": f"{type(exc).__name__}: {exc}"}
+		try:
+			sec["lightcone"] = run_lightcone(dev, rank, world, barrier, peak, rank == 0 and world == 1 and not args.no_cpu_baseline)
+		except Exception as exc:  # noqa: BLE001
+			sec["lightcone"] = {"error": f"{type(exc).__name__}: {exc}"}
 		line["secondary"] = sec
 
 	if rank == 0:

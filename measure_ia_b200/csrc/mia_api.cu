@@ -653,6 +653,8 @@ int mia_lightcone_paircount(const mia_lc_params *p, const mia_lc_sample *D, cons
 	P.rp2_cut = p->rp2_cut;
 	for (int b = 0; b <= p->n_r; b++) P.r2_thr[b] = p->r2_thr_host[b];
 	for (int b = 0; b <= p->n_2; b++) P.thr2[b] = p->thr2_host[b];
+	P.reach = sqrt(P.r2_thr[p->n_r]) * (1.0 + 1e-9);
+	P.cull_scale = (p->geometry == MIA_GEOM_RPPI) ? p->proj_scale : 1.0;  // the (r, mu_r) range test sees the unscaled dx, dy
 	if (p->geometry == MIA_GEOM_RPPI) {
 		P.win_lo = P.thr2[0];
 		P.win_hi = P.thr2[p->n_2];

@@ -40,6 +40,8 @@ struct LcDev {
 	double r2_thr[MIA_MAX_BINS + 1];
 	double thr2[MIA_MAX_BINS + 1];
 	double win_lo, win_hi;  // chi_s - chi_n outside [win_lo, win_hi] can never be binned
+	double reach;           // > largest separation that can be binned (sqrt of the last r threshold, plus a relative margin)
+	double cull_scale;      // factor of the separation components the range test sees: proj_scale for (r_p, Pi), 1 for (r, mu_r)
 };
 
 struct LcSampleDev {
@@ -125,6 +127,11 @@ __global__ void __launch_bounds__(LC_TP) k_lightcone(const LcDev P, const LcSamp
 		w_n = D.w ? D.w[n] : 1.0;
 		patch_n = D.patch ? D.patch[n] : 0;
 	}
+	// conservative pre-filter on the two sky offsets (a few ulp of error against a 1e-9 margin in `reach`): a pair whose dec
+	// or ra offset ALONE exceeds the largest binnable separation is skipped before the exact operation sequence is paid for
+	const double k_dec = (3.141592653589793 / 180.0) * chi_n * P.cull_scale;
+	const double lim_dec = (k_dec > 0.0) ? P.reach / k_dec : INFINITY;                 // degrees
+	const double lim_ra = (k_dec * fabs(cd_n) > 0.0) ? P.reach / (k_dec * fabs(cd_n)) : INFINITY;
 	unsigned long long tested = 0, binned = 0;
 	const long long n_tiles = (w1 - w0 + LC_TILE - 1) / LC_TILE;
 	for (long long t = blockIdx.y; t < n_tiles; t += n_seg) {
@@ -145,8 +152,9 @@ __global__ void __launch_bounds__(LC_TP) k_lightcone(const LcDev P, const LcSamp
 		}
 		__syncthreads();
 		if (!active) continue;
-		tested += (unsigned long long)cnt;
 		for (int k = 0; k < cnt; k++) {
+			if (fabs(t_dec[k] - dec_n) > lim_dec || fabs(t_ra[k] - ra_n) > lim_ra) continue;
+			tested++;
 			const double los = __dsub_rn(t_chi[k], chi_n);  // measure_w_lightcone.py:139
 			if (GEOM == MIA_GEOM_RPPI) {
 				if (!(los >= P.thr2[0] && los < P.thr2[P.n_2])) continue;  // :160-161
