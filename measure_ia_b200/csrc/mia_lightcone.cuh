@@ -14,7 +14,8 @@
 // Here: both samples arrive sorted by chi (the host mirror sorts; the library checks).  A CTA owns 128 consecutive position
 // galaxies (one per thread) and a segment of the shape sample's chi WINDOW that can reach them (Pi range of the binning,
 // or +-r_max): the only cull, exact because every pair inside the window is still tested with the reference's own
-// comparisons.  Shape galaxies are staged through shared memory in tiles.  Everything that decides a bin uses the
+// comparisons.  Shape galaxies' sky coordinates are staged through shared memory in tiles for a conservative pre-filter;
+// the pairs that pass are compacted per warp (see LC_Q below) before the exact sequence.  Everything that decides a bin uses the
 // reference's IEEE operation sequence (__d*_rn, no contraction) against the calibrated thresholds,
 // so pair counts are bit-exact.  The shape projection needs no transcendental call per pair:
 //     cos 2 phi_sep = (dx^2 - dy^2) / r_p^2,  sin 2 phi_sep = 2 dx dy / r_p^2,
@@ -64,16 +65,94 @@ __global__ void k_lc_check_sorted(const double *__restrict__ chi, int64_t n, int
 	if (i < n && !(chi[i] == chi[i])) atomicExch(flag, 1);
 }
 
+// One pair through the reference's exact operation sequence; accumulates into the CTA's shared histogram (and the global
+// per-patch rows).  Returns true when the pair was binned.
+struct LcAcc {
+	double *s_ddw, *s_sp, *s_sc;
+	unsigned int *s_cnt;
+	int nb;
+};
+
+template <int GEOM, bool SHAPES>
+__device__ __forceinline__ bool lc_pair(const LcDev &P, const LcOut &O, const LcAcc &A, double ra_n, double dec_n, double chi_n,
+										double cd_n, double w_n, int patch_n, double ra_s, double dec_s, double chi_s, double w_s,
+										double e1_s, double e2_s, int patch_s) {
+	const double los = __dsub_rn(chi_s, chi_n);  // measure_w_lightcone.py:139
+	if (GEOM == MIA_GEOM_RPPI) {
+		if (!(los >= P.thr2[0] && los < P.thr2[P.n_2])) return false;  // :160-161
+	}
+	const double dra = __dmul_rn(__ddiv_rn(__dsub_rn(ra_s, ra_n), 180.0), 3.141592653589793);    // :140
+	const double ddec = __dmul_rn(__ddiv_rn(__dsub_rn(dec_s, dec_n), 180.0), 3.141592653589793);  // :141
+	const double dx = __dmul_rn(__dmul_rn(dra, chi_n), cd_n);                                      // :142
+	const double dy = __dmul_rn(ddec, chi_n);                                                        // :143
+	const double px = P.scaled ? __dmul_rn(dx, P.proj_scale) : dx, py = P.scaled ? __dmul_rn(dy, P.proj_scale) : dy;  // :145-146
+	const double rp2 = __dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py));  // :147
+	double s;
+	int bin2;
+	if (GEOM == MIA_GEOM_RPPI) {
+		s = rp2;
+		if (!(s >= P.r2_thr[0] && s < P.r2_thr[P.n_r])) return false;
+		bin2 = count_thresholds(los, P.thr2, P.n_2);
+	} else {
+		if (!(rp2 > P.rp2_cut)) return false;  // measure_m_lightcone.py:172
+		// the 3-D separation keeps the UNSCALED dx, dy (:150 builds it before `projected_sep *= h`)
+		s = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(los, los));  // :154
+		if (!(s >= P.r2_thr[0] && s < P.r2_thr[P.n_r])) return false;
+		const double mu = __ddiv_rn(los, __dsqrt_rn(s));  // :157
+		bin2 = count_thresholds(mu, P.thr2, P.n_2);
+	}
+	const int b = count_thresholds(s, P.r2_thr, P.n_r) * P.n_2 + bin2;
+	const double ww = w_n * w_s;
+	double tp = 0.0, tc = 0.0;
+	if (SHAPES) {
+		// rp2 == 0 cannot be binned ((r_p, Pi): r_p >= r_min > 0; (r, mu_r): r_p^2 > rp2_cut >= 0), so the reference's
+		// NaN -> 0 rule (:153-154) never fires on a binned pair
+		const double inv = 1.0 / rp2;
+		const double c2 = (px * px - py * py) * inv, s2 = 2.0 * px * py * inv;
+		tp = -ww * (e1_s * c2 + e2_s * s2);
+		tc = -ww * (e2_s * c2 - e1_s * s2);
+	}
+	atomicAdd(&A.s_cnt[b], 1u);
+	atomicAdd(&A.s_ddw[b], ww);
+	if (SHAPES) {
+		atomicAdd(&A.s_sp[b], tp);
+		atomicAdd(&A.s_sc[b], tc);
+	}
+	if (P.num_patches > 0) {
+		size_t row = (size_t)patch_s * A.nb + b;
+		atomicAdd(&O.jcnt[row], 1ull);
+		atomicAdd(&O.jddw[row], ww);
+		if (SHAPES) atomicAdd(&O.jsp[row], tp);
+		if (patch_n != patch_s) {
+			row = (size_t)patch_n * A.nb + b;
+			atomicAdd(&O.jcnt[row], 1ull);
+			atomicAdd(&O.jddw[row], ww);
+			if (SHAPES) atomicAdd(&O.jsp[row], tp);
+		}
+	}
+	return true;
+}
+
+// Shared memory: shape tile (6 doubles + patch) | the CTA's position galaxies (5 doubles + patch) | histogram | per-warp queues.
+// Pairs that pass the pre-filter are rare (about one lane in a hundred per iteration) and the exact sequence is ~150
+// instructions, so running it in place would drag the whole warp through it for one or two lanes.  Instead the passing
+// (lane, shape index) pairs go to a per-warp ring in shared memory, and whenever 32 are waiting every lane takes one:
+// the exact sequence always runs with full warps (the shape galaxy is re-read from global memory, an L2 hit).
+constexpr int LC_Q = 64;  // ring entries per warp (at most 31 waiting + 32 new)
+
 template <int GEOM, bool SHAPES>
 __global__ void __launch_bounds__(LC_TP) k_lightcone(const LcDev P, const LcSampleDev D, const LcSampleDev S, int64_t p_begin,
 													 int64_t p_end, int n_seg, LcOut O) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int nb = P.n_r * P.n_2;
 	double *t_ra = reinterpret_cast<double *>(smem_raw);
-	double *t_dec = t_ra + LC_TILE, *t_chi = t_dec + LC_TILE, *t_w = t_chi + LC_TILE, *t_e1 = t_w + LC_TILE, *t_e2 = t_e1 + LC_TILE;
-	double *s_ddw = t_e2 + LC_TILE, *s_sp = s_ddw + nb, *s_sc = s_sp + nb;
+	double *t_dec = t_ra + LC_TILE;
+	double *p_ra = t_dec + LC_TILE, *p_dec = p_ra + LC_TP, *p_chi = p_dec + LC_TP, *p_cd = p_chi + LC_TP, *p_w = p_cd + LC_TP;
+	double *s_ddw = p_w + LC_TP, *s_sp = s_ddw + nb, *s_sc = s_sp + nb;
 	unsigned int *s_cnt = reinterpret_cast<unsigned int *>(s_sc + nb);
-	int *t_patch = reinterpret_cast<int *>(s_cnt + nb);
+	int *p_patch = reinterpret_cast<int *>(s_cnt + nb);
+	int *q_j = p_patch + LC_TP;                                               // [warps][LC_Q] shape index
+	unsigned char *q_lane = reinterpret_cast<unsigned char *>(q_j + (LC_TP / 32) * LC_Q);  // [warps][LC_Q] lane of the position galaxy
 	__shared__ long long win[2];
 
 	for (int b = threadIdx.x; b < nb; b += blockDim.x) {
@@ -112,9 +191,6 @@ __global__ void __launch_bounds__(LC_TP) k_lightcone(const LcDev P, const LcSamp
 			win[1] = S.n;
 		}
 	}
-	__syncthreads();
-	const long long w0 = win[0], w1 = win[1];
-
 	const int64_t n = blk0 + threadIdx.x;
 	const bool active = n < blk1;
 	double ra_n = 0.0, dec_n = 0.0, chi_n = 0.0, cd_n = 0.0, w_n = 0.0;
@@ -127,91 +203,67 @@ __global__ void __launch_bounds__(LC_TP) k_lightcone(const LcDev P, const LcSamp
 		w_n = D.w ? D.w[n] : 1.0;
 		patch_n = D.patch ? D.patch[n] : 0;
 	}
+	p_ra[threadIdx.x] = ra_n;
+	p_dec[threadIdx.x] = dec_n;
+	p_chi[threadIdx.x] = chi_n;
+	p_cd[threadIdx.x] = cd_n;
+	p_w[threadIdx.x] = w_n;
+	p_patch[threadIdx.x] = patch_n;
+	__syncthreads();
+	const long long w0 = win[0], w1 = win[1];
+
 	// conservative pre-filter on the two sky offsets (a few ulp of error against a 1e-9 margin in `reach`): a pair whose dec
 	// or ra offset ALONE exceeds the largest binnable separation is skipped before the exact operation sequence is paid for
 	const double k_dec = (3.141592653589793 / 180.0) * chi_n * P.cull_scale;
-	const double lim_dec = (k_dec > 0.0) ? P.reach / k_dec : INFINITY;                 // degrees
+	const double lim_dec = (k_dec > 0.0) ? P.reach / k_dec : INFINITY;  // degrees
 	const double lim_ra = (k_dec * fabs(cd_n) > 0.0) ? P.reach / (k_dec * fabs(cd_n)) : INFINITY;
+	const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+	int *my_qj = q_j + (threadIdx.x >> 5) * LC_Q;
+	unsigned char *my_ql = q_lane + (threadIdx.x >> 5) * LC_Q;
+	int q_head = 0, q_n = 0;  // warp-uniform
+	LcAcc A = {s_ddw, s_sp, s_sc, s_cnt, nb};
 	unsigned long long tested = 0, binned = 0;
+
+	auto take_entry = [&](int slot) {  // this lane evaluates the queued pair in ring slot `slot`
+		const int src = wbase + (int)my_ql[slot];
+		const long long j = (long long)my_qj[slot];
+		const bool ok = lc_pair<GEOM, SHAPES>(P, O, A, p_ra[src], p_dec[src], p_chi[src], p_cd[src], p_w[src], p_patch[src], S.ra[j],
+											  S.dec[j], S.chi[j], S.w ? S.w[j] : 1.0, SHAPES ? S.e1[j] : 0.0, SHAPES ? S.e2[j] : 0.0,
+											  S.patch ? S.patch[j] : 0);
+		binned += ok ? 1ull : 0ull;
+	};
+
 	const long long n_tiles = (w1 - w0 + LC_TILE - 1) / LC_TILE;
 	for (long long t = blockIdx.y; t < n_tiles; t += n_seg) {
 		const long long j0 = w0 + t * LC_TILE;
 		const int cnt = (int)((w1 - j0 < LC_TILE) ? (w1 - j0) : LC_TILE);
 		__syncthreads();  // the previous tile has been consumed
 		if ((int)threadIdx.x < cnt) {
-			const long long j = j0 + threadIdx.x;
-			t_ra[threadIdx.x] = S.ra[j];
-			t_dec[threadIdx.x] = S.dec[j];
-			t_chi[threadIdx.x] = S.chi[j];
-			t_w[threadIdx.x] = S.w ? S.w[j] : 1.0;
-			if (SHAPES) {
-				t_e1[threadIdx.x] = S.e1[j];
-				t_e2[threadIdx.x] = S.e2[j];
-			}
-			t_patch[threadIdx.x] = S.patch ? S.patch[j] : 0;
+			t_ra[threadIdx.x] = S.ra[j0 + threadIdx.x];
+			t_dec[threadIdx.x] = S.dec[j0 + threadIdx.x];
 		}
 		__syncthreads();
-		if (!active) continue;
 		for (int k = 0; k < cnt; k++) {
-			if (fabs(t_dec[k] - dec_n) > lim_dec || fabs(t_ra[k] - ra_n) > lim_ra) continue;
-			tested++;
-			const double los = __dsub_rn(t_chi[k], chi_n);  // measure_w_lightcone.py:139
-			if (GEOM == MIA_GEOM_RPPI) {
-				if (!(los >= P.thr2[0] && los < P.thr2[P.n_2])) continue;  // :160-161
+			const bool pass = active && !(fabs(t_dec[k] - dec_n) > lim_dec || fabs(t_ra[k] - ra_n) > lim_ra);
+			const unsigned m = __ballot_sync(0xffffffffu, pass);
+			if (!m) continue;
+			if (pass) {
+				const int slot = (q_head + q_n + __popc(m & ((1u << lane) - 1u))) & (LC_Q - 1);
+				my_qj[slot] = (int)(j0 + k);
+				my_ql[slot] = (unsigned char)lane;
+				tested++;
 			}
-			const double dra = __dmul_rn(__ddiv_rn(__dsub_rn(t_ra[k], ra_n), 180.0), 3.141592653589793);   // :140
-			const double ddec = __dmul_rn(__ddiv_rn(__dsub_rn(t_dec[k], dec_n), 180.0), 3.141592653589793);  // :141
-			const double dx = __dmul_rn(__dmul_rn(dra, chi_n), cd_n);                                       // :142
-			const double dy = __dmul_rn(ddec, chi_n);                                                         // :143
-			const double px = P.scaled ? __dmul_rn(dx, P.proj_scale) : dx, py = P.scaled ? __dmul_rn(dy, P.proj_scale) : dy;  // :145-146
-			const double rp2 = __dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py));  // :147
-			double s;
-			int bin2;
-			if (GEOM == MIA_GEOM_RPPI) {
-				s = rp2;
-				if (!(s >= P.r2_thr[0] && s < P.r2_thr[P.n_r])) continue;
-				bin2 = count_thresholds(los, P.thr2, P.n_2);
-			} else {
-				if (!(rp2 > P.rp2_cut)) continue;  // measure_m_lightcone.py:172
-				// the 3-D separation keeps the UNSCALED dx, dy (:150 builds it before `projected_sep *= h`)
-				s = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(los, los));  // :154
-				if (!(s >= P.r2_thr[0] && s < P.r2_thr[P.n_r])) continue;
-				const double mu = __ddiv_rn(los, __dsqrt_rn(s));  // :157
-				bin2 = count_thresholds(mu, P.thr2, P.n_2);
-			}
-			const int b = count_thresholds(s, P.r2_thr, P.n_r) * P.n_2 + bin2;
-			binned++;
-			const double ww = w_n * t_w[k];
-			double tp = 0.0, tc = 0.0;
-			if (SHAPES) {
-				// rp2 == 0 cannot be binned ((r_p, Pi): r_p >= r_min > 0; (r, mu_r): r_p^2 > rp2_cut >= 0), so the reference's
-				// NaN -> 0 rule (:153-154) never fires on a binned pair
-				const double inv = 1.0 / rp2;
-				const double c2 = (px * px - py * py) * inv, s2 = 2.0 * px * py * inv;
-				tp = -ww * (t_e1[k] * c2 + t_e2[k] * s2);
-				tc = -ww * (t_e2[k] * c2 - t_e1[k] * s2);
-			}
-			atomicAdd(&s_cnt[b], 1u);
-			atomicAdd(&s_ddw[b], ww);
-			if (SHAPES) {
-				atomicAdd(&s_sp[b], tp);
-				atomicAdd(&s_sc[b], tc);
-			}
-			if (P.num_patches > 0) {
-				const int ps = t_patch[k];
-				size_t row = (size_t)ps * nb + b;
-				atomicAdd(&O.jcnt[row], 1ull);
-				atomicAdd(&O.jddw[row], ww);
-				if (SHAPES) atomicAdd(&O.jsp[row], tp);
-				if (patch_n != ps) {
-					row = (size_t)patch_n * nb + b;
-					atomicAdd(&O.jcnt[row], 1ull);
-					atomicAdd(&O.jddw[row], ww);
-					if (SHAPES) atomicAdd(&O.jsp[row], tp);
-				}
+			q_n += __popc(m);
+			__syncwarp();
+			if (q_n >= 32) {
+				take_entry((q_head + lane) & (LC_Q - 1));
+				q_head = (q_head + 32) & (LC_Q - 1);
+				q_n -= 32;
+				__syncwarp();
 			}
 		}
 	}
+	if (lane < q_n) take_entry((q_head + lane) & (LC_Q - 1));  // what is left in the ring
 	__syncthreads();
 	for (int b = threadIdx.x; b < nb; b += blockDim.x) {
 		if (s_cnt[b]) {
@@ -227,14 +279,15 @@ __global__ void __launch_bounds__(LC_TP) k_lightcone(const LcDev P, const LcSamp
 		tested += __shfl_down_sync(0xffffffffu, tested, o);
 		binned += __shfl_down_sync(0xffffffffu, binned, o);
 	}
-	if ((threadIdx.x & 31) == 0) {
+	if (lane == 0) {
 		atomicAdd(&O.stats[0], tested);
 		atomicAdd(&O.stats[1], binned);
 	}
 }
 
 inline size_t lightcone_smem_bytes(int nb) {
-	return sizeof(double) * 6 * LC_TILE + (size_t)nb * (3 * sizeof(double) + sizeof(unsigned int)) + sizeof(int) * LC_TILE;
+	return sizeof(double) * (2 * LC_TILE + 5 * LC_TP) + (size_t)nb * (3 * sizeof(double) + sizeof(unsigned int)) + sizeof(int) * LC_TP +
+		   (size_t)(LC_TP / 32) * LC_Q * (sizeof(int) + 1);
 }
 
 }  // namespace mia
