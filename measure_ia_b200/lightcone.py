@@ -7,10 +7,11 @@
 (``_measure_xi_rp_pi_lightcone_brute``, ``_count_pairs_xi_rp_pi_lightcone_brute`` and their (r, mu_r) twins) are ONE operator,
 ``ops.lightcone_paircount`` (CUDA, sm_100a; no CPU fallback).
 
-Not built: the jackknife covariance of the light-cone estimators (``measure_cov`` / ``calc_errors``: k-means sky patches via
-``kmeans_radec`` and the leave-one-patch-out re-runs of measure_jackknife.py:59-483).  The operator already returns, per
-patch, the sums over pairs touching it (``num_patches``; realisation k = total - touch[k]); the host layout of the
-realisations is not mirrored, and asking for it raises ``NotImplementedError``.
+Jackknife covariance (``measure_cov`` / ``calc_errors``) with caller-supplied ``jk_patches``: the reference re-runs every loop K
+times without patch k (measure_jackknife.py:265-483, one process per patch); here the operator returns, in the SAME pass as
+the totals, the sums over pairs touching each patch, and realisation k = total - touch[k].  The files follow the reference's
+multiprocessing branch (its single-process branch, measure_jackknife.py:307-310, passes its arguments in the wrong order and
+cannot run).  Not built: assigning patches from ``num_jk`` alone (k-means on the sky via ``kmeans_radec``, measure_IA_base.py:744-803).
 """
 from __future__ import annotations
 
@@ -25,7 +26,7 @@ from .jackknife import JackknifeCombinationMixin
 
 
 class MeasureIALightcone(MeasureIABase, JackknifeCombinationMixin):
-	"""Drop-in for ``measureia.MeasureIALightcone`` (measure_IA.py:265-1058) without the jackknife covariance."""
+	"""Drop-in for ``measureia.MeasureIALightcone`` (measure_IA.py:265-1058); jackknife patches must be supplied (``jk_patches``)."""
 
 	def __init__(self, data, randoms_data, output_file_name, separation_limits=[0.1, 20.0], num_bins_r=8, num_bins_pi=20,
 				 pi_max=None, num_nodes=1):
@@ -92,6 +93,8 @@ class MeasureIALightcone(MeasureIABase, JackknifeCombinationMixin):
 		num_patches = 0
 		if patches is not None:
 			pp, ps = np.asarray(patches[0]), np.asarray(patches[1])
+			if masks is not None and len(pp) == len(masks["Redshift"]) and len(ps) == len(masks["Redshift_shape_sample"]):
+				pp, ps = pp[masks["Redshift"]], ps[masks["Redshift_shape_sample"]]  # labels of the full samples (measure_jackknife.py:351-355)
 			lo = int(min(pp.min(), ps.min())) if len(pp) and len(ps) else 0
 			num_patches = (int(max(pp.max(), ps.max())) - lo + 1) if len(pp) and len(ps) else 0
 			pos["patch"], shp["patch"] = (pp - lo).astype(np.int32), (ps - lo).astype(np.int32)
@@ -123,7 +126,7 @@ class MeasureIALightcone(MeasureIABase, JackknifeCombinationMixin):
 							   kernel_ms=ops.LAST_LC_TIMINGS_MS[0])
 		res = dict(count=cnt, DD=ddw, SpD=spd, ScD=scd)
 		if num_patches:
-			res.update(touch_count=t_cnt, touch_DD=t_w, touch_SpD=t_spd)
+			res.update(touch_count=t_cnt, touch_DD=t_w, touch_SpD=t_spd, patch_lo=lo, patches=(pp, ps))
 		self.last_result = res
 		return res
 
@@ -133,8 +136,48 @@ class MeasureIALightcone(MeasureIABase, JackknifeCombinationMixin):
 		b2 = self.pi_bins if geom == "rppi" else self.mu_r_bins
 		return sep, b2[:-1] + abs((b2[1:] - b2[:-1]) / 2.0)
 
-	def _measure_brute(self, geom, dataset_name, masks, return_output, print_num, over_h, cosmology, jk_group_name, rp_cut=None):
-		res = self._pair_sums(geom, True, masks, over_h, cosmology, rp_cut)
+	def _write_realisations(self, geom, res, dataset_name, shapes, data_suffix, sample_names):
+		"""Leave-one-patch-out realisations from the per-patch sums of the SAME operator call, in the layout of the reference's
+		multiprocessing branch (measure_jackknife.py:433-474): `xi_g_plus/<X>_jk<K>/<X>_<i>_SplusD`, `xi_gg/<X>_jk<K>/<X>_<i>_DD`
+		(or `<X>_<i><suffix>` for the pair counts), each with its bin centres; fills `self.num_samples[str(i)]` (:356-357)."""
+		pp, ps = res["patches"]
+		lo_p, hi_p = int(min(pp)), int(max(pp))  # group name and loop range follow the POSITION sample's labels (:337-338)
+		K = hi_p - lo_p + 1
+		sep, mid2 = self._centres(geom)
+		top = "w" if geom == "rppi" else "multipoles"
+		n1, n2 = ("_rp", "_pi") if geom == "rppi" else ("_r", "_mu_r")
+		writer = self.last_stats["rank"] == 0 and self.output_file_name is not None
+		f = open_file(self.output_file_name, "a") if writer else None
+		try:
+			for i in range(lo_p, hi_p + 1):
+				self.num_samples.setdefault(f"{i}", {})
+				self.num_samples[f"{i}"][sample_names[0]] = int(np.sum(ps != i))
+				self.num_samples[f"{i}"][sample_names[1]] = int(np.sum(pp != i))
+				if not writer:
+					continue
+				k = i - res["patch_lo"]
+				left = res["count"] - res["touch_count"][k]
+				DD = np.where(left > 0, res["DD"] - res["touch_DD"][k], 0.0)  # exactly 0 where no pair is left (no rounding residue)
+				DD[np.where(DD == 0)] = 1  # measure_w_lightcone.py:188
+				if shapes:
+					SpD = np.where(left > 0, res["SpD"] - res["touch_SpD"][k], 0.0)
+					g = create_group_hdf5(f, f"{self.snap_group}/{top}/xi_g_plus/{dataset_name}_jk{K}")
+					write_dataset_hdf5(g, f"{dataset_name}_{i}_SplusD", data=SpD)
+					write_dataset_hdf5(g, f"{dataset_name}_{i}{n1}", data=sep)
+					write_dataset_hdf5(g, f"{dataset_name}_{i}{n2}", data=mid2)
+				g = create_group_hdf5(f, f"{self.snap_group}/{top}/xi_gg/{dataset_name}_jk{K}")
+				write_dataset_hdf5(g, f"{dataset_name}_{i}" + ("_DD" if shapes else data_suffix), data=DD)
+				write_dataset_hdf5(g, f"{dataset_name}_{i}{n1}", data=sep)
+				write_dataset_hdf5(g, f"{dataset_name}_{i}{n2}", data=mid2)
+		finally:
+			if f is not None:
+				f.close()
+
+	def _measure_brute(self, geom, dataset_name, masks, return_output, print_num, over_h, cosmology, jk_group_name, rp_cut=None,
+					   jk=None):
+		res = self._pair_sums(geom, True, masks, over_h, cosmology, rp_cut, patches=None if jk is None else jk[:2])
+		if jk is not None:
+			self._write_realisations(geom, res, dataset_name, True, "_DD", jk[2])
 		if print_num and self.verbose:
 			print(f"There are {len(self.data['RA_shape_sample'])} galaxies in the shape sample and {len(self.data['RA'])} galaxies in the position sample.")
 		DD, SpD, ScD = res["DD"].copy(), res["SpD"], res["ScD"]
@@ -166,8 +209,10 @@ class MeasureIALightcone(MeasureIABase, JackknifeCombinationMixin):
 		return SpD, DD, sep, mid2
 
 	def _count_brute(self, geom, dataset_name, masks, return_output, print_num, over_h, cosmology, data_suffix, jk_group_name,
-					 rp_cut=None):
-		res = self._pair_sums(geom, False, masks, over_h, cosmology, rp_cut)
+					 rp_cut=None, jk=None):
+		res = self._pair_sums(geom, False, masks, over_h, cosmology, rp_cut, patches=None if jk is None else jk[:2])
+		if jk is not None:
+			self._write_realisations(geom, res, dataset_name, False, data_suffix, jk[2])
 		DD = res["DD"].copy()
 		DD[np.where(DD == 0)] = 1  # measure_w_lightcone.py:339
 		sep, mid2 = self._centres(geom)
@@ -187,25 +232,28 @@ class MeasureIALightcone(MeasureIABase, JackknifeCombinationMixin):
 		return DD, sep, mid2
 
 	def _measure_xi_rp_pi_lightcone_brute(self, dataset_name, masks=None, return_output=False, print_num=True, over_h=False,
-										  cosmology=None, jk_group_name=""):
-		"""measure_w_lightcone.py:45-214."""
-		return self._measure_brute("rppi", dataset_name, masks, return_output, print_num, over_h, cosmology, jk_group_name)
+										  cosmology=None, jk_group_name="", jk=None):
+		"""measure_w_lightcone.py:45-214.  `jk` (not in the reference): (patches_position, patches_shape, num_sample_names) --
+		also write the leave-one-patch-out realisations from the same operator call."""
+		return self._measure_brute("rppi", dataset_name, masks, return_output, print_num, over_h, cosmology, jk_group_name, jk=jk)
 
 	def _count_pairs_xi_rp_pi_lightcone_brute(self, dataset_name, masks=None, return_output=False, print_num=True, over_h=False,
-											  cosmology=None, data_suffix="_DD", jk_group_name=""):
+											  cosmology=None, data_suffix="_DD", jk_group_name="", jk=None):
 		"""measure_w_lightcone.py:216-343."""
-		return self._count_brute("rppi", dataset_name, masks, return_output, print_num, over_h, cosmology, data_suffix, jk_group_name)
+		return self._count_brute("rppi", dataset_name, masks, return_output, print_num, over_h, cosmology, data_suffix, jk_group_name,
+								 jk=jk)
 
 	def _measure_xi_r_mur_lightcone_brute(self, dataset_name, masks=None, return_output=False, print_num=True, over_h=True,
-										  cosmology=None, rp_cut=None, jk_group_name=""):
+										  cosmology=None, rp_cut=None, jk_group_name="", jk=None):
 		"""measure_m_lightcone.py:45-219."""
-		return self._measure_brute("rmu", dataset_name, masks, return_output, print_num, over_h, cosmology, jk_group_name, rp_cut)
+		return self._measure_brute("rmu", dataset_name, masks, return_output, print_num, over_h, cosmology, jk_group_name, rp_cut,
+								   jk=jk)
 
 	def _count_pairs_xi_r_mur_lightcone_brute(self, dataset_name, masks=None, return_output=False, print_num=True, over_h=False,
-											  cosmology=None, rp_cut=None, data_suffix="_DD", jk_group_name=""):
+											  cosmology=None, rp_cut=None, data_suffix="_DD", jk_group_name="", jk=None):
 		"""measure_m_lightcone.py:221-363."""
 		return self._count_brute("rmu", dataset_name, masks, return_output, print_num, over_h, cosmology, data_suffix, jk_group_name,
-								 rp_cut)
+								 rp_cut, jk=jk)
 
 	# ---- estimators (measure_IA_base.py:670-742) -----------------------------------------------------------------------------
 	def _obs_estimator(self, corr_type, IA_estimator, dataset_name, dataset_name_randoms, num_samples, jk_group_name="",
@@ -225,7 +273,8 @@ class MeasureIALightcone(MeasureIABase, JackknifeCombinationMixin):
 			group_gg = f[f"{self.snap_group}/{top}/xi_gg/{jk_group_name}"]
 			group_gg_r = f[f"{self.snap_group}/{top}/xi_gg/{jk_group_name_randoms}"]
 			DD = group_gg[f"{dataset_name}_DD"][:]
-			fD, fS = num_samples["D"] / num_samples["R_D"], num_samples["S"] / num_samples["R_S"]
+			fD = num_samples["D"] / num_samples["R_D"]
+			fS = num_samples["S"] / num_samples["R_S"] if (gg or IA_estimator == "galaxies") else None  # (not set for clusters / g+)
 			read_SR = lambda: (group_gg[f"{dataset_name}_SR"][:] if which == "gg" else group_gg_r[f"{dataset_name_randoms}_DD"][:])  # noqa: E731
 			with np.errstate(divide="ignore", invalid="ignore"):
 				if IA_estimator == "clusters":
@@ -255,6 +304,41 @@ class MeasureIALightcone(MeasureIABase, JackknifeCombinationMixin):
 		finally:
 			f.close()
 
+	def _measure_jackknife_covariance_lightcone(self, IA_estimator, corr_type, dataset_name, max_patch, min_patch=1,
+												randoms_suf="_randoms"):
+		"""Estimators and integrated statistics per realisation, then mean / std / covariance (measure_jackknife.py:172-263)."""
+		try:
+			kinds = {"both": ["_g_plus", "_gg"], "g+": ["_g_plus"], "gg": ["_gg"]}[corr_type[0]]
+		except KeyError:
+			raise KeyError("Unknown value for corr_type. Choose from [g+, gg, both]")
+		K = max_patch - min_patch + 1
+		covs, stds = [], []
+		for kind in kinds:
+			for b in range(min_patch, max_patch + 1):
+				self._obs_estimator(corr_type, IA_estimator, f"{dataset_name}_{b}", f"{dataset_name}{randoms_suf}_{b}",
+									self.num_samples[f"{b}"], jk_group_name=f"{dataset_name}_jk{K}",
+									jk_group_name_randoms=f"{dataset_name}{randoms_suf}_jk{K}")
+				if corr_type[1] == "w":
+					self._measure_w_g_i(corr_type=corr_type[0], dataset_name=f"{dataset_name}_{b}", jk_group_name=f"{dataset_name}_jk{K}")
+				else:
+					self._measure_multipoles(corr_type=corr_type[0], dataset_name=f"{dataset_name}_{b}",
+											 jk_group_name=f"{dataset_name}_jk{K}")
+			f = open_file(self.output_file_name, "a")
+			try:
+				grp = f[f"{self.snap_group}/{corr_type[1]}{kind}/{dataset_name}_jk{K}"]
+				reals = np.array([grp[f"{dataset_name}_{b}"][:] for b in range(min_patch, max_patch + 1)])
+				with np.errstate(invalid="ignore"):
+					mean, std, cov = self._jackknife_stats(reals)
+				out = create_group_hdf5(f, f"{self.snap_group}/{corr_type[1]}{kind}")
+				write_dataset_hdf5(out, f"{dataset_name}_mean_{K}", data=mean)
+				write_dataset_hdf5(out, f"{dataset_name}_jackknife_{K}", data=std)
+				write_dataset_hdf5(out, f"{dataset_name}_jackknife_cov_{K}", data=cov)
+			finally:
+				f.close()
+			covs.append(cov)
+			stds.append(std)
+		return covs, stds
+
 	# ---- public API -------------------------------------------------------------------------------------------------------------
 	def _prepare_randoms(self):
 		"""measure_IA.py:396-413: one random sample serves both roles; default unit weights."""
@@ -268,15 +352,24 @@ class MeasureIALightcone(MeasureIABase, JackknifeCombinationMixin):
 			r["weight_shape_sample"] = r["weight"] if one else np.ones(len(r["RA_shape_sample"]))
 		return one
 
-	def _measure(self, top, IA_estimator, dataset_name, corr_type, want_cov, masks, masks_randoms, cosmology, over_h, rp_cut):
+	def _measure(self, top, IA_estimator, dataset_name, corr_type, want_cov, masks, masks_randoms, cosmology, over_h, rp_cut,
+				 jk_patches=None, num_jk=None):
 		if IA_estimator not in ("clusters", "galaxies"):
 			raise KeyError("Unknown input for IA_estimator, choose from [clusters, galaxies].")
 		if corr_type not in ("both", "g+", "gg"):
 			raise KeyError("Unknown value for corr_type. Choose from [g+, gg, both]")
 		if want_cov:
-			raise NotImplementedError(
-				"measure_ia_b200: the jackknife covariance of the light-cone estimators is not built (pass measure_cov=False / "
-				"calc_errors=False); the operator's per-patch sums are available through _pair_sums(..., patches=(pos, shape))")
+			if jk_patches is None:
+				if num_jk is not None:
+					raise NotImplementedError(
+						"measure_ia_b200: assigning jackknife patches from num_jk needs kmeans_radec (measure_IA_base.py:744-803), "
+						"which is not built; pass jk_patches = {'position', 'shape', 'randoms' | 'randoms_position', 'randoms_shape'}")
+				raise ValueError("Set calc_errors to False, or provide either jk_patches or num_jk input.")
+			if corr_type == "gg":
+				# the reference's estimator opens the `<name>_randoms_jk<K>` group it only writes for g+ / both
+				# (measure_IA_base.py:703) and fails with this KeyError
+				raise KeyError(f"Unable to open object (object '{dataset_name}_randoms_jk' doesn't exist): the light-cone jackknife "
+							   "needs corr_type 'g+' or 'both'")
 		geom = "rppi" if top == "w" else "rmu"
 		kw = dict(over_h=over_h, cosmology=cosmology)
 		if geom == "rmu":
@@ -284,7 +377,10 @@ class MeasureIALightcone(MeasureIABase, JackknifeCombinationMixin):
 		measure = self._measure_xi_rp_pi_lightcone_brute if geom == "rppi" else self._measure_xi_r_mur_lightcone_brute
 		count = self._count_pairs_xi_rp_pi_lightcone_brute if geom == "rppi" else self._count_pairs_xi_r_mur_lightcone_brute
 		data = self.data  # restored at the end (measure_IA.py:392,687)
-		self._prepare_randoms()
+		one_random_sample = self._prepare_randoms()
+		if want_cov and one_random_sample and "randoms" in jk_patches:  # measure_IA.py:420-423
+			jk_patches["randoms_position"] = jk_patches["randoms"]
+			jk_patches["randoms_shape"] = jk_patches["randoms"]
 		self.data_dir = D = data
 		if "weight" not in D:
 			D["weight"] = np.ones(len(D["RA"]))
@@ -297,6 +393,9 @@ class MeasureIALightcone(MeasureIABase, JackknifeCombinationMixin):
 		n["R_D"] = len(R["RA"]) if masks_randoms is None else len(R["RA"][masks_randoms["RA"]])
 		n["R_S"] = len(R["RA_shape_sample"]) if masks_randoms is None else len(R["RA_shape_sample"][masks_randoms["RA_shape_sample"]])
 		self.num_samples = n
+		jk = (lambda a, b, names: None) if not want_cov else (lambda a, b, names: (jk_patches[a], jk_patches[b], names))
+		if want_cov:
+			self.num_samples = {}  # per patch from here on (measure_IA.py:551-554); `n` stays the totals' dictionary
 
 		def combo(position, shape, shapes):
 			"""The reference's temporary data dictionaries (measure_IA.py:460-552): position sample from `position`,
@@ -311,9 +410,9 @@ class MeasureIALightcone(MeasureIABase, JackknifeCombinationMixin):
 		try:
 			if corr_type in ("g+", "both"):
 				self.data = D  # S+D
-				measure(masks=masks, dataset_name=dataset_name, **kw)
+				measure(masks=masks, dataset_name=dataset_name, jk=jk("position", "shape", ["S", "D"]), **kw)
 				self.data = combo(R, D, True)  # S+R
-				measure(masks=masks, dataset_name=f"{dataset_name}_randoms", **kw)
+				measure(masks=masks, dataset_name=f"{dataset_name}_randoms", jk=jk("randoms_position", "shape", ["S", "R_D"]), **kw)
 			if corr_type == "gg":  # SD, SR (already there for 'both')
 				self.data = combo(D, D, False)
 				count(masks=masks, dataset_name=dataset_name, data_suffix="_DD", **kw)
@@ -321,26 +420,32 @@ class MeasureIALightcone(MeasureIABase, JackknifeCombinationMixin):
 				count(masks=masks, dataset_name=dataset_name, data_suffix="_SR", **kw)
 			if corr_type in ("gg", "both"):  # RD
 				self.data = combo(D, R, False)
-				count(masks=masks, dataset_name=dataset_name, data_suffix="_RD", **kw)
+				count(masks=masks, dataset_name=dataset_name, data_suffix="_RD", jk=jk("position", "randoms_shape", ["R_S", "D"]), **kw)
 			if IA_estimator == "galaxies" or corr_type in ("gg", "both"):  # RR
 				self.data = combo(R, R, False)
-				count(masks=masks, dataset_name=dataset_name, data_suffix="_RR", **kw)
+				count(masks=masks, dataset_name=dataset_name, data_suffix="_RR",
+					  jk=jk("randoms_position", "randoms_shape", ["R_S", "R_D"]), **kw)
 			if self.last_stats["rank"] == 0:
 				self._obs_estimator([corr_type, top], IA_estimator, dataset_name, f"{dataset_name}_randoms", n)
 				if top == "w":
 					self._measure_w_g_i(corr_type=corr_type, dataset_name=dataset_name, return_output=False)
 				else:
 					self._measure_multipoles(corr_type=corr_type, dataset_name=dataset_name, return_output=False)
+				if want_cov:
+					self._measure_jackknife_covariance_lightcone(IA_estimator, [corr_type, top], dataset_name,
+																 max_patch=int(max(jk_patches["shape"])),
+																 min_patch=int(min(jk_patches["shape"])), randoms_suf="_randoms")
 		finally:
 			self.data = data
 
 	def measure_xi_w(self, IA_estimator, dataset_name, corr_type, jk_patches=None, num_jk=None, measure_cov=True, masks=None,
 					 masks_randoms=None, cosmology=None, over_h=False):
 		"""xi_gg, xi_g+ and w_gg, w_g+ for light-cone data (measure_IA.py:336-688)."""
-		self._measure("w", IA_estimator, dataset_name, corr_type, measure_cov, masks, masks_randoms, cosmology, over_h, None)
+		self._measure("w", IA_estimator, dataset_name, corr_type, measure_cov, masks, masks_randoms, cosmology, over_h, None,
+					  jk_patches, num_jk)
 
 	def measure_xi_multipoles(self, IA_estimator, dataset_name, corr_type, jk_patches=None, num_jk=None, calc_errors=True,
 							  masks=None, masks_randoms=None, cosmology=None, over_h=False, rp_cut=None):
 		"""Multipoles for light-cone data (measure_IA.py:690-1058)."""
 		self._measure("multipoles", IA_estimator, dataset_name, corr_type, calc_errors, masks, masks_randoms, cosmology, over_h,
-					  rp_cut)
+					  rp_cut, jk_patches, num_jk)

@@ -33,6 +33,13 @@ CONFIGS = {
 									   dict(kind="multipoles", IA_estimator="clusters", corr_type="both", over_h=True, rp_cut=1.5)),
 	"lc_m_galaxies_gg": (dict(n=300, n_shape=300, n_rand=600, seed=17, weights=True),
 						 dict(kind="multipoles", IA_estimator="galaxies", corr_type="gg", over_h=False)),
+	# jackknife covariance with caller-supplied patches (RA stripes, labels 1..K); the reference needs num_nodes > 1 for it
+	"lc_w_galaxies_both_jk4": (dict(n=420, n_shape=330, n_rand=700, seed=18, weights=True, jk=4),
+							   dict(kind="w", IA_estimator="galaxies", corr_type="both", over_h=False)),
+	"lc_w_clusters_gplus_jk3_two_randoms": (dict(n=360, n_shape=300, n_rand=600, n_rand_shape=520, seed=19, weights=True, jk=3),
+											dict(kind="w", IA_estimator="clusters", corr_type="g+", over_h=False)),
+	"lc_m_clusters_both_overh_jk3": (dict(n=380, n_shape=300, n_rand=640, seed=20, weights=False, jk=3),
+									 dict(kind="multipoles", IA_estimator="clusters", corr_type="both", over_h=True)),
 }
 BINNING = dict(separation_limits=[0.5, 20.0], num_bins_r=5, num_bins_pi=6, pi_max=40.0)
 
@@ -65,6 +72,20 @@ def build_inputs(cat):
 	return data, randoms, masks
 
 
+def build_patches(cat, data, randoms):
+	"""Jackknife patches as RA stripes, labels 1..K (k-means labels of the reference come from kmeans_radec, absent here)."""
+	K = cat.get("jk")
+	if not K:
+		return None
+	lab = lambda ra: np.minimum((np.asarray(ra) - 10.0) / 4.0 * K, K - 1).astype(int) + 1  # noqa: E731
+	jk = {"position": lab(data["RA"]), "shape": lab(data["RA_shape_sample"])}
+	if "RA_shape_sample" in randoms and randoms["RA_shape_sample"] is not randoms["RA"]:
+		jk["randoms_position"], jk["randoms_shape"] = lab(randoms["RA"]), lab(randoms["RA_shape_sample"])
+	else:
+		jk["randoms"] = lab(randoms["RA"])
+	return jk
+
+
 def run_reference(cat, call):
 	import run_reference as rr
 	from measure_ia_b200 import h5lite
@@ -75,14 +96,15 @@ def run_reference(cat, call):
 	devnull, stdout = open(os.devnull, "w"), sys.stdout
 	sys.stdout = devnull
 	try:
+		jk = build_patches(cat, data, randoms)
 		obj = measureia.MeasureIALightcone(data, randoms, out, BINNING["separation_limits"], BINNING["num_bins_r"],
-										   BINNING["num_bins_pi"], BINNING["pi_max"], 1)
-		kw = dict(masks=masks, over_h=call["over_h"])
+										   BINNING["num_bins_pi"], BINNING["pi_max"], 2 if jk else 1)
+		kw = dict(masks=masks, over_h=call["over_h"], jk_patches=jk)
 		with np.errstate(all="ignore"):
 			if call["kind"] == "w":
-				obj.measure_xi_w(call["IA_estimator"], "All", call["corr_type"], measure_cov=False, **kw)
+				obj.measure_xi_w(call["IA_estimator"], "All", call["corr_type"], measure_cov=bool(jk), **kw)
 			else:
-				obj.measure_xi_multipoles(call["IA_estimator"], "All", call["corr_type"], calc_errors=False,
+				obj.measure_xi_multipoles(call["IA_estimator"], "All", call["corr_type"], calc_errors=bool(jk),
 										  rp_cut=call.get("rp_cut"), **kw)
 	finally:
 		sys.stdout = stdout

@@ -37,13 +37,17 @@ def oracle_lc_pair_sums():
 		shp, _ = pylightcone.sample(sel["RA_shape_sample"], sel["DEC_shape_sample"], sel["Redshift_shape_sample"],
 									sel["weight_shape_sample"], cosmology, over_h, sel.get("e1"), sel.get("e2"))
 		bins2 = self.pi_bins if geom == "rppi" else self.mu_r_bins
-		kw = {}
+		kw, extra = {}, {}
 		if patches is not None:
-			lo = int(min(np.min(patches[0]), np.min(patches[1])))
-			kw = dict(patches_pos=np.asarray(patches[0]) - lo, patches_shape=np.asarray(patches[1]) - lo,
-					  num_patches=int(max(np.max(patches[0]), np.max(patches[1]))) - lo + 1)
+			pp, ps = np.asarray(patches[0]), np.asarray(patches[1])
+			if masks is not None and len(pp) == len(masks["Redshift"]) and len(ps) == len(masks["Redshift_shape_sample"]):
+				pp, ps = pp[masks["Redshift"]], ps[masks["Redshift_shape_sample"]]
+			lo = int(min(np.min(pp), np.min(ps)))
+			kw = dict(patches_pos=pp - lo, patches_shape=ps - lo, num_patches=int(max(np.max(pp), np.max(ps))) - lo + 1)
+			extra = dict(patch_lo=lo, patches=(pp, ps))
 		r = pylightcone.pair_sums(geom, pos, shp, self.r_min, self.r_max, self.r_bins, bins2, self.num_bins_r, self.num_bins_pi,
 								  h=h, over_h=over_h, rp_cut=0.0 if rp_cut is None else rp_cut, shapes=shapes, **kw)
+		r.update(extra)
 		self.last_stats = dict(rank=0)
 		self.last_result = r
 		return r
@@ -53,13 +57,15 @@ def oracle_lc_pair_sums():
 def run_product(meta, out, monkeypatch=None):
 	import make_golden_lightcone as mg
 	data, randoms, masks = mg.build_inputs(meta["catalogue"])
+	jk = mg.build_patches(meta["catalogue"], data, randoms)
 	b, call = meta["binning"], meta["call"]
 	obj = MeasureIALightcone(data, randoms, out, b["separation_limits"], b["num_bins_r"], b["num_bins_pi"], b["pi_max"], 1)
 	with np.errstate(all="ignore"):
 		if call["kind"] == "w":
-			obj.measure_xi_w(call["IA_estimator"], "All", call["corr_type"], measure_cov=False, masks=masks, over_h=call["over_h"])
+			obj.measure_xi_w(call["IA_estimator"], "All", call["corr_type"], jk_patches=jk, measure_cov=bool(jk), masks=masks,
+							 over_h=call["over_h"])
 		else:
-			obj.measure_xi_multipoles(call["IA_estimator"], "All", call["corr_type"], calc_errors=False, masks=masks,
+			obj.measure_xi_multipoles(call["IA_estimator"], "All", call["corr_type"], jk_patches=jk, calc_errors=bool(jk), masks=masks,
 									  over_h=call["over_h"], rp_cut=call.get("rp_cut"))
 	return obj
 
@@ -114,10 +120,12 @@ def test_lightcone_error_behaviour(tmp_path):
 		obj.measure_xi_w("stars", "All", "both", measure_cov=False)
 	with pytest.raises(KeyError, match="corr_type"):
 		obj.measure_xi_w("galaxies", "All", "g++", measure_cov=False)
-	with pytest.raises(NotImplementedError, match="jackknife"):
+	with pytest.raises(NotImplementedError, match="kmeans_radec"):
 		obj.measure_xi_w("galaxies", "All", "both", num_jk=4)  # measure_cov defaults to True, as in the reference
-	with pytest.raises(NotImplementedError, match="jackknife"):
-		obj.measure_xi_multipoles("clusters", "All", "both", num_jk=4)
+	with pytest.raises(ValueError, match="jk_patches or num_jk"):
+		obj.measure_xi_multipoles("clusters", "All", "both")
+	with pytest.raises(KeyError, match="randoms_jk"):  # the reference's estimator fails the same way for a 'gg'-only jackknife
+		obj.measure_xi_w("galaxies", "All", "gg", jk_patches=mg.build_patches(dict(jk=3), data, randoms))
 	with pytest.raises(ValueError, match="pi_max and boxsize"):
 		MeasureIALightcone(data, randoms, None)
 	import torch
