@@ -145,9 +145,8 @@ __global__ void __launch_bounds__(LC_TP) k_lightcone(const LcDev P, const LcSamp
 													 int64_t p_end, int n_seg, LcOut O) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int nb = P.n_r * P.n_2;
-	double *t_ra = reinterpret_cast<double *>(smem_raw);
-	double *t_dec = t_ra + LC_TILE;
-	double *p_ra = t_dec + LC_TILE, *p_dec = p_ra + LC_TP, *p_chi = p_dec + LC_TP, *p_cd = p_chi + LC_TP, *p_w = p_cd + LC_TP;
+	double2 *t_sky = reinterpret_cast<double2 *>(smem_raw);  // {dec, ra} of the staged shape galaxies: one 16-byte load per pair
+	double *p_ra = reinterpret_cast<double *>(t_sky + LC_TILE), *p_dec = p_ra + LC_TP, *p_chi = p_dec + LC_TP, *p_cd = p_chi + LC_TP, *p_w = p_cd + LC_TP;
 	double *s_ddw = p_w + LC_TP, *s_sp = s_ddw + nb, *s_sc = s_sp + nb;
 	unsigned int *s_cnt = reinterpret_cast<unsigned int *>(s_sc + nb);
 	int *p_patch = reinterpret_cast<int *>(s_cnt + nb);
@@ -238,13 +237,13 @@ __global__ void __launch_bounds__(LC_TP) k_lightcone(const LcDev P, const LcSamp
 		const long long j0 = w0 + t * LC_TILE;
 		const int cnt = (int)((w1 - j0 < LC_TILE) ? (w1 - j0) : LC_TILE);
 		__syncthreads();  // the previous tile has been consumed
-		if ((int)threadIdx.x < cnt) {
-			t_ra[threadIdx.x] = S.ra[j0 + threadIdx.x];
-			t_dec[threadIdx.x] = S.dec[j0 + threadIdx.x];
-		}
+		if ((int)threadIdx.x < cnt) t_sky[threadIdx.x] = make_double2(S.dec[j0 + threadIdx.x], S.ra[j0 + threadIdx.x]);
 		__syncthreads();
+#pragma unroll 1
 		for (int k = 0; k < cnt; k++) {
-			const bool pass = active && !(fabs(t_dec[k] - dec_n) > lim_dec || fabs(t_ra[k] - ra_n) > lim_ra);
+			const double2 sk = t_sky[k];
+			// branch-free (a NaN coordinate fails both comparisons: the reference's range mask rejects such a pair too)
+			const bool pass = active & (fabs(sk.x - dec_n) <= lim_dec) & (fabs(sk.y - ra_n) <= lim_ra);
 			const unsigned m = __ballot_sync(0xffffffffu, pass);
 			if (!m) continue;
 			if (pass) {
