@@ -714,6 +714,9 @@ int mia_lightcone_paircount(const mia_lc_params *p, const mia_lc_sample *D, cons
 		const long long max_tiles = (S->n + LC_TILE - 1) / LC_TILE;
 		if (n_seg > max_tiles) n_seg = max_tiles;
 		if (n_seg > 1024) n_seg = 1024;
+		// a CTA counts its binned pairs per bin in 32 bits: at most 128 x 128 x (tiles per CTA) < 2^32
+		const long long min_seg = (max_tiles + 200000 - 1) / 200000;
+		if (n_seg < min_seg) n_seg = min_seg;
 		if (n_seg < 1) n_seg = 1;
 		const size_t smem = lightcone_smem_bytes(nb);
 		const dim3 grid(gx, (unsigned)n_seg);
