@@ -11,7 +11,10 @@ Jackknife covariance (``measure_cov`` / ``calc_errors``) with caller-supplied ``
 times without patch k (measure_jackknife.py:265-483, one process per patch); here the operator returns, in the SAME pass as
 the totals, the sums over pairs touching each patch, and realisation k = total - touch[k].  The files follow the reference's
 multiprocessing branch (its single-process branch, measure_jackknife.py:307-310, passes its arguments in the wrong order and
-cannot run).  Not built: assigning patches from ``num_jk`` alone (k-means on the sky via ``kmeans_radec``, measure_IA_base.py:744-803).
+cannot run).  ``num_jk`` without ``jk_patches``: the reference clusters the randoms on the sky with ``kmeans_radec``
+(measure_IA_base.py:744-803), which is not in this image; ``assign_jackknife_patches`` uses it when importable and otherwise a
+spherical k-means of its own (same role: centres from the position randoms, nearest centre for the other samples; the labels are
+a different -- equally arbitrary -- partition, since kmeans_radec starts from unseeded random centres).
 """
 from __future__ import annotations
 
@@ -339,6 +342,53 @@ class MeasureIALightcone(MeasureIABase, JackknifeCombinationMixin):
 			stds.append(std)
 		return covs, stds
 
+	# ---- jackknife patches on the sky (measure_IA_base.py:744-803) ---------------------------------------------------------------
+	@staticmethod
+	def _unit_vectors(ra, dec):
+		ra, dec = np.radians(np.asarray(ra, dtype=np.float64)), np.radians(np.asarray(dec, dtype=np.float64))
+		return np.stack([np.cos(dec) * np.cos(ra), np.cos(dec) * np.sin(ra), np.sin(dec)], axis=1)
+
+	@staticmethod
+	def _nearest_centre(x, centres, block=1 << 18):
+		out = np.empty(len(x), dtype=np.int64)
+		for i in range(0, len(x), block):
+			out[i:i + block] = np.argmax(x[i:i + block] @ centres.T, axis=1)  # largest cosine = smallest angle
+		return out
+
+	def assign_jackknife_patches(self, data, randoms_data, num_jk, maxiter=100, tol=1.0e-5, seed=0):
+		"""Patch labels 0..num_jk-1 for the four samples: k-means of the position randoms on the sphere, nearest centre for
+		the shape randoms and the data (the reference: ``kmeans_radec.kmeans_sample(..., maxiter=100, tol=1.0e-5)`` then
+		``find_nearest``).  Uses kmeans_radec when it is installed, else Lloyd iterations on unit vectors from `num_jk`
+		randoms drawn with ``default_rng(seed)`` (reproducible; kmeans_radec's own start is unseeded)."""
+		try:  # pragma: no cover - kmeans_radec is absent from the build image
+			from kmeans_radec import kmeans_sample
+			km = kmeans_sample(np.column_stack((randoms_data["RA"], randoms_data["DEC"])), num_jk, maxiter=maxiter, tol=tol)
+			near = lambda ra, dec: km.find_nearest(np.column_stack((ra, dec)))  # noqa: E731
+			first = km.labels
+		except ImportError:
+			x = self._unit_vectors(randoms_data["RA"], randoms_data["DEC"])
+			if num_jk < 1 or num_jk > len(x):
+				raise ValueError("num_jk must be between 1 and the number of randoms")
+			centres = x[np.random.default_rng(seed).choice(len(x), size=num_jk, replace=False)].copy()
+			for _ in range(maxiter):
+				lab = self._nearest_centre(x, centres)
+				new = np.zeros_like(centres)
+				np.add.at(new, lab, x)
+				norm = np.sqrt(np.sum(new ** 2, axis=1))
+				empty = norm == 0.0
+				new[~empty] /= norm[~empty, None]
+				new[empty] = centres[empty]  # a centre that lost all its points stays where it is
+				shift = float(np.max(np.arccos(np.clip(np.sum(new * centres, axis=1), -1.0, 1.0))))
+				centres = new
+				if shift < np.radians(tol):
+					break
+			near = lambda ra, dec: self._nearest_centre(self._unit_vectors(ra, dec), centres)  # noqa: E731
+			first = near(randoms_data["RA"], randoms_data["DEC"])
+		return {"randoms_position": first,
+				"randoms_shape": near(randoms_data["RA_shape_sample"], randoms_data["DEC_shape_sample"]),
+				"position": near(data["RA"], data["DEC"]),
+				"shape": near(data["RA_shape_sample"], data["DEC_shape_sample"])}
+
 	# ---- public API -------------------------------------------------------------------------------------------------------------
 	def _prepare_randoms(self):
 		"""measure_IA.py:396-413: one random sample serves both roles; default unit weights."""
@@ -359,11 +409,7 @@ class MeasureIALightcone(MeasureIABase, JackknifeCombinationMixin):
 		if corr_type not in ("both", "g+", "gg"):
 			raise KeyError("Unknown value for corr_type. Choose from [g+, gg, both]")
 		if want_cov:
-			if jk_patches is None:
-				if num_jk is not None:
-					raise NotImplementedError(
-						"measure_ia_b200: assigning jackknife patches from num_jk needs kmeans_radec (measure_IA_base.py:744-803), "
-						"which is not built; pass jk_patches = {'position', 'shape', 'randoms' | 'randoms_position', 'randoms_shape'}")
+			if jk_patches is None and num_jk is None:
 				raise ValueError("Set calc_errors to False, or provide either jk_patches or num_jk input.")
 			if corr_type == "gg":
 				# the reference's estimator opens the `<name>_randoms_jk<K>` group it only writes for g+ / both
@@ -378,6 +424,8 @@ class MeasureIALightcone(MeasureIABase, JackknifeCombinationMixin):
 		count = self._count_pairs_xi_rp_pi_lightcone_brute if geom == "rppi" else self._count_pairs_xi_r_mur_lightcone_brute
 		data = self.data  # restored at the end (measure_IA.py:392,687)
 		one_random_sample = self._prepare_randoms()
+		if want_cov and jk_patches is None:  # measure_IA.py:415-418
+			jk_patches = self.assign_jackknife_patches(data, self.randoms_data, num_jk)
 		if want_cov and one_random_sample and "randoms" in jk_patches:  # measure_IA.py:420-423
 			jk_patches["randoms_position"] = jk_patches["randoms"]
 			jk_patches["randoms_shape"] = jk_patches["randoms"]

@@ -120,9 +120,7 @@ def test_lightcone_error_behaviour(tmp_path):
 		obj.measure_xi_w("stars", "All", "both", measure_cov=False)
 	with pytest.raises(KeyError, match="corr_type"):
 		obj.measure_xi_w("galaxies", "All", "g++", measure_cov=False)
-	with pytest.raises(NotImplementedError, match="kmeans_radec"):
-		obj.measure_xi_w("galaxies", "All", "both", num_jk=4)  # measure_cov defaults to True, as in the reference
-	with pytest.raises(ValueError, match="jk_patches or num_jk"):
+	with pytest.raises(ValueError, match="jk_patches or num_jk"):  # measure_cov / calc_errors default to True, as in the reference
 		obj.measure_xi_multipoles("clusters", "All", "both")
 	with pytest.raises(KeyError, match="randoms_jk"):  # the reference's estimator fails the same way for a 'gg'-only jackknife
 		obj.measure_xi_w("galaxies", "All", "gg", jk_patches=mg.build_patches(dict(jk=3), data, randoms))
@@ -147,3 +145,33 @@ def test_flat_lcdm_distance_against_direct_quadrature():
 	assert np.allclose(chi, want, rtol=1e-12, atol=0) and chi[0] == 0.0
 	assert abs(chi[2] - 1202.3) < 0.5  # 1.20 Gpc at z = 0.3 for Om = 0.27, h = 0.7
 	assert np.array_equal(cosmo.comoving_radial_distance(lambda a: 3000.0 * (1 / a - 1), 1 / (1 + z)), 3000.0 * (1 / (1 / (1 + z)) - 1))
+
+
+def test_jackknife_patches_from_num_jk(tmp_path, monkeypatch):
+	"""`num_jk` without `jk_patches` (measure_IA.py:415-418): patches from a spherical k-means of the position randoms
+	(kmeans_radec's role, measure_IA_base.py:744-803) -- every sample labelled with its nearest centre, all labels used,
+	reproducible; then the whole jackknife pipeline on those patches."""
+	import make_golden_lightcone as mg
+	data, randoms, _ = mg.build_inputs(dict(n=260, n_shape=220, n_rand=500, seed=33, weights=True))
+	obj = MeasureIALightcone(data, randoms, str(tmp_path / "k.hdf5"), [0.5, 20.0], 5, 6, 40.0)
+	obj._prepare_randoms()
+	jk = obj.assign_jackknife_patches(data, randoms, 4)
+	assert set(jk) == {"position", "shape", "randoms_position", "randoms_shape"}
+	assert len(jk["position"]) == 260 and len(jk["shape"]) == 220 and len(jk["randoms_position"]) == 500
+	assert set(np.unique(jk["randoms_position"])) == {0, 1, 2, 3}
+	again = obj.assign_jackknife_patches(data, randoms, 4)
+	assert all(np.array_equal(jk[k], again[k]) for k in jk)
+	# nearest-centre property: a galaxy's patch is the patch of the centre (mean direction of its randoms) closest to it
+	x = obj._unit_vectors(randoms["RA"], randoms["DEC"])
+	centres = np.stack([x[jk["randoms_position"] == k].mean(axis=0) for k in range(4)])
+	centres /= np.linalg.norm(centres, axis=1)[:, None]
+	assert np.mean(obj._nearest_centre(obj._unit_vectors(data["RA"], data["DEC"]), centres) == jk["position"]) > 0.97
+	# patches are compact on the sky: mean angular distance to the own centre well below the patch-to-patch distance
+	own = np.degrees(np.arccos(np.clip(np.sum(x * centres[jk["randoms_position"]], axis=1), -1, 1))).mean()
+	assert own < 1.5, own  # a 4 x 4 degree field in 4 patches
+	monkeypatch.setattr(MeasureIALightcone, "_pair_sums", oracle_lc_pair_sums())
+	with np.errstate(all="ignore"):
+		obj.measure_xi_w("galaxies", "All", "both", num_jk=4)
+	got = read_all(str(tmp_path / "k.hdf5"))
+	assert got["w_g_plus/All_jackknife_cov_4"].shape == (5, 5) and "w/xi_gg/All_jk4/All_3_RR" in got
+	assert sorted(obj.num_samples) == ["0", "1", "2", "3"] and obj.num_samples["0"]["D"] == int(np.sum(jk["position"] != 0))
