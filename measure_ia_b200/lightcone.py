@@ -106,9 +106,10 @@ class MeasureIALightcone(MeasureIABase, JackknifeCombinationMixin):
 			if any(len(v) != n for v in dd.values()):
 				raise ValueError(f"light-cone {k} sample: arrays of different lengths")
 
-		def upload(d):  # sorted by chi: the operator's one requirement (it culls on the chi window)
-			order = np.argsort(d["chi"], kind="stable")
-			return {k: torch.from_numpy(np.ascontiguousarray(v[order])).to(dev) for k, v in d.items()}
+		def upload(d):  # sorted by chi -- the operator's one requirement (it culls on the chi window) -- on the device
+			t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in d.items()}
+			order = torch.argsort(t["chi"], stable=True)
+			return {k: v[order].contiguous() for k, v in t.items()}
 
 		r2_thr, thr2, rp2_cut, clean = self._thresholds_for("rppi" if geom == "rppi" else "rmu", rp_cut)
 		rank, world = 0, 1
