@@ -709,6 +709,8 @@ class MeasureIABox(MeasureIABase, JackknifeCombinationMixin):
 		statistics : any of ``"w"`` ((r_p, Pi) grid, ``measure_xi_w``) and ``"multipoles"`` ((r, mu_r), ``measure_xi_multipoles``).
 		"""
 		dataset_names = list(dataset_names)
+		if not dataset_names:
+			raise ValueError("measure_xi_projections needs at least one dataset name")
 		if projections is None:
 			projections = [{"LOS": i} for i in range(len(dataset_names))]
 		projections = [dict(p) for p in projections]

@@ -27,13 +27,13 @@ def _partials(rank, n_r=5, n_2=4, num_jk=8, tasks_skew=0):
 	return dd_count, f(n_r, n_2), f(n_r, n_2), f(n_r, n_2), jk_count, f(num_jk, n_r, n_2), f(num_jk, n_r, n_2), stats
 
 
-def _worker(rank, world, port, out_dir, tasks_skew=0):
+def _worker(rank, world, port, out_dir, tasks_skew=0, num_jk=8):
 	os.environ["MASTER_ADDR"] = "127.0.0.1"
 	os.environ["MASTER_PORT"] = str(port)
 	dist.init_process_group("gloo", rank=rank, world_size=world)
 	try:
 		from measure_ia_b200.box import combine_across_ranks
-		res = combine_across_ranks(*_partials(rank, tasks_skew=tasks_skew))
+		res = combine_across_ranks(*_partials(rank, tasks_skew=tasks_skew, num_jk=num_jk))
 		torch.save([t.clone() for t in res], os.path.join(out_dir, f"rank{rank}.pt"))
 	finally:
 		dist.destroy_process_group()
@@ -53,6 +53,19 @@ def test_combine_across_two_ranks(tmp_path):
 	for r in range(world):
 		s = got[r][7]
 		assert s[0] == 21 and s[1] == 41 and s[6] == 5 and s[4] == 2 and s[5] == 77
+
+
+def test_combine_without_jackknife_rows(tmp_path):
+	"""The light-cone operator without patches (and the box without jackknife) hands over EMPTY [0, n_r, n_2] jackknife arrays:
+	the packed exchange must carry them through (position-sample shards of MeasureIALightcone._pair_sums)."""
+	world = 2
+	mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), 0, 0), nprocs=world, join=True)
+	got = [torch.load(tmp_path / f"rank{r}.pt") for r in range(world)]
+	parts = [_partials(r, num_jk=0) for r in range(world)]
+	for r in range(world):
+		assert len(got[r]) == 8 and got[r][4].shape == (0, 5, 4) and got[r][5].shape == (0, 5, 4)
+		for i in range(4):
+			assert torch.equal(got[r][i], parts[0][i] + parts[1][i])
 
 
 def test_ranks_with_different_task_tables_fail_loudly(tmp_path):
