@@ -29,18 +29,32 @@ _GL = {n: np.polynomial.legendre.leggauss(n) for n in (16, 32, 64)}
 def flat_lcdm_distance(omega_m, h, a):
 	"""chi(a) = c / H0 int_0^z dz' / sqrt(Om (1 + z')^3 + 1 - Om), Gauss-Legendre per object on [0, z].  The integrand is
 	smooth: 16 nodes are converged to rounding (2e-16 against adaptive quadrature) up to z = 1, 32 up to z = 10; beyond
-	that 64 nodes (2e-15 at z = 10, degrading slowly: a light-cone catalogue does not go there)."""
-	a = np.asarray(a, dtype=np.float64)
+	that 64 nodes (2e-15 at z = 10, degrading slowly: a light-cone catalogue does not go there).
+
+	`a`: a numpy array, or a float64 torch tensor (any device) -- the same sequence of individually rounded IEEE operations
+	either way, so the device version returns the host version's bits."""
+	is_torch = type(a).__module__.startswith("torch")
+	if is_torch:
+		import torch
+		sqrt, zeros_like = torch.sqrt, torch.zeros_like
+	else:
+		a = np.asarray(a, dtype=np.float64)
+		sqrt, zeros_like = np.sqrt, np.zeros_like
 	z = 1.0 / a - 1.0
-	zmax = float(np.max(z)) if z.size else 0.0
+	zmax = float(z.max()) if z.shape[0] else 0.0
 	xs, ws = _GL[16 if zmax <= 1.0 else (32 if zmax <= 10.0 else 64)]
 	half = 0.5 * z
-	acc = np.zeros_like(z)
+	acc = zeros_like(z)
 	lam = 1.0 - omega_m
 	for x, w in zip(xs, ws):
-		t = half * (x + 1.0) + 1.0
-		acc += w / np.sqrt(omega_m * (t * t * t) + lam)
+		t = half * (float(x) + 1.0) + 1.0
+		acc += float(w) * (1.0 / sqrt(omega_m * (t * t * t) + lam))  # (reciprocal, then product: torch evaluates scalar / tensor that way)
 	return C_KM_S / (100.0 * h) * half * acc
+
+
+def is_builtin_flat_lcdm(cosmology):
+	"""True when `comoving_radial_distance` would use the flat-LCDM integral above (so it may as well run on the device)."""
+	return isinstance(cosmology, Cosmology)
 
 
 def comoving_radial_distance(cosmology, a):

@@ -67,8 +67,8 @@ class MeasureIALightcone(MeasureIABase, JackknifeCombinationMixin):
 		return out
 
 	def _pair_sums(self, geom, shapes, masks, over_h, cosmology, rp_cut=None, patches=None):
-		"""Per-galaxy preparation on the host with the reference's numpy expressions (distances, cos(dec), shape angles:
-		O(N)), then ONE operator call for the O(N_p N_s) loop.  Returns dict(count, DD, SpD, ScD[, touch_*])."""
+		"""Per-galaxy preparation (distances, cos(dec), shape angles: O(N)), then ONE operator call for the O(N_p N_s) loop.
+		Returns dict(count, DD, SpD, ScD[, touch_*])."""
 		import torch
 
 		from . import ops
@@ -79,20 +79,29 @@ class MeasureIALightcone(MeasureIABase, JackknifeCombinationMixin):
 			cosmology = cosmo.Cosmology(Omega_c=0.225, Omega_b=0.045, sigma8=0.8, h=0.7, n_s=1.0)
 		h = cosmology["h"]
 		f = lambda a: np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
-		chi_p = f(cosmo.comoving_radial_distance(cosmology, 1 / (1 + f(sel["Redshift"]))))
-		chi_s = f(cosmo.comoving_radial_distance(cosmology, 1 / (1 + f(sel["Redshift_shape_sample"]))))
+		up = lambda a: torch.from_numpy(f(a)).to(dev)  # noqa: E731
+		# cos(dec) decides which bin a pair falls in and numpy's cos differs from CUDA's in the last bit: it stays numpy's.
+		# Everything else per galaxy is +, -, *, /, sqrt (IEEE-exact on the device: the same bits as numpy) or only enters the
+		# sums (shape angles), so it runs on the device in fp64 once the raw columns are uploaded.
+		pos = dict(ra=up(sel["RA"]), dec=up(sel["DEC"]), cosdec=up(np.cos(f(sel["DEC"]) / 180 * np.pi)), weight=up(sel["weight"]))
+		shp = dict(ra=up(sel["RA_shape_sample"]), dec=up(sel["DEC_shape_sample"]), weight=up(sel["weight_shape_sample"]))
+		if cosmo.is_builtin_flat_lcdm(cosmology):
+			om = cosmology["Omega_c"] + cosmology["Omega_b"]
+			pos["chi"] = cosmo.flat_lcdm_distance(om, h, 1 / (1 + up(sel["Redshift"])))
+			shp["chi"] = cosmo.flat_lcdm_distance(om, h, 1 / (1 + up(sel["Redshift_shape_sample"])))
+		else:  # pyccl, or a caller-supplied chi(a): on the host
+			pos["chi"] = up(cosmo.comoving_radial_distance(cosmology, 1 / (1 + f(sel["Redshift"]))))
+			shp["chi"] = up(cosmo.comoving_radial_distance(cosmology, 1 / (1 + f(sel["Redshift_shape_sample"]))))
 		if over_h:  # :131-133
-			chi_p, chi_s = chi_p * h, chi_s * h
-		pos = dict(ra=f(sel["RA"]), dec=f(sel["DEC"]), chi=chi_p, cosdec=np.cos(f(sel["DEC"]) / 180 * np.pi), weight=f(sel["weight"]))
-		shp = dict(ra=f(sel["RA_shape_sample"]), dec=f(sel["DEC_shape_sample"]), chi=chi_s, weight=f(sel["weight_shape_sample"]))
-		if shapes:  # :135-140; e cos 2phi_axis and e sin 2phi_axis are what the device needs
-			e1, e2 = f(sel["e1"]), f(sel["e2"])
-			theta = 1. / 2 * np.arctan2(e2, e1)
-			axis = np.array([np.cos(theta), np.sin(theta)])
-			axis = axis / np.sqrt(np.sum(axis ** 2, axis=0))
-			e = np.sqrt(e1 ** 2 + e2 ** 2)
-			phi_axis = np.arctan2(axis[1], axis[0])
-			shp["e1"], shp["e2"] = e * np.cos(2 * phi_axis), e * np.sin(2 * phi_axis)
+			pos["chi"], shp["chi"] = pos["chi"] * h, shp["chi"] * h
+		if shapes:  # :135-140; e cos 2phi_axis and e sin 2phi_axis are what the operator needs
+			e1, e2 = up(sel["e1"]), up(sel["e2"])
+			theta = 1. / 2 * torch.atan2(e2, e1)
+			a0, a1 = torch.cos(theta), torch.sin(theta)
+			norm = torch.sqrt(a0 ** 2 + a1 ** 2)
+			phi_axis = torch.atan2(a1 / norm, a0 / norm)
+			e = torch.sqrt(e1 ** 2 + e2 ** 2)
+			shp["e1"], shp["e2"] = e * torch.cos(2 * phi_axis), e * torch.sin(2 * phi_axis)
 		num_patches = 0
 		if patches is not None:
 			pp, ps = np.asarray(patches[0]), np.asarray(patches[1])
@@ -100,16 +109,15 @@ class MeasureIALightcone(MeasureIABase, JackknifeCombinationMixin):
 				pp, ps = pp[masks["Redshift"]], ps[masks["Redshift_shape_sample"]]  # labels of the full samples (measure_jackknife.py:351-355)
 			lo = int(min(pp.min(), ps.min())) if len(pp) and len(ps) else 0
 			num_patches = (int(max(pp.max(), ps.max())) - lo + 1) if len(pp) and len(ps) else 0
-			pos["patch"], shp["patch"] = (pp - lo).astype(np.int32), (ps - lo).astype(np.int32)
-		for k, n in (("position", len(pos["ra"])), ("shape", len(shp["ra"]))):
-			dd = pos if k == "position" else shp
-			if any(len(v) != n for v in dd.values()):
+			pos["patch"] = torch.from_numpy(np.ascontiguousarray((pp - lo).astype(np.int32))).to(dev)
+			shp["patch"] = torch.from_numpy(np.ascontiguousarray((ps - lo).astype(np.int32))).to(dev)
+		for k, dd in (("position", pos), ("shape", shp)):
+			if any(v.shape[0] != dd["ra"].shape[0] for v in dd.values()):
 				raise ValueError(f"light-cone {k} sample: arrays of different lengths")
 
-		def upload(d):  # sorted by chi -- the operator's one requirement (it culls on the chi window) -- on the device
-			t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in d.items()}
-			order = torch.argsort(t["chi"], stable=True)
-			return {k: v[order].contiguous() for k, v in t.items()}
+		def upload(d):  # sorted by chi -- the operator's one requirement (it culls on the chi window)
+			order = torch.argsort(d["chi"], stable=True)
+			return {k: v[order].contiguous() for k, v in d.items()}
 
 		r2_thr, thr2, rp2_cut, clean = self._thresholds_for("rppi" if geom == "rppi" else "rmu", rp_cut)
 		rank, world = 0, 1

@@ -35,6 +35,19 @@ def test_reference_lightcone_fixture(torch_cuda, tmp_path, name):
 	compare_with_fixture(_read_all(out), want, f"{name}: ", not meta["catalogue"].get("weights"))
 
 
+def test_device_distances_equal_numpy_bit_for_bit(torch_cuda):
+	"""The distance integral runs on the device (lightcone._pair_sums): +, *, /, sqrt in the same order as the numpy version the
+	reference fixtures were generated with -- the bits must agree, or pairs next to a bin edge could move."""
+	from measure_ia_b200 import cosmo
+	c = cosmo.Cosmology()
+	om = c["Omega_c"] + c["Omega_b"]
+	for zmax in (0.4, 3.0, 12.0):  # 16 / 32 / 64 nodes
+		z = np.random.default_rng(7).uniform(0.0, zmax, 200_000)
+		a = 1 / (1 + z)
+		dev = cosmo.flat_lcdm_distance(om, c["h"], 1 / (1 + torch_cuda.from_numpy(z).cuda())).cpu().numpy()
+		assert np.array_equal(dev, cosmo.comoving_radial_distance(c, a)), zmax
+
+
 def _catalogue(n, ns, seed, K=6):
 	rng = np.random.default_rng(seed)
 	d = {"RA": rng.uniform(10.0, 16.0, n), "DEC": rng.uniform(-3.0, 3.0, n), "Redshift": rng.uniform(0.10, 0.16, n),

@@ -145,6 +145,12 @@ def test_flat_lcdm_distance_against_direct_quadrature():
 	assert np.allclose(chi, want, rtol=1e-12, atol=0) and chi[0] == 0.0
 	assert abs(chi[2] - 1202.3) < 0.5  # 1.20 Gpc at z = 0.3 for Om = 0.27, h = 0.7
 	assert np.array_equal(cosmo.comoving_radial_distance(lambda a: 3000.0 * (1 / a - 1), 1 / (1 + z)), 3000.0 * (1 / (1 / (1 + z)) - 1))
+	# the same function on torch tensors (the product evaluates it on the device, where sqrt and division are IEEE-exact and the
+	# result equals numpy's bit for bit: tests/test_gpu_lightcone.py; torch's CPU sqrt is not correctly rounded, hence 4 ulp here)
+	import torch
+	zz = np.random.default_rng(1).uniform(0.01, 2.5, 5000)
+	t = cosmo.flat_lcdm_distance(om, c["h"], torch.from_numpy(1 / (1 + zz))).numpy()
+	assert np.allclose(t, cosmo.comoving_radial_distance(c, 1 / (1 + zz)), rtol=1e-15, atol=0)
 
 
 def test_jackknife_patches_from_num_jk(tmp_path, monkeypatch):
