@@ -11,7 +11,9 @@ e2e    = the same count divided by the wall time of the public API call (Measure
 The default (headline) workload is BASELINE.json configs[1]: 1e6 galaxies, L = 205, r_p in [0.1, 20], 10 x 8 bins,
 wgg + wg+ with 27 jackknife regions (2.99e10 pairs per step).  The same JSON line carries, under "secondary", short runs
 of configs[2] (multipoles, every N), configs[3] (1e7 galaxies, N = 8 only: the north-star target) and the
-constructor-default 8 x 20 bins, and under "parity_check" a comparison of the timed kernel against the reference-exact
+constructor-default 8 x 20 bins, configs[4] through the public API (cfg5: cross-correlation with weights and masks, three lines
+of sight, combined covariance; separate calls and the batched measure_xi_projections) and the light-cone brute loop (SURVEY.md
+8(f)-4: raw pairs per second through MeasureIALightcone, numpy-oracle CPU leg), and under "parity_check" a comparison of the timed kernel against the reference-exact
 general kernel on the full workload plus (N = 1) against the CPU oracle on the cpu_baseline sample.
 """
 import argparse
@@ -374,6 +376,7 @@ def run_lightcone(dev, rank, world, barrier, peak, cpu_leg):
 	binned = int(res["count"].sum())
 	rec = {"value": binned / wall, "unit": "pairs/s", "wall_s": wall, "pair_kernel_ms_rank0": kernel_ms, "pairs": binned,
 		   "separations_computed": st["tested"], "raw_pairs": n * n, "raw_pairs_per_s": n * n / wall,
+		   "split_s": {"t_prep": st.get("t_prep"), "t_device": st.get("t_device")},
 		   "config": {"n_position": n, "n_shape": n, "sky": "30 x 30 deg, 0.1 < z < 0.4", "bins": [10, 8], "pi_max": 60.0,
 					  "api": "MeasureIALightcone._measure_xi_rp_pi_lightcone_brute(host numpy dict, return_output=True)"}}
 	if peak:
