@@ -66,3 +66,22 @@ def test_sky_prefilter_is_conservative():
 			px, py = _exact_offsets(ra_s2, dec_s2, ra_n, dec_n, chi_n, scale)
 			dropped = np.abs(ra_s2 - ra_n) > lim_ra
 			assert np.all((px ** 2 + py ** 2)[dropped] >= r_max2)
+
+
+def test_chi_window_is_a_superset():
+	"""The per-CTA window [chi(first) + win_lo - slack, chi(last) + win_hi + slack] (mia_lightcone.cuh) holds every shape galaxy whose
+	exactly rounded Pi = chi_s - chi_n passes the reference's range mask for some position galaxy of the block."""
+	rng = np.random.default_rng(4)
+	lo_thr, hi_thr = -60.0, 60.0
+	for _ in range(300):
+		chi_p = np.sort(rng.uniform(100.0, 3000.0) + rng.uniform(0, 5.0, 128))
+		c0, c1 = chi_p[0], chi_p[-1]
+		lo = c0 + lo_thr - 1e-9 * (abs(c0) + abs(lo_thr)) - 1e-300
+		hi = c1 + hi_thr + 1e-9 * (abs(c1) + abs(hi_thr)) + 1e-300
+		# shape galaxies within a few ulp of the window's ends, as seen from the first / last position galaxy
+		eps = np.arange(-8, 9)
+		chi_s = np.concatenate([np.nextafter(c0 + lo_thr, np.inf) + eps * np.spacing(c0), np.nextafter(c1 + hi_thr, -np.inf) + eps * np.spacing(c1)])
+		pi = chi_s[None, :] - chi_p[:, None]
+		binned_by_some = np.any((pi >= lo_thr) & (pi < hi_thr), axis=0)
+		inside = (chi_s >= lo) & (chi_s <= hi)
+		assert np.all(inside[binned_by_some])
